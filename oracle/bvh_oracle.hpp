@@ -1,0 +1,653 @@
+// ============================================================================
+// oracle/bvh_oracle.hpp -- TEST INFRASTRUCTURE ONLY. NOT PART OF THE PRODUCT.
+//
+// CPU restatement (C++17, host only) of the reference crate's hot path
+// (svenstaro/bvh 0.12.0): SAH-binned Bvh::build, Bvh::flatten, and ray
+// traversal (recursive, flat, iterator), plus the reference's deterministic
+// test fixtures.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may build, load or call this code; the
+// product path (bvh_b200/) never links or falls back to it.
+//
+// PARITY STATUS: the reference is Rust and cannot be compiled in this image
+// (no rustc/cargo, nalgebra/num-traits not vendored).  The restatement is
+// pinned against every golden / known-answer test the reference holds for
+// this path (tests/test_oracle_goldens.py) and against an
+// independent numpy restatement (tests/pyref.py).  Exact node arrays for
+// non-trivial scenes are NOT published by the reference, so beyond those
+// goldens "parity" means GPU == this oracle, bit for bit.
+//
+// Arithmetic rules: everything in T, round to nearest,
+// NO fused multiply-add (compile with -ffp-contract=off, never -ffast-math).
+// All file:line citations are relative to /root/reference/.
+// ============================================================================
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cmath>
+#include <limits>
+#include <vector>
+#include <array>
+#include <string>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <algorithm>
+
+namespace orc {
+
+static constexpr uint32_t U32_MAX = 0xFFFFFFFFu;
+
+// ----------------------------------------------------------------------------
+// POD mirrors (host layout shared with the tests' numpy dtypes).
+// ----------------------------------------------------------------------------
+template <class T> struct Aabb3 {       // src/aabb/aabb_impl.rs:10-16
+    T min[3];
+    T max[3];
+};
+template <class T> struct Ray3 {        // src/ray/ray_impl.rs:17-29
+    T origin[3];
+    T direction[3];
+    T inv_direction[3];
+};
+// BvhNode enum flattened to a POD (src/bvh/bvh_node.rs:21-47).
+//   Leaf : child_l == U32_MAX, shape = shape_index, child_r = U32_MAX, AABBs = empty
+//   Node : child_l/child_r indices, shape = number of shapes below the node
+//          (extra information, not in the reference enum), AABBs of children.
+template <class T> struct Node {
+    uint32_t parent;
+    uint32_t child_l;
+    uint32_t child_r;
+    uint32_t shape;
+    Aabb3<T> l_aabb;
+    Aabb3<T> r_aabb;
+    bool is_leaf() const { return child_l == U32_MAX; }
+};
+template <class T> struct FlatNode {    // src/flat_bvh.rs:17-46
+    Aabb3<T> aabb;
+    uint32_t entry_index;
+    uint32_t exit_index;
+    uint32_t shape_index;
+};
+
+// ----------------------------------------------------------------------------
+// L0 geometry.
+// ----------------------------------------------------------------------------
+// simba simd_min/simd_max for primitive floats [3p nalgebra ^0.34 / simba]:
+//   simd_min(a,b) = if a <= b {a} else {b};  simd_max(a,b) = if a >= b {a} else {b}
+template <class T> inline T smin(T a, T b) { return a <= b ? a : b; }
+template <class T> inline T smax(T a, T b) { return a >= b ? a : b; }
+// src/utils.rs:29,52
+template <class T> inline T fast_min(T x, T y) { return x < y ? x : y; }
+template <class T> inline T fast_max(T x, T y) { return x > y ? x : y; }
+
+template <class T> inline Aabb3<T> aabb_empty() {   // src/aabb/aabb_impl.rs:119-124
+    const T inf = std::numeric_limits<T>::infinity();
+    return Aabb3<T>{{inf, inf, inf}, {-inf, -inf, -inf}};
+}
+template <class T> inline Aabb3<T> aabb_join(const Aabb3<T>& a, const Aabb3<T>& b) {  // :303-308
+    Aabb3<T> r;
+    for (int k = 0; k < 3; ++k) { r.min[k] = smin(a.min[k], b.min[k]); r.max[k] = smax(a.max[k], b.max[k]); }
+    return r;
+}
+template <class T> inline Aabb3<T> aabb_grow(const Aabb3<T>& a, const T p[3]) {      // :375-380
+    Aabb3<T> r;
+    for (int k = 0; k < 3; ++k) { r.min[k] = smin(a.min[k], p[k]); r.max[k] = smax(a.max[k], p[k]); }
+    return r;
+}
+template <class T> inline void aabb_center(const Aabb3<T>& a, T c[3]) {              // :501-504
+    for (int k = 0; k < 3; ++k) c[k] = a.min[k] * T(0.5) + a.max[k] * T(0.5);
+}
+template <class T> inline T aabb_surface_area(const Aabb3<T>& a) {                   // :459-461, :551-554
+    const T sx = a.max[0] - a.min[0], sy = a.max[1] - a.min[1], sz = a.max[2] - a.min[2];
+    return T(2) * ((sx * sx + sy * sy) + sz * sz);      // [3p] nalgebra dot for R=3: a + b + c
+}
+template <class T> inline int aabb_largest_axis(const Aabb3<T>& a) {                 // :594-596, [3p] imax
+    T best = a.max[0] - a.min[0];
+    int axis = 0;
+    for (int k = 1; k < 3; ++k) { const T s = a.max[k] - a.min[k]; if (s > best) { best = s; axis = k; } }
+    return axis;
+}
+// src/aabb/aabb_impl.rs:198-202, 221-224 (used by the invariants only)
+template <class T> inline bool aabb_approx_contains_point(const Aabb3<T>& a, const T p[3], T eps) {
+    for (int k = 0; k < 3; ++k) { if (!((p[k] - a.min[k]) > -eps)) return false; if (!((p[k] - a.max[k]) < eps)) return false; }
+    return true;
+}
+template <class T> inline bool aabb_approx_contains_aabb(const Aabb3<T>& a, const Aabb3<T>& o, T eps) {
+    return aabb_approx_contains_point(a, o.min, eps) && aabb_approx_contains_point(a, o.max, eps);
+}
+
+// ----------------------------------------------------------------------------
+// L1 ray.
+// ----------------------------------------------------------------------------
+// src/ray/ray_impl.rs:70-80.  [3p] normalize = v / sqrt((x*x + y*y) + z*z).
+template <class T> inline Ray3<T> ray_new(const T o[3], const T d[3]) {
+    Ray3<T> r;
+    const T n2 = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+    const T n = std::sqrt(n2);
+    for (int k = 0; k < 3; ++k) {
+        r.origin[k] = o[k];
+        r.direction[k] = d[k] / n;
+        r.inv_direction[k] = T(1) / r.direction[k];
+    }
+    return r;
+}
+// src/ray/intersect_default.rs:16-37 (scalar path; the SIMD specialisations in
+// intersect_simd.rs compute the same predicate).
+template <class T> inline bool ray_intersects_aabb(const Ray3<T>& ray, const Aabb3<T>& b) {
+    T l[3], r[3];
+    for (int k = 0; k < 3; ++k) {
+        l[k] = (b.min[k] - ray.origin[k]) * ray.inv_direction[k];
+        r[k] = (b.max[k] - ray.origin[k]) * ray.inv_direction[k];
+    }
+    for (int k = 0; k < 3; ++k) if (std::isnan(l[k]) || std::isnan(r[k])) return false;   // utils.rs:113-115
+    T tmin = smin(l[0], r[0]), tmax = smax(l[0], r[0]);                                  // inf_sup
+    for (int k = 1; k < 3; ++k) {
+        tmin = smax(tmin, smin(l[k], r[k]));                                             // inf.max()
+        tmax = smin(tmax, smax(l[k], r[k]));                                             // sup.min()
+    }
+    return tmax >= fast_max(tmin, T(0));
+}
+
+// ----------------------------------------------------------------------------
+// L2a build.
+// ----------------------------------------------------------------------------
+struct BuildStats {
+    uint64_t prim_visits = 0;       // P: sum over internal nodes of |indices|
+    uint64_t degenerate_splits = 0; // nodes taking bvh_node.rs:114-124
+    uint64_t nosplit_fallthrough = 0; // nodes where no cost < +inf (bvh_node.rs:239 never true)
+    uint32_t max_depth = 0;
+};
+
+template <class T> struct BuildArgs {   // src/bvh/bvh_node.rs:437-446
+    uint32_t start, count;              // slice of the (shared) index array
+    uint32_t parent, node;
+    uint32_t depth;
+    Aabb3<T> aabb_bounds, centroid_bounds;
+};
+
+// src/utils.rs:97-109
+template <class T>
+inline void joint_aabb_of_shapes(const uint32_t* idx, uint32_t count, const Aabb3<T>* shapes,
+                                 Aabb3<T>& aabb, Aabb3<T>& centroid) {
+    aabb = aabb_empty<T>();
+    centroid = aabb_empty<T>();
+    for (uint32_t i = 0; i < count; ++i) {
+        const Aabb3<T>& s = shapes[idx[i]];
+        aabb = aabb_join(aabb, s);
+        T c[3];
+        aabb_center(s, c);
+        centroid = aabb_grow(centroid, c);
+    }
+}
+
+// One call of BvhNode::prep_build (src/bvh/bvh_node.rs:81-180) including
+// build_buckets (:183-279).  Returns false for a leaf; otherwise fills l/r.
+// `scratch` plays the role of the thread-local bucket vectors (bucket.rs:14-24).
+template <class T>
+inline bool prep_build(const BuildArgs<T>& a, const Aabb3<T>* shapes, uint32_t* indices,
+                       Node<T>* nodes, uint32_t* node_index_of_shape,
+                       std::array<std::vector<uint32_t>, 6>& scratch,
+                       BuildArgs<T>& left, BuildArgs<T>& right, BuildStats& st) {
+    uint32_t* I = indices + a.start;
+    if (a.depth > st.max_depth) st.max_depth = a.depth;
+    if (a.count == 1) {                                         // :95-104
+        Node<T>& n = nodes[a.node];
+        n.parent = a.parent; n.child_l = U32_MAX; n.child_r = U32_MAX; n.shape = I[0];
+        n.l_aabb = aabb_empty<T>(); n.r_aabb = aabb_empty<T>();
+        node_index_of_shape[I[0]] = a.node;
+        return false;
+    }
+    st.prim_visits += a.count;
+    const int axis = aabb_largest_axis(a.centroid_bounds);       // :107
+    const T ext = a.centroid_bounds.max[axis] - a.centroid_bounds.min[axis];   // :108
+    Aabb3<T> lab, lcb, rab, rcb;
+    uint32_t nl;
+    if (ext < std::numeric_limits<T>::epsilon()) {              // :114-124
+        st.degenerate_splits++;
+        nl = a.count / 2;
+        joint_aabb_of_shapes(I, nl, shapes, lab, lcb);
+        joint_aabb_of_shapes(I + nl, a.count - nl, shapes, rab, rcb);
+    } else {                                                    // build_buckets :183-279
+        struct Bucket { uint32_t size; Aabb3<T> aabb, centroid; };    // utils.rs:59-95
+        Bucket buckets[6];
+        for (auto& b : buckets) { b.size = 0; b.aabb = aabb_empty<T>(); b.centroid = aabb_empty<T>(); }
+        for (auto& v : scratch) v.clear();
+        const T K = T(6) - T(0.01);                             // :214-215 (T::from(0.01): f64 literal rounded to T)
+        for (uint32_t i = 0; i < a.count; ++i) {                // :204-222
+            const Aabb3<T>& s = shapes[I[i]];
+            T c[3];
+            aabb_center(s, c);
+            const T rel = (c[axis] - a.centroid_bounds.min[axis]) / ext;
+            const T scaled = rel * K;
+            // to_usize(): truncation toward zero; NaN / out of range => the reference panics.
+            const int b = (int)scaled;
+            buckets[b].size += 1;
+            buckets[b].aabb = aabb_join(buckets[b].aabb, s);
+            buckets[b].centroid = aabb_grow(buckets[b].centroid, c);
+            scratch[b].push_back(I[i]);
+        }
+        int min_bucket = 0;                                     // :225-230
+        T min_cost = std::numeric_limits<T>::infinity();
+        lab = lcb = rab = rcb = aabb_empty<T>();
+        bool any = false;
+        for (int s = 0; s < 5; ++s) {                           // :231-247
+            Bucket L{0, aabb_empty<T>(), aabb_empty<T>()}, R{0, aabb_empty<T>(), aabb_empty<T>()};
+            for (int b = 0; b <= s; ++b) { L.size += buckets[b].size; L.aabb = aabb_join(L.aabb, buckets[b].aabb); L.centroid = aabb_join(L.centroid, buckets[b].centroid); }
+            for (int b = s + 1; b < 6; ++b) { R.size += buckets[b].size; R.aabb = aabb_join(R.aabb, buckets[b].aabb); R.centroid = aabb_join(R.centroid, buckets[b].centroid); }
+            const T cost = (T(L.size) * aabb_surface_area(L.aabb) + T(R.size) * aabb_surface_area(R.aabb))
+                           / aabb_surface_area(a.aabb_bounds);
+            if (cost < min_cost) {
+                any = true;
+                min_bucket = s; min_cost = cost;
+                lab = L.aabb; lcb = L.centroid; rab = R.aabb; rcb = R.centroid;
+            }
+        }
+        if (!any) st.nosplit_fallthrough++;
+        nl = 0;                                                 // :250-272
+        for (int b = 0; b <= min_bucket; ++b) nl += (uint32_t)scratch[b].size();
+        uint32_t w = 0;
+        for (int b = 0; b < 6; ++b) for (uint32_t v : scratch[b]) I[w++] = v;
+    }
+    const uint32_t child_l = a.node + 1;                        // :138-142
+    const uint32_t child_r = child_l + (2 * nl - 1);
+    Node<T>& n = nodes[a.node];                                 // :145-151
+    n.parent = a.parent; n.child_l = child_l; n.child_r = child_r; n.shape = a.count;
+    n.l_aabb = lab; n.r_aabb = rab;
+    left = BuildArgs<T>{a.start, nl, a.node, child_l, a.depth + 1, lab, lcb};               // :154-179
+    right = BuildArgs<T>{a.start + nl, a.count - nl, a.node, child_r, a.depth + 1, rab, rcb};
+    return true;
+}
+
+// Sequential subtree build (BvhNode::build, bvh_node.rs:55-60) with an explicit stack.
+template <class T>
+inline void build_subtree(const BuildArgs<T>& root, const Aabb3<T>* shapes, uint32_t* indices,
+                          Node<T>* nodes, uint32_t* node_index_of_shape, BuildStats& st) {
+    std::array<std::vector<uint32_t>, 6> scratch;
+    std::vector<BuildArgs<T>> stack;
+    stack.push_back(root);
+    while (!stack.empty()) {
+        BuildArgs<T> a = stack.back();
+        stack.pop_back();
+        BuildArgs<T> l, r;
+        if (prep_build(a, shapes, indices, nodes, node_index_of_shape, scratch, l, r, st)) {
+            stack.push_back(r);
+            stack.push_back(l);
+        }
+    }
+}
+
+// Bvh::build (src/bvh/bvh_impl.rs:40-96).  nodes must hold 2n-1 entries,
+// node_index_of_shape n entries (BHShape::set_bh_node_index, bounding_hierarchy.rs:58).
+template <class T>
+inline BuildStats build(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index_of_shape) {
+    BuildStats st;
+    if (n == 0) return st;                                      // :57-59
+    std::vector<uint32_t> indices(n);
+    for (uint32_t i = 0; i < n; ++i) indices[i] = i;            // :61-63
+    BuildArgs<T> root{0, n, 0, 0, 0, {}, {}};
+    joint_aabb_of_shapes(indices.data(), n, shapes, root.aabb_bounds, root.centroid_bounds);  // :74
+    build_subtree(root, shapes, indices.data(), nodes, node_index_of_shape, st);
+    return st;
+}
+
+// Bvh::build_par analogue (bounding_hierarchy.rs:170-177 + rayon_executor,
+// bvh_impl.rs:527-543): children are forked iff their combined shape count is
+// >= 64; the result is identical to the sequential build because children
+// write disjoint slices.  rayon is replaced by a small shared-queue pool.
+template <class T>
+inline BuildStats build_par(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index_of_shape,
+                            unsigned threads) {
+    BuildStats st;
+    if (n == 0) return st;
+    if (threads <= 1) return build(shapes, n, nodes, node_index_of_shape);
+    std::vector<uint32_t> indices(n);
+    for (uint32_t i = 0; i < n; ++i) indices[i] = i;
+    BuildArgs<T> root{0, n, 0, 0, 0, {}, {}};
+    joint_aabb_of_shapes(indices.data(), n, shapes, root.aabb_bounds, root.centroid_bounds);
+
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<BuildArgs<T>> queue;
+    size_t outstanding = 1;         // tasks queued or running
+    queue.push_back(root);
+    std::vector<BuildStats> tstats(threads);
+
+    auto worker = [&](unsigned tid) {
+        std::array<std::vector<uint32_t>, 6> scratch;
+        BuildStats& ls = tstats[tid];
+        for (;;) {
+            BuildArgs<T> a;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !queue.empty() || outstanding == 0; });
+                if (queue.empty()) return;
+                a = queue.back();
+                queue.pop_back();
+            }
+            // Run this task: descend, forking the right child while the grain rule allows.
+            bool have = true;
+            while (have) {
+                BuildArgs<T> l, r;
+                if (!prep_build(a, shapes, indices.data(), nodes, node_index_of_shape, scratch, l, r, ls)) break;
+                if (l.count + r.count < 64) {                   // bvh_impl.rs:534
+                    build_subtree(l, shapes, indices.data(), nodes, node_index_of_shape, ls);
+                    build_subtree(r, shapes, indices.data(), nodes, node_index_of_shape, ls);
+                    have = false;
+                } else {
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        queue.push_back(r);
+                        ++outstanding;
+                    }
+                    cv.notify_one();
+                    a = l;
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                --outstanding;
+                if (outstanding == 0) cv.notify_all();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t) pool.emplace_back(worker, t);
+    for (auto& th : pool) th.join();
+    for (auto& s : tstats) {
+        st.prim_visits += s.prim_visits;
+        st.degenerate_splits += s.degenerate_splits;
+        st.nosplit_fallthrough += s.nosplit_fallthrough;
+        st.max_depth = std::max(st.max_depth, s.max_depth);
+    }
+    return st;
+}
+
+// ----------------------------------------------------------------------------
+// L2b flatten: literal restatement of the recursion (src/flat_bvh.rs:60-143,
+// 240-251, 312-319) with an explicit stack that reproduces Vec::push order.
+// ----------------------------------------------------------------------------
+template <class T>
+inline void flatten(const Node<T>* nodes, uint32_t n_nodes, std::vector<FlatNode<T>>& out) {
+    out.clear();
+    if (n_nodes == 0) return;                                   // :245-248
+    // Frames emulate flatten_custom(node, next_free) / create_flat_branch.
+    struct Frame { uint32_t node; int stage; uint32_t nav_l, nav_r; };
+    auto push_leaf = [&](const Node<T>& nd) {                   // :129-141
+        FlatNode<T> f;
+        f.aabb = aabb_empty<T>();
+        f.entry_index = U32_MAX;
+        f.exit_index = (uint32_t)out.size() + 1;
+        f.shape_index = nd.shape;
+        out.push_back(f);
+    };
+    if (nodes[0].is_leaf()) { push_leaf(nodes[0]); return; }
+    std::vector<Frame> stack;
+    stack.push_back(Frame{0, 0, 0, 0});
+    while (!stack.empty()) {
+        Frame& fr = stack.back();
+        const Node<T>& nd = nodes[fr.node];
+        if (nd.is_leaf()) { push_leaf(nd); stack.pop_back(); continue; }
+        if (fr.stage == 0) {                                    // create_flat_branch(child_l): push dummy (:71-74)
+            fr.stage = 1;
+            fr.nav_l = (uint32_t)out.size();
+            out.push_back(FlatNode<T>{aabb_empty<T>(), 0, 0, 0});
+            stack.push_back(Frame{nd.child_l, 0, 0, 0});
+        } else if (fr.stage == 1) {                             // overwrite left navigator (:80-88), then right dummy
+            FlatNode<T>& nav = out[fr.nav_l];
+            nav.aabb = nd.l_aabb; nav.entry_index = fr.nav_l + 1; nav.exit_index = (uint32_t)out.size(); nav.shape_index = U32_MAX;
+            fr.stage = 2;
+            fr.nav_r = (uint32_t)out.size();
+            out.push_back(FlatNode<T>{aabb_empty<T>(), 0, 0, 0});
+            const uint32_t child = nd.child_r;
+            stack.push_back(Frame{child, 0, 0, 0});
+        } else {
+            FlatNode<T>& nav = out[fr.nav_r];
+            nav.aabb = nd.r_aabb; nav.entry_index = fr.nav_r + 1; nav.exit_index = (uint32_t)out.size(); nav.shape_index = U32_MAX;
+            stack.pop_back();
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Traversal.
+// ----------------------------------------------------------------------------
+struct TraverseStats { uint64_t node_visits = 0; uint64_t slab_tests = 0; uint64_t leaf_visits = 0; uint64_t hits = 0; };
+
+// BvhNode::traverse_recursive (src/bvh/bvh_node.rs:288-319) + Bvh::traverse
+// (src/bvh/bvh_impl.rs:104-119).  Explicit stack, left child first.
+template <class T>
+inline void traverse_recursive(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes,
+                               const Ray3<T>& ray, std::vector<uint32_t>& out, TraverseStats* st = nullptr) {
+    if (n_nodes == 0) return;                                   // bvh_impl.rs:109-112
+    if (nodes[0].is_leaf()) {                                   // bvh_node.rs:314 (root leaf re-tests the shape)
+        if (st) st->slab_tests++;
+        if (ray_intersects_aabb(ray, shapes[nodes[0].shape])) { out.push_back(nodes[0].shape); if (st) st->hits++; }
+        return;
+    }
+    uint32_t stack[128];
+    std::vector<uint32_t> big;          // only used if depth exceeds 128
+    int sp = 0;
+    auto push = [&](uint32_t v) { if (sp < 128) stack[sp++] = v; else { big.push_back(v); ++sp; } };
+    auto pop = [&]() -> uint32_t { if (sp > 128) { uint32_t v = big.back(); big.pop_back(); --sp; return v; } return stack[--sp]; };
+    push(0);
+    while (sp > 0) {
+        const uint32_t i = pop();
+        const Node<T>& nd = nodes[i];
+        if (st) st->node_visits++;
+        if (nd.is_leaf()) { out.push_back(nd.shape); if (st) st->hits++; continue; }
+        if (st) st->slab_tests += 2;
+        const bool hl = ray_intersects_aabb(ray, nd.l_aabb);
+        const bool hr = ray_intersects_aabb(ray, nd.r_aabb);
+        if (hr) push(nd.child_r);       // popped after the whole left subtree
+        if (hl) push(nd.child_l);
+    }
+}
+
+// BvhTraverseIterator (src/bvh/iter.rs:6-182), literal state machine with the
+// 32-slot stack.  Returns false if the reference would have panicked
+// (stack overflow, iter.rs:56-59).
+template <class T>
+inline bool traverse_iterator(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes,
+                              const Ray3<T>& ray, std::vector<uint32_t>& out) {
+    bool has_node;
+    if (n_nodes == 0) has_node = false;                         // iter.rs:164-182
+    else if (nodes[0].is_leaf()) has_node = ray_intersects_aabb(ray, shapes[nodes[0].shape]);
+    else has_node = true;
+    uint32_t stack[32];
+    uint32_t sp = 0, node = 0;
+    for (;;) {
+        if (sp == 0 && !has_node) break;
+        if (has_node) {
+            if (sp >= 32) return false;
+            stack[sp++] = node;
+            const Node<T>& nd = nodes[node];                    // move_left
+            if (!nd.is_leaf() && ray_intersects_aabb(ray, nd.l_aabb)) { node = nd.child_l; has_node = true; }
+            else has_node = false;
+        } else {
+            node = stack[--sp];
+            const Node<T>& nd = nodes[node];
+            if (!nd.is_leaf()) {                                // move_right
+                if (ray_intersects_aabb(ray, nd.r_aabb)) { node = nd.child_r; has_node = true; }
+                else has_node = false;
+            } else {
+                has_node = false;
+                out.push_back(nd.shape);
+            }
+        }
+    }
+    return true;
+}
+
+// FlatBvh::traverse (src/flat_bvh.rs:396-431).
+template <class T>
+inline void traverse_flat(const FlatNode<T>* flat, uint32_t n_flat, const Aabb3<T>* shapes,
+                          const Ray3<T>& ray, std::vector<uint32_t>& out, TraverseStats* st = nullptr) {
+    uint32_t index = 0;
+    while (index < n_flat) {
+        const FlatNode<T>& node = flat[index];
+        if (st) st->node_visits++;
+        if (node.entry_index == U32_MAX) {
+            if (st) { st->leaf_visits++; st->slab_tests++; }
+            if (ray_intersects_aabb(ray, shapes[node.shape_index])) { out.push_back(node.shape_index); if (st) st->hits++; }
+            index = node.exit_index;
+        } else {
+            if (st) st->slab_tests++;
+            index = ray_intersects_aabb(ray, node.aabb) ? node.entry_index : node.exit_index;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Invariants: Bvh::is_consistent / assert_tight (src/bvh/bvh_impl.rs:280-485).
+// ----------------------------------------------------------------------------
+template <class T>
+inline bool is_consistent(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes) {
+    if (n_nodes == 0) return true;
+    const T inf = std::numeric_limits<T>::infinity();
+    struct F { uint32_t node, parent; Aabb3<T> outer; };
+    std::vector<F> stack;
+    stack.push_back(F{0, 0, Aabb3<T>{{-inf, -inf, -inf}, {inf, inf, inf}}});
+    uint64_t count = 0;
+    const T eps = std::numeric_limits<T>::epsilon();
+    bool ok = true;
+    while (!stack.empty()) {
+        F f = stack.back();
+        stack.pop_back();
+        if (f.node >= n_nodes) return false;
+        ++count;
+        if (count > n_nodes) return false;
+        const Node<T>& nd = nodes[f.node];
+        if (nd.parent != f.parent) ok = false;
+        if (nd.is_leaf()) {
+            if (!aabb_approx_contains_aabb(f.outer, shapes[nd.shape], eps)) ok = false;
+        } else {
+            if (!aabb_approx_contains_aabb(f.outer, nd.l_aabb, eps)) ok = false;
+            if (!aabb_approx_contains_aabb(f.outer, nd.r_aabb, eps)) ok = false;
+            stack.push_back(F{nd.child_r, f.node, nd.r_aabb});
+            stack.push_back(F{nd.child_l, f.node, nd.l_aabb});
+        }
+    }
+    return ok && count == n_nodes;
+}
+template <class T>
+inline bool is_tight(const Node<T>* nodes, uint32_t n_nodes) {
+    if (n_nodes == 0 || nodes[0].is_leaf()) return true;
+    struct F { uint32_t node; Aabb3<T> outer; };
+    std::vector<F> stack;
+    stack.push_back(F{0, aabb_join(nodes[0].l_aabb, nodes[0].r_aabb)});
+    while (!stack.empty()) {
+        F f = stack.back();
+        stack.pop_back();
+        const Node<T>& nd = nodes[f.node];
+        if (nd.is_leaf()) continue;
+        const Aabb3<T> j = aabb_join(nd.l_aabb, nd.r_aabb);
+        for (int k = 0; k < 3; ++k) if (!(j.min[k] == f.outer.min[k] && j.max[k] == f.outer.max[k])) return false;
+        stack.push_back(F{nd.child_r, nd.r_aabb});
+        stack.push_back(F{nd.child_l, nd.l_aabb});
+    }
+    return true;
+}
+
+// Whole-tree SAH cost (definition fixed in SURVEY.md 8d; the reference has no
+// whole-tree cost): sum over non-root nodes of SA(child aabb stored in the
+// parent) / SA(root aabb), in double.  pseudo = reference's 2*|size|^2,
+// geometric = 2(xy+yz+zx).
+template <class T>
+inline void sah_cost(const Node<T>* nodes, uint32_t n_nodes, double& pseudo, double& geometric) {
+    pseudo = geometric = 0.0;
+    if (n_nodes == 0 || nodes[0].is_leaf()) return;
+    auto sa = [](const Aabb3<T>& a, bool geo) {
+        const double x = (double)a.max[0] - (double)a.min[0], y = (double)a.max[1] - (double)a.min[1], z = (double)a.max[2] - (double)a.min[2];
+        return geo ? 2.0 * (x * y + y * z + z * x) : 2.0 * (x * x + y * y + z * z);
+    };
+    const Aabb3<T> root = aabb_join(nodes[0].l_aabb, nodes[0].r_aabb);
+    const double rp = sa(root, false), rg = sa(root, true);
+    for (uint32_t i = 0; i < n_nodes; ++i) {
+        if (nodes[i].is_leaf()) continue;
+        pseudo += sa(nodes[i].l_aabb, false) + sa(nodes[i].r_aabb, false);
+        geometric += sa(nodes[i].l_aabb, true) + sa(nodes[i].r_aabb, true);
+    }
+    pseudo /= rp;
+    geometric /= rg;
+}
+
+// ----------------------------------------------------------------------------
+// Fixtures (src/testbase.rs).
+// ----------------------------------------------------------------------------
+inline uint64_t splitmix64(uint64_t& x) {                       // testbase.rs:560-566
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+inline void next_point3_raw(uint64_t& seed, int32_t& a, int32_t& b, int32_t& c) {   // :569-575
+    const uint64_t u = splitmix64(seed);
+    const int64_t ia = (int64_t)((u >> 32) & 0xFFFFFFFFull) - 0x80000000ll;
+    const int64_t ib = (int64_t)(u & 0xFFFFFFFFull) - 0x80000000ll;
+    const uint64_t ub = (uint64_t)ib;
+    const int64_t rot = (int64_t)((ub << 6) | (ub >> 58));      // i64::rotate_left(6)
+    const int64_t ic = ia ^ rot;
+    a = (int32_t)ia; b = (int32_t)ib; c = (int32_t)ic;          // `as i32` truncates
+}
+// next_point3 (:578-597), generic in T so that config 5 can restate it in f64
+// from the same integer stream.  T = float is the reference.
+template <class T> inline void next_point3(uint64_t& seed, const Aabb3<T>& bounds, T out[3]) {
+    int32_t r[3];
+    next_point3_raw(seed, r[0], r[1], r[2]);
+    const T imax = (T)2147483647;                               // i32::MAX as f32 == 2147483648.0f
+    for (int k = 0; k < 3; ++k) {
+        const T fv = (((T)r[k] / imax) + T(1)) * T(0.5);
+        const T size = bounds.max[k] - bounds.min[k];
+        out[k] = bounds.min[k] + fv * size;
+    }
+}
+template <class T> inline Aabb3<T> default_bounds() {           // :600-605
+    return Aabb3<T>{{T(-100000), T(-100000), T(-100000)}, {T(100000), T(100000), T(100000)}};
+}
+// Triangle::new (:347-357): aabb = empty.grow(a).grow(b).grow(c)
+template <class T> inline Aabb3<T> triangle_aabb(const T a[3], const T b[3], const T c[3]) {
+    return aabb_grow(aabb_grow(aabb_grow(aabb_empty<T>(), a), b), c);
+}
+// push_cube (:490-556): 12 triangles, vertices pos +- 0.5.  tri_out: 9 T per triangle.
+template <class T> inline void push_cube(const T pos[3], std::vector<T>& tri_out) {
+    auto V = [&](T sx, T sy, T sz, T v[3]) { v[0] = pos[0] + sx; v[1] = pos[1] + sy; v[2] = pos[2] + sz; };
+    const T h = T(0.5);
+    T tfr[3], tbr[3], tbl[3], tfl[3], bfr[3], bbr[3], bbl[3], bfl[3];
+    V(h, h, -h, tfr); V(h, h, h, tbr); V(-h, h, h, tbl); V(-h, h, -h, tfl);
+    V(h, -h, -h, bfr); V(h, -h, h, bbr); V(-h, -h, h, bbl); V(-h, -h, -h, bfl);
+    const T* tris[12][3] = {
+        {tbr, tfr, tfl}, {tfl, tbl, tbr}, {bfl, bfr, bbr}, {bbr, bbl, bfl},
+        {tbl, tfl, bfl}, {bfl, bbl, tbl}, {bfr, tfr, tbr}, {tbr, bbr, bfr},
+        {tfl, tfr, bfr}, {bfr, bfl, tfl}, {bbr, tbr, tbl}, {tbl, bbl, bbr}};
+    for (auto& t : tris) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) tri_out.push_back(t[v][k]);
+}
+template <class T> inline void create_n_cubes(uint32_t n_cubes, const Aabb3<T>& bounds, std::vector<T>& tri_out) {   // :608-615
+    uint64_t seed = 0;
+    tri_out.clear();
+    tri_out.reserve((size_t)n_cubes * 108);
+    for (uint32_t i = 0; i < n_cubes; ++i) {
+        T p[3];
+        next_point3(seed, bounds, p);
+        push_cube(p, tri_out);
+    }
+}
+template <class T> inline Ray3<T> create_ray(uint64_t& seed, const Aabb3<T>& bounds) {     // :687-691
+    T o[3], d[3];
+    next_point3(seed, bounds, o);
+    next_point3(seed, bounds, d);
+    return ray_new(o, d);
+}
+// generate_aligned_boxes (:109-116) + UnitBox::aabb (:84-90)
+template <class T> inline void aligned_boxes(std::vector<Aabb3<T>>& out) {
+    out.clear();
+    for (int x = -10; x < 11; ++x) {
+        const T pos[3] = {(T)x, T(0), T(0)};
+        Aabb3<T> b;
+        for (int k = 0; k < 3; ++k) { b.min[k] = pos[k] + T(-0.5); b.max[k] = pos[k] + T(0.5); }
+        out.push_back(b);
+    }
+}
+
+}  // namespace orc

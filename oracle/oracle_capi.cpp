@@ -1,0 +1,150 @@
+// ============================================================================
+// oracle/oracle_capi.cpp -- TEST INFRASTRUCTURE ONLY (see bvh_oracle.hpp).
+// extern "C" surface over the CPU restatement so that tests/ and bench.py's
+// cpu_baseline / --impl reference legs can drive it through ctypes.
+// ============================================================================
+#include "bvh_oracle.hpp"
+#include <cstring>
+#include <chrono>
+
+using namespace orc;
+
+namespace {
+
+template <class T>
+uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3<T>* shapes,
+                        const Ray3<T>* rays, uint64_t nrays, uint64_t* offsets, uint32_t* hits, uint64_t cap,
+                        uint64_t* stats, unsigned threads, int* overflow32) {
+    // mode 0: Bvh::traverse (recursive)   1: FlatBvh::traverse   2: BvhTraverseIterator
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > nrays) threads = nrays ? (unsigned)nrays : 1;
+    std::vector<std::vector<uint32_t>> lists(threads);
+    std::vector<std::vector<uint64_t>> counts(threads);
+    std::vector<TraverseStats> tst(threads);
+    std::vector<int> ok(threads, 1);
+    auto work = [&](unsigned t) {
+        const uint64_t lo = nrays * t / threads, hi = nrays * (t + 1) / threads;
+        std::vector<uint32_t> out;
+        counts[t].reserve(hi - lo);
+        for (uint64_t r = lo; r < hi; ++r) {
+            out.clear();
+            if (mode == 0) traverse_recursive((const Node<T>*)tree, n_tree, shapes, rays[r], out, &tst[t]);
+            else if (mode == 1) traverse_flat((const FlatNode<T>*)tree, n_tree, shapes, rays[r], out, &tst[t]);
+            else if (!traverse_iterator((const Node<T>*)tree, n_tree, shapes, rays[r], out)) ok[t] = 0;
+            counts[t].push_back(out.size());
+            lists[t].insert(lists[t].end(), out.begin(), out.end());
+        }
+    };
+    if (threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    uint64_t total = 0, r = 0;
+    for (unsigned t = 0; t < threads; ++t) {
+        for (uint64_t c : counts[t]) { if (offsets) offsets[r] = total; total += c; ++r; }
+    }
+    if (offsets) offsets[nrays] = total;
+    if (hits) {
+        uint64_t w = 0;
+        for (unsigned t = 0; t < threads; ++t) {
+            for (uint32_t h : lists[t]) { if (w < cap) hits[w] = h; ++w; }
+        }
+    }
+    if (stats) {
+        stats[0] = stats[1] = stats[2] = stats[3] = 0;
+        for (auto& s : tst) { stats[0] += s.node_visits; stats[1] += s.slab_tests; stats[2] += s.leaf_visits; stats[3] += s.hits; }
+    }
+    if (overflow32) { *overflow32 = 0; for (int o : ok) if (!o) *overflow32 = 1; }
+    return total;
+}
+
+template <class T>
+void tri_aabbs(const T* tris, uint64_t n, Aabb3<T>* out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = triangle_aabb(tris + 9 * i, tris + 9 * i + 3, tris + 9 * i + 6);
+}
+
+}  // namespace
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+#define DEFINE_FOR(T, SUF)                                                                                   \
+    ORC_API void orc_build_##SUF(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index,   \
+                                 uint64_t* stats4) {                                                         \
+        BuildStats st = build(shapes, n, nodes, node_index);                                                 \
+        if (stats4) { stats4[0] = st.prim_visits; stats4[1] = st.degenerate_splits; stats4[2] = st.max_depth; stats4[3] = st.nosplit_fallthrough; } \
+    }                                                                                                        \
+    ORC_API void orc_build_par_##SUF(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index, \
+                                     uint64_t* stats4, uint32_t threads) {                                   \
+        BuildStats st = build_par(shapes, n, nodes, node_index, threads);                                    \
+        if (stats4) { stats4[0] = st.prim_visits; stats4[1] = st.degenerate_splits; stats4[2] = st.max_depth; stats4[3] = st.nosplit_fallthrough; } \
+    }                                                                                                        \
+    ORC_API uint64_t orc_flatten_##SUF(const Node<T>* nodes, uint32_t n_nodes, FlatNode<T>* out, uint64_t cap) { \
+        std::vector<FlatNode<T>> v;                                                                          \
+        flatten(nodes, n_nodes, v);                                                                          \
+        if (out) std::memcpy(out, v.data(), sizeof(FlatNode<T>) * std::min<uint64_t>(cap, v.size()));       \
+        return v.size();                                                                                     \
+    }                                                                                                        \
+    ORC_API uint64_t orc_traverse_batch_##SUF(int mode, const void* tree, uint32_t n_tree, const Aabb3<T>* shapes, \
+                                              const Ray3<T>* rays, uint64_t nrays, uint64_t* offsets,        \
+                                              uint32_t* hits, uint64_t cap, uint64_t* stats4, uint32_t threads, \
+                                              int* iter_overflow) {                                          \
+        return traverse_batch<T>(mode, tree, n_tree, shapes, rays, nrays, offsets, hits, cap, stats4, threads, iter_overflow); \
+    }                                                                                                        \
+    ORC_API int orc_is_consistent_##SUF(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes) {    \
+        return is_consistent(nodes, n_nodes, shapes) ? 1 : 0;                                                \
+    }                                                                                                        \
+    ORC_API int orc_is_tight_##SUF(const Node<T>* nodes, uint32_t n_nodes) { return is_tight(nodes, n_nodes) ? 1 : 0; } \
+    ORC_API void orc_sah_cost_##SUF(const Node<T>* nodes, uint32_t n_nodes, double* out2) {                  \
+        sah_cost(nodes, n_nodes, out2[0], out2[1]);                                                          \
+    }                                                                                                        \
+    ORC_API void orc_create_n_cubes_##SUF(uint32_t n_cubes, const Aabb3<T>* bounds, T* tris_out /*108 per cube*/, \
+                                          Aabb3<T>* aabbs_out /*12 per cube*/) {                             \
+        std::vector<T> tris;                                                                                 \
+        create_n_cubes(n_cubes, *bounds, tris);                                                              \
+        if (tris_out) std::memcpy(tris_out, tris.data(), tris.size() * sizeof(T));                           \
+        if (aabbs_out) tri_aabbs(tris.data(), (uint64_t)n_cubes * 12, aabbs_out);                            \
+    }                                                                                                        \
+    ORC_API void orc_tri_aabbs_##SUF(const T* tris, uint64_t n, Aabb3<T>* out) { tri_aabbs(tris, n, out); }  \
+    ORC_API void orc_create_rays_##SUF(uint64_t* seed, const Aabb3<T>* bounds, uint64_t n, Ray3<T>* out) {   \
+        for (uint64_t i = 0; i < n; ++i) out[i] = create_ray(*seed, *bounds);                                \
+    }                                                                                                        \
+    ORC_API void orc_next_points_##SUF(uint64_t* seed, const Aabb3<T>* bounds, uint64_t n, T* out) {         \
+        for (uint64_t i = 0; i < n; ++i) next_point3(*seed, *bounds, out + 3 * i);                           \
+    }                                                                                                        \
+    ORC_API void orc_ray_new_##SUF(const T* origins, const T* dirs, uint64_t n, Ray3<T>* out) {              \
+        for (uint64_t i = 0; i < n; ++i) out[i] = ray_new(origins + 3 * i, dirs + 3 * i);                    \
+    }                                                                                                        \
+    ORC_API int orc_ray_intersects_aabb_##SUF(const Ray3<T>* ray, const Aabb3<T>* aabb) {                    \
+        return ray_intersects_aabb(*ray, *aabb) ? 1 : 0;                                                     \
+    }                                                                                                        \
+    ORC_API void orc_aligned_boxes_##SUF(Aabb3<T>* out21) {                                                  \
+        std::vector<Aabb3<T>> v;                                                                             \
+        aligned_boxes(v);                                                                                    \
+        std::memcpy(out21, v.data(), sizeof(Aabb3<T>) * 21);                                                 \
+    }                                                                                                        \
+    ORC_API void orc_aabb_ops_##SUF(const Aabb3<T>* a, T* center3, T* surface_area, int* largest_axis) {     \
+        aabb_center(*a, center3);                                                                            \
+        *surface_area = aabb_surface_area(*a);                                                               \
+        *largest_axis = aabb_largest_axis(*a);                                                               \
+    }
+
+DEFINE_FOR(float, f32)
+DEFINE_FOR(double, f64)
+
+ORC_API uint64_t orc_splitmix64(uint64_t* seed) { return splitmix64(*seed); }
+ORC_API uint32_t orc_hardware_threads() { return std::thread::hardware_concurrency(); }
+ORC_API uint32_t orc_sizeof(int what) {
+    switch (what) {
+        case 0: return sizeof(Aabb3<float>);
+        case 1: return sizeof(Ray3<float>);
+        case 2: return sizeof(Node<float>);
+        case 3: return sizeof(FlatNode<float>);
+        case 4: return sizeof(Aabb3<double>);
+        case 5: return sizeof(Ray3<double>);
+        case 6: return sizeof(Node<double>);
+        case 7: return sizeof(FlatNode<double>);
+    }
+    return 0;
+}

@@ -1,0 +1,287 @@
+"""Pins the CPU oracle (oracle/) against every golden / known-answer test the reference holds for
+the build -> flatten -> traverse path, and against an independent numpy restatement
+(tests/pyref.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import pyref
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+MODES = {"recursive": O.MODE_RECURSIVE, "flat": O.MODE_FLAT, "iterator": O.MODE_ITERATOR}
+
+
+def _trav(mode, res, flat, shapes, rays, prec="f32"):
+    tree = flat if mode == O.MODE_FLAT else res.nodes
+    return O.traverse(tree, shapes, rays, mode, prec)
+
+
+# ---- (1) 21-box scene hit sets: testbase.rs:174-225, iter.rs:269-308 ------------------------------
+@pytest.mark.parametrize("threads", [1, 4])           # Bvh::build and Bvh::build_par
+@pytest.mark.parametrize("mode", list(MODES))
+def test_aligned_boxes_hit_sets(mode, threads):
+    boxes = O.aligned_boxes()
+    res = O.build(boxes, threads=threads)
+    flat = O.flatten(res.nodes)
+    for case in G["aligned_boxes_21"]["rays"]:
+        ray = O.ray_new([case["origin"]], [case["direction"]])
+        t = _trav(MODES[mode], res, flat, boxes, ray)
+        ids = sorted(int(h) - 10 for h in t.hits)
+        assert ids == sorted(case["hit_ids"]), (mode, case)
+        assert len(t.hits) == len(case["hit_ids"])
+
+
+# ---- (2) degenerate sizes: bvh_impl.rs:564-574, 665-690; flat_bvh.rs:620-625 ----------------------
+def test_empty():
+    e = np.zeros(0, dtype=O.AABB3F)
+    res = O.build(e)
+    assert len(res.nodes) == 0
+    assert len(O.flatten(res.nodes)) == 0
+    ray = O.ray_new([[0, 0, 0]], [[1, 0, 0]])
+    for m in MODES.values():
+        tree = O.flatten(res.nodes) if m == O.MODE_FLAT else res.nodes
+        assert len(O.traverse(tree, e, ray, m).hits) == 0
+    assert O.is_consistent(res.nodes, e) and O.is_tight(res.nodes)
+
+
+@pytest.mark.parametrize("case", G["one_node_bvh"]["cases"])
+def test_one_node(case):
+    boxes = O.unit_boxes([case["box_center"]])
+    res = O.build(boxes)
+    assert len(res.nodes) == 1 and res.nodes[0]["child_l"] == O.U32_MAX and res.nodes[0]["shape"] == 0
+    flat = O.flatten(res.nodes)
+    assert len(flat) == 1 and flat[0]["entry_index"] == O.U32_MAX and flat[0]["exit_index"] == 1
+    ray = O.ray_new([case["origin"]], [case["direction"]])
+    for m in MODES.values():
+        assert len(_trav(m, res, flat, boxes, ray).hits) == case["hits"]
+
+
+# ---- (3)+(4) every shape in exactly one leaf; consistent + tight: bvh_impl.rs:588-614, optimization.rs:648-656
+@pytest.mark.parametrize("scene", ["boxes21", "cubes100", "cubes1000"])
+def test_structure_invariants(scene):
+    shapes = O.aligned_boxes() if scene == "boxes21" else O.create_n_cubes(int(scene[5:]))
+    for threads in (1, 4):
+        res = O.build(shapes, threads=threads)
+        n = len(shapes)
+        assert len(res.nodes) == 2 * n - 1
+        leaves = res.nodes[res.nodes["child_l"] == O.U32_MAX]
+        assert sorted(leaves["shape"].tolist()) == list(range(n))
+        assert np.array_equal(res.nodes["shape"][res.node_index], np.arange(n))
+        assert O.is_consistent(res.nodes, shapes)
+        assert O.is_tight(res.nodes)
+
+
+def test_moved_shapes_make_tree_inconsistent():        # optimization.rs:657-663 (negative control for the checker)
+    shapes = O.create_n_cubes(100)
+    res = O.build(shapes)
+    moved = shapes.copy()
+    moved["min"][::3] += 1000.0
+    moved["max"][::3] += 1000.0
+    assert not O.is_consistent(res.nodes, moved)
+
+
+# ---- (5) SAH pairs boxes -50/-40 against 50: optimization.rs:421-455 ------------------------------
+def test_sah_pairing():
+    k = G["sah_pairing"]
+    boxes = O.unit_boxes(k["box_centers"])
+    res = O.build(boxes)
+    a, b = k["same_parent"]
+    na, nb = res.nodes[res.node_index[a]], res.nodes[res.node_index[b]]
+    assert na["child_l"] == O.U32_MAX and nb["child_l"] == O.U32_MAX
+    assert na["parent"] == nb["parent"]
+
+
+# ---- (6) fuzz.rs:299-329 grid-mode property: traverse == traverse_iterator == flatten().traverse ----
+@pytest.mark.parametrize("seed", range(8))
+def test_grid_mode_agreement(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 33))                       # fuzz.rs:427-438 caps trees at 32 shapes (iterator stack)
+    mins = rng.integers(-20, 20, size=(n, 3)).astype(np.float32)
+    size = rng.integers(0, 4, size=(n, 3)).astype(np.float32)
+    shapes = O.make_aabbs(mins, mins + size)
+    res = O.build(shapes)
+    flat = O.flatten(res.nodes)
+    assert O.is_consistent(res.nodes, shapes) and O.is_tight(res.nodes)
+    origins = rng.integers(-25, 25, size=(64, 3)).astype(np.float32) + np.float32(1.0 / 3.0)
+    dirs = np.zeros((64, 3), dtype=np.float32)
+    dirs[np.arange(64), rng.integers(0, 3, 64)] = rng.choice([-1.0, 1.0], 64)
+    rays = O.ray_new(origins, dirs)
+    r0 = O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE)
+    r1 = O.traverse(flat, shapes, rays, O.MODE_FLAT)
+    r2 = O.traverse(res.nodes, shapes, rays, O.MODE_ITERATOR)
+    assert not r2.iter_overflow
+    for a, b, c in zip(O.per_ray_lists(r0.offsets, r0.hits), O.per_ray_lists(r1.offsets, r1.hits), O.per_ray_lists(r2.offsets, r2.hits)):
+        assert set(a.tolist()) == set(b.tolist()) == set(c.tolist())
+    # brute force over shape AABBs must contain every reported hit (a BVH never invents hits)
+    for r, lst in zip(rays, O.per_ray_lists(r0.offsets, r0.hits)):
+        for h in lst:
+            assert O.ray_intersects_aabb(r, shapes[h])
+
+
+# ---- (7) ray / aabb KATs --------------------------------------------------------------------------
+@pytest.mark.parametrize("case", G["ray_aabb"]["cases"], ids=lambda c: c["name"])
+def test_ray_aabb_kats(case):
+    ray = O.ray_new([case["origin"]], [case["direction"]])
+    box = O.make_aabbs([case["min"]], [case["max"]])
+    assert O.ray_intersects_aabb(ray, box) == case["hit"]
+
+
+def test_ray_new_unit_direction():                      # ray_impl.rs:60-65
+    ray = O.ray_new([[0, 0, 0]], [[1, 0, 0]])[0]
+    assert ray["direction"].tolist() == [1.0, 0.0, 0.0]
+    assert ray["inv_direction"][0] == 1.0 and np.isinf(ray["inv_direction"][1]) and np.isinf(ray["inv_direction"][2])
+
+
+def test_ray_points_at_center_proptest():               # ray_impl.rs:304-330 restated with a seeded generator
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        a, b, pos = (rng.uniform(-1e11, 1e11, 3).astype(np.float32) for _ in range(3))
+        box = O.make_aabbs([np.minimum(a, b)], [np.maximum(a, b)])
+        c, _, _ = O.aabb_ops(box)
+        ray = O.ray_new([pos], [c - pos])
+        assert O.ray_intersects_aabb(ray, box)
+        back = ray.copy()
+        back["direction"] = -back["direction"]
+        back["inv_direction"] = -back["inv_direction"]
+        inside = bool(np.all(pos >= box["min"][0]) and np.all(pos <= box["max"][0]))
+        assert (not O.ray_intersects_aabb(back, box)) or inside
+
+
+def test_aabb_kats():
+    k = G["aabb"]
+    _, _, axis = O.aabb_ops(O.make_aabbs([k["largest_axis"]["min"]], [k["largest_axis"]["max"]]))
+    assert axis == k["largest_axis"]["axis"]
+    p1, p2 = np.float32(k["center_overflow"]["p1"]), np.float32(k["center_overflow"]["p2"])
+    box = O.make_aabbs([np.minimum(p1, p2)], [np.maximum(p1, p2)])
+    with np.errstate(over="ignore"):
+        assert np.isinf(box["max"][0][0] - box["min"][0][0])
+    c, _, _ = O.aabb_ops(box)
+    assert np.isfinite(c[0]) and box["min"][0][0] <= c[0] <= box["max"][0][0]
+    rng = np.random.default_rng(1)
+    for _ in range(200):                                 # aabb_impl.rs:889-899
+        s = np.float32(10 ** rng.uniform(-6, 15))
+        pos = rng.uniform(-1e3, 1e3, 3).astype(np.float32) * np.float32(0)   # exact corner so that size == s
+        _, sa, _ = O.aabb_ops(O.make_aabbs([pos], [pos + s]))
+        want = float(np.float32(6) * s * s)
+        # 2*rn(3*rn(s*s)) vs rn(rn(6s)*s): any association of the 3-term dot gives the former, which can sit
+        # 2 ulp from the latter for rare s (the reference's proptest samples 256 values); allow 2 eps here.
+        assert abs(float(sa) - want) <= 2 * float(np.finfo(np.float32).eps) * max(abs(float(sa)), abs(want))
+
+
+# ---- derived fingerprints (independent survey-session restatement; not reference-published) --------
+def test_derived_fingerprints():
+    d = G["derived"]
+    res = O.build(O.aligned_boxes())
+    assert res.node_index.tolist() == d["aligned_boxes_21_node_index"]
+    for key, sc in d["scenes"].items():
+        n = int(key)
+        shapes = O.aligned_boxes() if n == 21 else O.create_n_cubes(n // 12)
+        res = O.build(shapes)
+        flat = O.flatten(res.nodes)
+        assert len(res.nodes) == sc["bvh_nodes"] and len(flat) == sc["flat_nodes"]
+        assert res.max_depth == sc["max_depth"] and res.degenerate_splits == sc["degenerate_splits"]
+        # the survey counted bucketed nodes only; the oracle's P also counts degenerate nodes (2 prims each here)
+        assert res.prim_visits - 2 * res.degenerate_splits == sc["bucketed_prim_visits"]
+        if "rays" in sc:
+            rays, _ = O.create_rays(sc["rays"])
+            t = O.traverse(flat, shapes, rays, O.MODE_FLAT)
+            assert len(t.hits) / sc["rays"] == sc["hits_per_ray"]
+
+
+# ---- oracle == independent numpy restatement, bit for bit ------------------------------------------
+def _cmp_nodes(py_nodes, nodes):
+    assert len(py_nodes) == len(nodes)
+    for i, p in enumerate(py_nodes):
+        o = nodes[i]
+        assert p[1] == o["parent"], i
+        if p[0] == "leaf":
+            assert o["child_l"] == O.U32_MAX and p[2] == o["shape"], i
+        else:
+            assert (p[2], p[3]) == (o["child_l"], o["child_r"]), i
+            assert np.array_equal(np.array(p[4][0]), o["l_aabb"]["min"]) and np.array_equal(np.array(p[4][1]), o["l_aabb"]["max"]), i
+            assert np.array_equal(np.array(p[5][0]), o["r_aabb"]["min"]) and np.array_equal(np.array(p[5][1]), o["r_aabb"]["max"]), i
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("scene", ["boxes21", "cubes40", "random300", "huge", "points"])
+def test_oracle_equals_pyref(scene, prec):
+    F = np.float32 if prec == "f32" else np.float64
+    rng = np.random.default_rng(7)
+    if scene == "boxes21":
+        shapes = O.aligned_boxes(prec)
+    elif scene == "cubes40":
+        shapes = O.create_n_cubes(40, prec=prec)
+    elif scene == "random300":
+        mn = rng.uniform(-100, 100, (300, 3))
+        shapes = O.make_aabbs(mn, mn + rng.uniform(0, 30, (300, 3)), prec)
+    elif scene == "huge":                                # SA overflows to +inf in f32: "no split wins" fallthrough
+        mn = rng.uniform(-1e30, 1e30, (64, 3))
+        shapes = O.make_aabbs(mn, mn + rng.uniform(0, 1e29, (64, 3)), prec)
+    else:                                                # many coincident centroids: degenerate halving
+        mn = np.repeat(rng.integers(-3, 3, (20, 3)).astype(float), 5, axis=0)
+        shapes = O.make_aabbs(mn, mn, prec)
+    res = O.build(shapes, prec)
+    py_nodes, py_idx = pyref.build(shapes, F)
+    _cmp_nodes(py_nodes, res.nodes)
+    assert py_idx == res.node_index.tolist()
+    flat = O.flatten(res.nodes, prec)
+    py_flat = pyref.flatten(py_nodes)
+    assert len(py_flat) == len(flat)
+    for pf, of in zip(py_flat, flat):
+        assert (pf[1], pf[2], pf[3]) == (of["entry_index"], of["exit_index"], of["shape_index"])
+        if pf[0] is not None:
+            assert np.array_equal(np.array(pf[0][0]), of["aabb"]["min"]) and np.array_equal(np.array(pf[0][1]), of["aabb"]["max"])
+    if scene == "huge" and prec == "f32":
+        assert res.nosplit_fallthrough > 0
+    if scene == "points":
+        assert res.degenerate_splits > 0
+    # traversal: oracle (three variants) == pyref recursive, as sequences
+    b = shapes["min"].min(axis=0), shapes["max"].max(axis=0)
+    origins = rng.uniform(b[0], b[1], (40, 3))
+    targets = rng.uniform(b[0], b[1], (40, 3))
+    rays = O.ray_new(origins, targets - origins, prec)
+    r0 = O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, prec)
+    r1 = O.traverse(flat, shapes, rays, O.MODE_FLAT, prec)
+    assert np.array_equal(r0.hits, r1.hits) and np.array_equal(r0.offsets, r1.offsets)
+    for ray, lst in zip(rays, O.per_ray_lists(r0.offsets, r0.hits)):
+        pr = pyref.ray_new(F, ray["origin"], ray["direction"])
+        pr = ([F(v) for v in ray["origin"]], None, [F(v) for v in ray["inv_direction"]])
+        got = pyref.traverse_recursive(py_nodes, shapes, (pr[0], pr[2]), F)
+        assert got == lst.tolist()
+
+
+def test_ray_new_matches_pyref():
+    rng = np.random.default_rng(3)
+    o = rng.uniform(-1e5, 1e5, (50, 3)).astype(np.float32)
+    d = rng.uniform(-1e5, 1e5, (50, 3)).astype(np.float32)
+    rays = O.ray_new(o, d)
+    for i in range(50):
+        po, pd, pinv = pyref.ray_new(np.float32, o[i], d[i])
+        assert np.array_equal(np.array(pd), rays[i]["direction"]) and np.array_equal(np.array(pinv), rays[i]["inv_direction"])
+
+
+# ---- closed-form flatten == literal recursion ------------------------------------------
+@pytest.mark.parametrize("n_cubes", [1, 5, 100])
+def test_closed_form_flatten(n_cubes):
+    shapes = O.create_n_cubes(n_cubes)
+    res = O.build(shapes)
+    flat = O.flatten(res.nodes)
+    nodes = res.nodes
+    n = len(shapes)
+    is_leaf = nodes["child_l"] == O.U32_MAX
+    leaves_before = np.concatenate([[0], np.cumsum(is_leaf)[:-1]])
+    count = np.where(is_leaf, 1, nodes["shape"])
+    assert len(flat) == 3 * n - 2
+    for i in range(1, len(nodes)):
+        nav = (i - 1) + leaves_before[i]
+        par = nodes[nodes[i]["parent"]]
+        aabb = par["l_aabb"] if par["child_l"] == i else par["r_aabb"]
+        f = flat[nav]
+        assert f["entry_index"] == nav + 1 and f["exit_index"] == nav + 3 * count[i] - 1 and f["shape_index"] == O.U32_MAX
+        assert f["aabb"] == aabb
+        if is_leaf[i]:
+            g = flat[nav + 1]
+            assert g["entry_index"] == O.U32_MAX and g["exit_index"] == nav + 2 and g["shape_index"] == nodes[i]["shape"]
