@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference crate's interface for the hot path, on top of the C ABI.
+
+Names follow the reference (svenstaro/bvh 0.12.0):
+
+    Bvh.build(shapes) / Bvh.build_par(shapes)     src/bvh/bvh_impl.rs:40-96, src/bounding_hierarchy.rs:158-177
+    bvh.nodes, shape node indices                  src/bvh/bvh_impl.rs:27-33, src/bounding_hierarchy.rs:53-65
+    bvh.flatten() -> FlatBvh                       src/flat_bvh.rs:312-319
+    bvh.traverse(ray, shapes)                      src/bvh/bvh_impl.rs:104-119
+    bvh.traverse_iterator(ray, shapes)             src/bvh/bvh_impl.rs:128-134
+    flat_bvh.traverse(ray, shapes)                 src/flat_bvh.rs:396-431
+    Ray.new(origin, direction)                     src/ray/ray_impl.rs:70-80
+
+plus the batched form the GPU exists for: bvh.traverse_batch(rays) -> CSR (offsets, hits).
+"Shapes" are anything with an `.aabb()` method (Bounded, src/aabb/aabb_impl.rs:28-56) and
+optionally `set_bh_node_index` (BHShape, src/bounding_hierarchy.rs:53-65); numpy AABB arrays are
+accepted directly.  Everything below runs on the GPU through libbvh_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import capi
+from .dtypes import BY_PREC, U32_MAX
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One per device (stream + scratch pool)."""
+
+    _default: dict[int, "Context"] = {}
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().bvhgpu_create(device, C.byref(self._h)))
+        self.device = device
+
+    @classmethod
+    def default(cls, device: int = 0) -> "Context":
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        capi.check(capi.lib().bvhgpu_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def synchronize(self):
+        capi.check(capi.lib().bvhgpu_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(capi.lib().bvhgpu_launch_count(self._h))
+
+    def set_option(self, name: str, value: int):
+        capi.check(capi.lib().bvhgpu_set_option(self._h, name.encode(), int(value)))
+
+    def get_metric(self, name: str) -> float:
+        out = C.c_double(0.0)
+        capi.check(capi.lib().bvhgpu_get_metric(self._h, name.encode(), C.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            capi.lib().bvhgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def _gather_aabbs(shapes, prec):
+    d = BY_PREC[prec]
+    if isinstance(shapes, np.ndarray):
+        return np.ascontiguousarray(shapes, dtype=d["aabb"])
+    out = np.zeros(len(shapes), dtype=d["aabb"])
+    for i, s in enumerate(shapes):                      # Bounded::aabb(), once per shape
+        a = s.aabb()
+        out[i]["min"] = a[0]
+        out[i]["max"] = a[1]
+    return out
+
+
+class Ray:
+    """Ray<T,3> (src/ray/ray_impl.rs:17-29).  Ray.new normalises on the device (bvhgpu_rays_new_dev_*)."""
+
+    @staticmethod
+    def new(origins, directions, prec: str = "f32", ctx: Context | None = None) -> np.ndarray:
+        import torch
+
+        d = BY_PREC[prec]
+        ctx = ctx or Context.default()
+        o = np.ascontiguousarray(origins, dtype=d["scalar"]).reshape(-1, 3)
+        v = np.ascontiguousarray(directions, dtype=d["scalar"]).reshape(-1, 3)
+        n = len(o)
+        dev = torch.device("cuda", ctx.device)
+        to, tv = torch.from_numpy(o).to(dev), torch.from_numpy(v).to(dev)
+        out = torch.empty(n * d["ray"].itemsize, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        capi.check(getattr(capi.lib(), f"bvhgpu_rays_new_dev_{d['suffix']}")(ctx._h, to.data_ptr(), tv.data_ptr(), n, out.data_ptr()))
+        ctx.synchronize()
+        return out.cpu().numpy().view(d["ray"]).copy()
+
+
+class FlatBvh:
+    """FlatBvh = Vec<FlatNode> (src/flat_bvh.rs:153) produced by Bvh.flatten(); traversal runs on the device tree."""
+
+    def __init__(self, bvh: "Bvh", nodes: np.ndarray):
+        self._bvh = bvh
+        self.nodes = nodes
+
+    def __len__(self):
+        return len(self.nodes)
+
+    def traverse(self, ray, shapes=None):
+        return self._bvh._traverse_one(ray, shapes, capi.TRAVERSE_FLAT)
+
+    def traverse_batch(self, rays):
+        return self._bvh.traverse_batch(rays, mode=capi.TRAVERSE_FLAT)
+
+
+class Bvh:
+    """Device-resident Bvh<T,3>."""
+
+    def __init__(self, handle, prec: str, ctx: Context):
+        self._h = handle
+        self.prec = prec
+        self.ctx = ctx
+        self._d = BY_PREC[prec]
+        self._nodes = None
+        self._node_index = None
+
+    # ---- construction ----------------------------------------------------------------------------
+    @classmethod
+    def build(cls, shapes, prec: str = "f32", ctx: Context | None = None, mode: int = capi.BUILD_EXACT_SAH) -> "Bvh":
+        ctx = ctx or Context.default()
+        d = BY_PREC[prec]
+        aabbs = _gather_aabbs(shapes, prec)
+        h = C.c_void_p()
+        capi.check(getattr(capi.lib(), f"bvhgpu_build_{d['suffix']}")(ctx._h, _ptr(aabbs), len(aabbs), mode, C.byref(h)))
+        bvh = cls(h, prec, ctx)
+        if not isinstance(shapes, np.ndarray) and len(shapes) and hasattr(shapes[0], "set_bh_node_index"):
+            for s, ni in zip(shapes, bvh.node_index):    # BHShape::set_bh_node_index
+                s.set_bh_node_index(int(ni))
+        return bvh
+
+    build_par = build          # rayon is off the hot path: same builder (bounding_hierarchy.rs:170-177)
+
+    @classmethod
+    def build_dev(cls, dev_ptr: int, n: int, prec: str = "f32", ctx: Context | None = None, mode: int = capi.BUILD_EXACT_SAH) -> "Bvh":
+        """AABBs already on the device (C-ABI layout); asynchronous on the context's stream."""
+        ctx = ctx or Context.default()
+        d = BY_PREC[prec]
+        h = C.c_void_p()
+        capi.check(getattr(capi.lib(), f"bvhgpu_build_dev_{d['suffix']}")(ctx._h, C.c_void_p(dev_ptr), n, mode, C.byref(h)))
+        return cls(h, prec, ctx)
+
+    @classmethod
+    def from_nodes(cls, nodes: np.ndarray, shapes, prec: str = "f32", ctx: Context | None = None) -> "Bvh":
+        ctx = ctx or Context.default()
+        d = BY_PREC[prec]
+        nodes = np.ascontiguousarray(nodes, dtype=d["node"])
+        aabbs = _gather_aabbs(shapes, prec)
+        h = C.c_void_p()
+        capi.check(getattr(capi.lib(), f"bvhgpu_tree_from_nodes_{d['suffix']}")(ctx._h, _ptr(nodes), len(nodes), _ptr(aabbs), len(aabbs), C.byref(h)))
+        return cls(h, prec, ctx)
+
+    def free(self):
+        if self._h:
+            getattr(capi.lib(), f"bvhgpu_tree_free_{self._d['suffix']}")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- Bvh.nodes / node indices ------------------------------------------------------------------
+    @property
+    def num_shapes(self) -> int:
+        return int(getattr(capi.lib(), f"bvhgpu_tree_num_shapes_{self._d['suffix']}")(self._h))
+
+    def _materialise(self):
+        if self._nodes is None:
+            n = self.num_shapes
+            nodes = np.zeros(max(2 * n - 1, 0), dtype=self._d["node"])
+            idx = np.zeros(n, dtype=np.uint32)
+            capi.check(getattr(capi.lib(), f"bvhgpu_tree_nodes_{self._d['suffix']}")(self._h, _ptr(nodes), _ptr(idx)))
+            self._nodes, self._node_index = nodes, idx
+
+    @property
+    def nodes(self) -> np.ndarray:
+        self._materialise()
+        return self._nodes
+
+    @property
+    def node_index(self) -> np.ndarray:
+        self._materialise()
+        return self._node_index
+
+    # ---- flatten -----------------------------------------------------------------------------------
+    def flatten(self) -> FlatBvh:
+        n = self.num_shapes
+        cap = 0 if n == 0 else (1 if n == 1 else 3 * n - 2)
+        out = np.zeros(cap, dtype=self._d["flat"])
+        ln = C.c_size_t(0)
+        capi.check(getattr(capi.lib(), f"bvhgpu_flatten_{self._d['suffix']}")(self._h, _ptr(out), cap, C.byref(ln)))
+        return FlatBvh(self, out[: ln.value])
+
+    # ---- traversal ---------------------------------------------------------------------------------
+    def traverse_batch(self, rays: np.ndarray, mode: int = capi.TRAVERSE_BVH, cap: int | None = None):
+        """CSR (offsets u32[nrays+1], hits u32[total]); hits of a ray are in the reference's DFS order."""
+        rays = np.ascontiguousarray(rays, dtype=self._d["ray"])
+        nrays = len(rays)
+        offsets = np.zeros(nrays + 1, dtype=np.uint32)
+        cap = max(4 * nrays, 1024) if cap is None else cap
+        hits = np.zeros(cap, dtype=np.uint32)
+        total = C.c_size_t(0)
+        fn = getattr(capi.lib(), f"bvhgpu_traverse_{self._d['suffix']}")
+        st = fn(self._h, mode, _ptr(rays), nrays, _ptr(offsets), _ptr(hits), cap, C.byref(total))
+        if st == capi.ERR_CAPACITY and total.value <= U32_MAX:
+            hits = np.zeros(total.value, dtype=np.uint32)
+            capi.check(getattr(capi.lib(), f"bvhgpu_traverse_fetch_{self._d['suffix']}")(self._h, _ptr(hits), total.value))
+        else:
+            capi.check(st)
+        return offsets, hits[: total.value]
+
+    def traverse_dev(self, rays_ptr: int, nrays: int, offsets_ptr: int, hits_ptr: int, cap: int, mode: int = capi.TRAVERSE_BVH,
+                     want_total: bool = False):
+        total = C.c_size_t(0)
+        fn = getattr(capi.lib(), f"bvhgpu_traverse_dev_{self._d['suffix']}")
+        capi.check(fn(self._h, mode, C.c_void_p(rays_ptr), nrays, C.c_void_p(offsets_ptr), C.c_void_p(hits_ptr), cap,
+                      C.byref(total) if want_total else None))
+        return total.value if want_total else None
+
+    def traverse_stats(self):
+        out = (C.c_uint64 * 2)()
+        capi.check(getattr(capi.lib(), f"bvhgpu_traverse_stats_{self._d['suffix']}")(self._h, out))
+        return int(out[0]), int(out[1])
+
+    def _traverse_one(self, ray, shapes, mode):
+        rays = np.ascontiguousarray(ray, dtype=self._d["ray"]).reshape(1)
+        _, hits = self.traverse_batch(rays, mode)
+        return [shapes[int(h)] for h in hits] if shapes is not None else hits.tolist()
+
+    def traverse(self, ray, shapes: Sequence | None = None):
+        """Bvh::traverse: the shapes (or shape indices) whose AABB the ray hits, reference order."""
+        return self._traverse_one(ray, shapes, capi.TRAVERSE_BVH)
+
+    def traverse_iterator(self, ray, shapes: Sequence | None = None) -> Iterable:
+        """BvhTraverseIterator (src/bvh/iter.rs): same sequence as traverse, lazily yielded on the host."""
+        return iter(self._traverse_one(ray, shapes, capi.TRAVERSE_BVH))
+
+    # ---- extras ------------------------------------------------------------------------------------
+    def sah_cost(self):
+        out = (C.c_double * 2)()
+        capi.check(getattr(capi.lib(), f"bvhgpu_sah_cost_{self._d['suffix']}")(self._h, out))
+        return float(out[0]), float(out[1])
+
+    def refit(self, shapes):
+        aabbs = _gather_aabbs(shapes, self.prec)
+        capi.check(getattr(capi.lib(), f"bvhgpu_refit_{self._d['suffix']}")(self._h, _ptr(aabbs), len(aabbs)))
+        self._nodes = self._node_index = None

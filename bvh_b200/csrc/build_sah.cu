@@ -1,0 +1,727 @@
+// bvh_b200/csrc/build_sah.cu -- exact 6-bucket SAH builder, bit-identical to the reference's
+// Bvh::build (src/bvh/bvh_impl.rs:53-96, src/bvh/bvh_node.rs:81-279, src/utils.rs:59-109).
+//
+// B200-first design (DESIGN.md "builder"): the reference recursion is re-expressed as ONE
+// persistent kernel in which every warp is a worker pulling tasks from a device-wide ticket
+// queue.  A task is a node of the tree = a contiguous range of the shape-index array:
+//
+//   SEG      (range <= TILE shapes): one warp bins the range into the 6 SAH buckets (shared
+//            memory min/max on order-preserving integer keys), evaluates the 5 splits in the
+//            reference's operation order, performs the STABLE 6-way partition with warp ballots
+//            (the reference rewrites indices bucket by bucket, bvh_node.rs:250-272 -- the order
+//            is observable through the degenerate "halve by position" branch, :114-124), writes
+//            the node, then continues depth-first with the left child; the right child goes to
+//            a per-warp shared-memory stack (small) or to the global queue (large).
+//   BIN / SCATTER tiles (range > TILE): the range is cut into TILE-sized tiles processed by
+//            different warps; per-tile bucket counts are prefix-summed by the last finishing
+//            tile so that the multi-warp partition is still stable; the last SCATTER tile emits
+//            the node and creates the children.
+//
+// No level-wide barriers, no host round trips, one launch for the whole tree.  Node indices
+// follow the reference rule child_l = i+1, child_r = i + 2*n_l (bvh_node.rs:138-142), so the
+// output array IS the reference's preorder `Bvh.nodes`.
+#include "internal.h"
+
+namespace bvhb200 {
+
+constexpr int TILE = 256;              // shapes per tile task of a multi-warp segment
+constexpr int WARPS_PER_CTA = 8;
+constexpr int LOCAL_STACK = 24;        // per-warp DFS stack (entries)
+constexpr uint32_t LOCAL_MAX = 32;     // right children up to this size stay on the warp's own stack
+constexpr uint32_t KIND_SEG = 0, KIND_BIN = 1, KIND_SCATTER = 2;
+
+template <class T> struct __align__(16) BTask {
+    uint32_t start, count, node, parent_buf;   // parent_buf: bit31 = which index buffer holds the range
+    T ab[6];                                   // aabb_bounds      (min xyz, max xyz)
+    T cb[6];                                   // centroid_bounds
+};
+template <class T> struct __align__(16) QSlot {
+    BTask<T> t;
+    uint32_t kind, a, b, pad;                  // tile tasks: a = big-segment id, b = tile index
+};
+template <class T> struct __align__(16) BigSeg {
+    using Key = typename Traits<T>::Key;
+    BTask<T> t;
+    Key keys[72];                              // [bucket][12]: aabb min3, aabb max3, centroid min3, centroid max3
+    uint32_t cnt[6]; uint32_t tiles; uint32_t bin_done;
+    uint32_t scat_done; uint32_t nl; uint32_t pad0[2];
+    uint32_t base[6]; uint32_t pad1[2];
+    T child[24];                               // lab, lcb, rab, rcb of the chosen split
+};
+template <class T> struct __align__(16) WarpScratch {
+    using Key = typename Traits<T>::Key;
+    Key keys[72];
+    uint32_t cnt[8];
+    T child[24];
+    BTask<T> stack[LOCAL_STACK];
+};
+struct BuildCtl {
+    uint32_t head, tail, leaves_done, error;
+    unsigned long long t_start;
+    uint32_t pad[2];
+};
+
+template <class T> struct BuildParams {
+    using Tr = Traits<T>;
+    const typename Tr::DAabb* aabb;
+    uint32_t* idx[2];
+    uint8_t* bkt;
+    typename Tr::Node* nodes;
+    uint32_t* node_index;
+    uint32_t* node_start;
+    QSlot<T>* q;
+    uint32_t* qseq;
+    uint32_t qmask;
+    BigSeg<T>* big;
+    uint32_t* tilecnt;
+    BuildCtl* ctl;
+    typename Tr::Key* rootkeys;     // 12 keys: AB min3 max3, CB min3 max3
+    BuildStatus* status;
+    uint32_t n;
+    unsigned long long timeout_ns;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class S> __device__ __forceinline__ void load_struct_cg(S& dst, const S* src) {
+    static_assert(sizeof(S) % 16 == 0, "16-byte granules");
+    uint4* d = reinterpret_cast<uint4*>(&dst);
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 16); ++i) d[i] = __ldcg(s + i);
+}
+template <class S> __device__ __forceinline__ void store_struct_cg(S* dst, const S& src) {
+    static_assert(sizeof(S) % 16 == 0, "16-byte granules");
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint4* s = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 16); ++i) __stcg(d + i, s[i]);
+}
+
+template <class T> __device__ __forceinline__ bool key_is_min(int e) { const int k = e % 12; return k < 3 || (k >= 6 && k < 9); }
+
+template <class T> __device__ __forceinline__ void zero_bins(WarpScratch<T>* ws) {
+    using Tr = Traits<T>;
+    for (int e = lane_id(); e < 72; e += 32) ws->keys[e] = key_is_min<T>(e) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+    if (lane_id() < 8) ws->cnt[lane_id()] = 0;
+    __syncwarp();
+}
+
+// Split axis and extent: Aabb::largest_axis on the centroid bounds (aabb_impl.rs:594-596, first
+// maximum wins) and split_axis_size (bvh_node.rs:107-108).
+template <class T> __device__ __forceinline__ void split_axis(const BTask<T>& t, int& axis, T& ext, T& cbmin) {
+    const T sx = sub_rn(t.cb[3], t.cb[0]), sy = sub_rn(t.cb[4], t.cb[1]), sz = sub_rn(t.cb[5], t.cb[2]);
+    axis = 0; ext = sx; cbmin = t.cb[0];
+    if (sy > ext) { axis = 1; ext = sy; cbmin = t.cb[1]; }
+    if (sz > ext) { axis = 2; ext = sz; cbmin = t.cb[2]; }
+}
+
+// Bucket assignment + Bucket::add_aabb (bvh_node.rs:204-222, utils.rs:78-83) for positions [p0,p1).
+template <class T>
+__device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T>* ws, const uint32_t* __restrict__ src,
+                                          uint32_t seg_start, uint32_t p0, uint32_t p1, int axis, T cbmin, T ext,
+                                          bool degenerate, uint32_t half, bool store_bkt, uint32_t& last_id, int& last_b) {
+    const uint32_t lane = lane_id();
+    const T K = sub_rn(T(6), T(0.01));                 // T::from(NUM_BUCKETS) - T::from(0.01), bvh_node.rs:214-215
+    for (uint32_t base = p0; base < p1; base += 32) {
+        const uint32_t pos = base + lane;
+        uint32_t id = 0;
+        int b = 0;
+        if (pos < p1) {
+            id = __ldcg(src + pos);
+            T mn[3], mx[3], c[3];
+            load_aabb(P.aabb + id, mn, mx);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = center1(mn[k], mx[k]);
+            if (degenerate) {
+                b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
+            } else {
+                const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
+                const T rel = div_rn(sub_rn(ca, cbmin), ext);
+                b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
+                b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
+            }
+            if (store_bkt) P.bkt[pos] = (uint8_t)b;
+            typename Traits<T>::Key* kb = ws->keys + b * 12;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicMin(kb + k, f2key(mn[k]));
+                atomicMax(kb + 3 + k, f2key(mx[k]));
+                atomicMin(kb + 6 + k, f2key(c[k]));
+                atomicMax(kb + 9 + k, f2key(c[k]));
+            }
+            atomicAdd(&ws->cnt[b], 1u);
+        }
+        last_id = id;
+        last_b = b;
+    }
+    __syncwarp();
+}
+
+// The 5 candidate splits (bvh_node.rs:231-247): lane s evaluates split s; the strict `<`
+// first-wins argmin is replayed sequentially over the 5 costs.  Leaves the chosen child bounds in
+// ws->child (lab, lcb, rab, rcb) -- Aabb::empty() for all four when no cost is < +inf -- and
+// returns the left shape count.
+template <class T>
+__device__ __forceinline__ uint32_t split_eval(WarpScratch<T>* ws, const T parent_ab[6], bool degenerate) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    const uint32_t lane = lane_id();
+    const int s = degenerate ? 0 : (lane < 5 ? (int)lane : 4);
+    Key L[12], R[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { L[k] = R[k] = key_is_min<T>(k) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF; }
+    uint32_t nL = 0, nR = 0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const bool inL = b <= s;
+        const uint32_t c = ws->cnt[b];
+        if (inL) nL += c; else nR += c;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const Key v = ws->keys[b * 12 + k];
+            if (key_is_min<T>(k)) { if (inL) L[k] = v < L[k] ? v : L[k]; else R[k] = v < R[k] ? v : R[k]; }
+            else                  { if (inL) L[k] = v > L[k] ? v : L[k]; else R[k] = v > R[k] ? v : R[k]; }
+        }
+    }
+    T lmn[3], lmx[3], rmn[3], rmx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lmn[k] = key2f(L[k]); lmx[k] = key2f(L[3 + k]); rmn[k] = key2f(R[k]); rmx[k] = key2f(R[3 + k]); }
+    // cost = (T(nL)*SA(L) + T(nR)*SA(R)) / SA(aabb_bounds), bvh_node.rs:236-238
+    const T cost = div_rn(add_rn(mul_rn((T)nL, surface_area(lmn, lmx)), mul_rn((T)nR, surface_area(rmn, rmx))),
+                          surface_area(parent_ab, parent_ab + 3));
+    int best = 0;
+    bool found = degenerate;
+    if (!degenerate) {
+        T min_cost = Tr::inf();
+#pragma unroll
+        for (int s2 = 0; s2 < 5; ++s2) {
+            const T c = __shfl_sync(0xffffffffu, cost, s2);
+            if (c < min_cost) { best = s2; min_cost = c; found = true; }
+        }
+    }
+    if ((int)lane == best) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            ws->child[k]      = found ? key2f(L[k])     : (k < 3 ? Tr::inf() : -Tr::inf());
+            ws->child[6 + k]  = found ? key2f(L[6 + k]) : (k < 3 ? Tr::inf() : -Tr::inf());
+            ws->child[12 + k] = found ? key2f(R[k])     : (k < 3 ? Tr::inf() : -Tr::inf());
+            ws->child[18 + k] = found ? key2f(R[6 + k]) : (k < 3 ? Tr::inf() : -Tr::inf());
+        }
+    }
+    const uint32_t nl = __shfl_sync(0xffffffffu, nL, best);
+    __syncwarp();
+    return nl;
+}
+
+// Stable 6-way partition of positions [p0,p1) (bvh_node.rs:250-272).  base[b] = next free
+// destination of bucket b (warp-uniform registers, advanced here).
+template <class T>
+__device__ __forceinline__ void scatter_range(const BuildParams<T>& P, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                              uint32_t p0, uint32_t p1, uint32_t base[6], bool use_cached,
+                                              uint32_t cached_id, int cached_b) {
+    const uint32_t lane = lane_id();
+    const uint32_t lt = lanemask_lt();
+    for (uint32_t bpos = p0; bpos < p1; bpos += 32) {
+        const uint32_t pos = bpos + lane;
+        const bool valid = pos < p1;
+        uint32_t id = cached_id;
+        int b = cached_b;
+        if (!use_cached && valid) { id = __ldcg(src + pos); b = (int)__ldcg(P.bkt + pos); }
+        uint32_t dest = 0;
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) {
+            const uint32_t m = __ballot_sync(0xffffffffu, valid && b == bb);
+            if (b == bb) dest = base[bb] + __popc(m & lt);
+            base[bb] += __popc(m);
+        }
+        if (valid) __stcg(dst + dest, id);
+    }
+    __syncwarp();
+}
+
+template <class T> __device__ __forceinline__ void write_leaf(const BuildParams<T>& P, uint32_t node, uint32_t parent, uint32_t shape, uint32_t start) {
+    using Tr = Traits<T>;
+    typename Tr::Node nd;
+    nd.parent = parent; nd.child_l = BVH_INVALID; nd.child_r = BVH_INVALID; nd.shape = shape;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { nd.l_aabb.min[k] = nd.r_aabb.min[k] = Tr::inf(); nd.l_aabb.max[k] = nd.r_aabb.max[k] = -Tr::inf(); }
+    store_struct_cg(P.nodes + node, nd);
+    P.node_index[shape] = node;                 // Shapes::set_node_index, bvh_node.rs:103
+    P.node_start[node] = start;
+}
+
+// Writes the inner node (bvh_node.rs:138-151), emits leaves for single-shape children (:95-104) and
+// returns the children that still have to be split in out[0..nc).
+template <class T>
+__device__ __forceinline__ int finish_node(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t nl,
+                                           bool moved, BTask<T> out[2], uint32_t& leaves) {
+    using Tr = Traits<T>;
+    const uint32_t buf = t.parent_buf >> 31, parent = t.parent_buf & 0x7FFFFFFFu;
+    const uint32_t nbuf = moved ? (buf ^ 1u) : buf;
+    const uint32_t cl = t.node + 1, cr = cl + 2 * nl - 1;
+    if (lane_id() == 0) {
+        typename Tr::Node nd;
+        nd.parent = parent; nd.child_l = cl; nd.child_r = cr; nd.shape = t.count;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            nd.l_aabb.min[k] = ws->child[k];      nd.l_aabb.max[k] = ws->child[3 + k];
+            nd.r_aabb.min[k] = ws->child[12 + k]; nd.r_aabb.max[k] = ws->child[15 + k];
+        }
+        store_struct_cg(P.nodes + t.node, nd);
+        P.node_start[t.node] = t.start;
+    }
+    int nc = 0;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t cstart = side ? t.start + nl : t.start;
+        const uint32_t ccount = side ? t.count - nl : nl;
+        const uint32_t cnode = side ? cr : cl;
+        if (ccount == 1) {
+            if (lane_id() == 0) write_leaf(P, cnode, t.node, __ldcg(P.idx[nbuf] + cstart), cstart);
+            leaves += 1;
+        } else {
+            BTask<T>& c = out[nc++];
+            c.start = cstart; c.count = ccount; c.node = cnode; c.parent_buf = t.node | (nbuf << 31);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { c.ab[k] = ws->child[side * 12 + k]; c.cb[k] = ws->child[side * 12 + 6 + k]; }
+        }
+    }
+    return nc;
+}
+
+// ---- queue ---------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ void push_seg(const BuildParams<T>& P, const BTask<T>& t) {
+    if (lane_id() == 0) {
+        const uint32_t tk = atomicAdd(&P.ctl->tail, 1u);
+        const uint32_t slot = tk & P.qmask;
+        store_struct_cg(&P.q[slot].t, t);
+        __stcg(reinterpret_cast<uint4*>(&P.q[slot].kind), make_uint4(KIND_SEG, 0u, 0u, 0u));
+        __threadfence();
+        st_release(P.qseq + slot, tk + 1u);
+    }
+    __syncwarp();
+}
+template <class T> __device__ __forceinline__ void push_tiles(const BuildParams<T>& P, uint32_t kind, uint32_t sid, uint32_t tiles) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(&P.ctl->tail, tiles);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t j = lane_id(); j < tiles; j += 32) {
+        const uint32_t tk = base + j, slot = tk & P.qmask;
+        __stcg(reinterpret_cast<uint4*>(&P.q[slot].kind), make_uint4(kind, sid, j, 0u));
+        __threadfence();
+        st_release(P.qseq + slot, tk + 1u);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t tile_slot(uint32_t p, bool first) { return 2u * (p / TILE) + (first ? 1u : 0u); }
+
+template <class T> __device__ __forceinline__ void create_big(const BuildParams<T>& P, const BTask<T>& t) {
+    using Tr = Traits<T>;
+    BigSeg<T>* B = P.big + t.start / TILE;
+    const uint32_t tiles = (t.count + TILE - 1) / TILE;
+    const uint32_t lane = lane_id();
+    if (lane == 0) store_struct_cg(&B->t, t);
+    for (int e = lane; e < 72; e += 32) __stcg(&B->keys[e], key_is_min<T>(e) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF);
+    if (lane < 6) __stcg(&B->cnt[lane], 0u);
+    if (lane == 6) __stcg(&B->tiles, tiles);
+    if (lane == 7) __stcg(&B->bin_done, 0u);
+    if (lane == 8) __stcg(&B->scat_done, 0u);
+    __threadfence();
+    __syncwarp();
+    __threadfence();
+    push_tiles(P, KIND_BIN, t.start / TILE, tiles);
+}
+
+template <class T>
+__device__ __forceinline__ void dispatch_children(const BuildParams<T>& P, BTask<T> ch[2], int nc) {
+    for (int i = 0; i < nc; ++i) {
+        if (ch[i].count > (uint32_t)TILE) create_big(P, ch[i]);
+        else push_seg(P, ch[i]);
+    }
+}
+
+// ---- SEG: one warp owns the whole range; depth-first continuation ------------------------------------
+template <class T>
+__device__ void process_seg(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T> t, uint32_t& leaves) {
+    using Tr = Traits<T>;
+    int sp = 0;
+    for (;;) {
+        int axis; T ext, cbmin;
+        split_axis(t, axis, ext, cbmin);
+        const bool degenerate = ext < Tr::eps();            // bvh_node.rs:114
+        const uint32_t buf = t.parent_buf >> 31;
+        const uint32_t p0 = t.start, p1 = t.start + t.count;
+        const bool single = t.count <= 32;
+        zero_bins(ws);
+        uint32_t cid = 0; int cb = 0;
+        bin_range(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !single && !degenerate, cid, cb);
+        const uint32_t nl = split_eval(ws, t.ab, degenerate);
+        if (!degenerate) {
+            uint32_t base[6];
+            uint32_t run = t.start;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) { base[b] = run; run += ws->cnt[b]; }
+            scatter_range(P, P.idx[buf], P.idx[buf ^ 1u], p0, p1, base, single, cid, cb);
+        }
+        BTask<T> ch[2];
+        const int nc = finish_node(P, ws, t, nl, !degenerate, ch, leaves);
+        if (nc == 2) {
+            if (ch[1].count <= LOCAL_MAX && sp < LOCAL_STACK) {
+                if (lane_id() == 0) ws->stack[sp] = ch[1];
+                ++sp;
+                __syncwarp();
+            } else {
+                push_seg(P, ch[1]);
+            }
+            t = ch[0];
+        } else if (nc == 1) {
+            t = ch[0];
+        } else {
+            if (sp == 0) return;
+            --sp;
+            t = ws->stack[sp];
+            __syncwarp();
+        }
+    }
+}
+
+// ---- BIN tile of a multi-warp segment -------------------------------------------------------------
+template <class T>
+__device__ void finish_big(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t nl, bool moved, uint32_t& leaves) {
+    BTask<T> ch[2];
+    const int nc = finish_node(P, ws, t, nl, moved, ch, leaves);
+    dispatch_children(P, ch, nc);
+}
+
+template <class T>
+__device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, uint32_t sid, uint32_t k, uint32_t& leaves) {
+    using Tr = Traits<T>;
+    BigSeg<T>* B = P.big + sid;
+    const uint32_t lane = lane_id();
+    BTask<T> t;
+    load_struct_cg(t, &B->t);
+    const uint32_t tiles = __ldcg(&B->tiles);
+    int axis; T ext, cbmin;
+    split_axis(t, axis, ext, cbmin);
+    const bool degenerate = ext < Tr::eps();
+    const uint32_t buf = t.parent_buf >> 31;
+    const uint32_t p0 = t.start + k * TILE;
+    const uint32_t pend = t.start + t.count;
+    const uint32_t p1 = p0 + TILE < pend ? p0 + TILE : pend;
+    zero_bins(ws);
+    uint32_t cid; int cb;
+    bin_range(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !degenerate, cid, cb);
+    // flush this tile's buckets into the segment's global buckets
+    for (int e = lane; e < 72; e += 32) {
+        const typename Tr::Key v = ws->keys[e];
+        if (key_is_min<T>(e)) { if (v != Tr::KEY_POS_INF) atomicMin(&B->keys[e], v); }
+        else                  { if (v != Tr::KEY_NEG_INF) atomicMax(&B->keys[e], v); }
+    }
+    const uint32_t slot = tile_slot(p0, k == 0);
+    if (lane < 6) {
+        const uint32_t c = ws->cnt[lane];
+        __stcg(&P.tilecnt[slot * 6 + lane], c);
+        if (c) atomicAdd(&B->cnt[lane], c);
+    }
+    __threadfence();
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) last = (atomicAdd(&B->bin_done, 1u) == tiles - 1) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    // ---- last tile: choose the split for the whole segment ----
+    for (int e = lane; e < 72; e += 32) ws->keys[e] = __ldcg(&B->keys[e]);
+    if (lane < 6) ws->cnt[lane] = __ldcg(&B->cnt[lane]);
+    __syncwarp();
+    const uint32_t nl = split_eval(ws, t.ab, degenerate);
+    if (degenerate) {                       // halves stay in place: children can be created right away
+        finish_big(P, ws, t, nl, false, leaves);
+        return;
+    }
+    uint32_t run = t.start;
+    uint32_t basev = 0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) { if ((int)lane == b) basev = run; run += ws->cnt[b]; }
+    if (lane < 6) __stcg(&B->base[lane], basev);
+    if (lane == 6) __stcg(&B->nl, nl);
+    if (lane < 24) __stcg(&B->child[lane], ws->child[lane]);
+    // exclusive prefix of the per-tile bucket counts (keeps the multi-warp partition stable)
+    uint32_t running[6] = {0, 0, 0, 0, 0, 0};
+    for (uint32_t j0 = 0; j0 < tiles; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < tiles;
+        const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const uint32_t c = valid ? __ldcg(&P.tilecnt[sj * 6 + b]) : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+            if (valid) __stcg(&P.tilecnt[sj * 6 + b], running[b] + incl - c);
+            running[b] += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    __threadfence();
+    push_tiles(P, KIND_SCATTER, sid, tiles);
+}
+
+template <class T>
+__device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws, uint32_t sid, uint32_t k, uint32_t& leaves) {
+    BigSeg<T>* B = P.big + sid;
+    const uint32_t lane = lane_id();
+    BTask<T> t;
+    load_struct_cg(t, &B->t);
+    const uint32_t tiles = __ldcg(&B->tiles);
+    const uint32_t buf = t.parent_buf >> 31;
+    const uint32_t p0 = t.start + k * TILE;
+    const uint32_t pend = t.start + t.count;
+    const uint32_t p1 = p0 + TILE < pend ? p0 + TILE : pend;
+    const uint32_t slot = tile_slot(p0, k == 0);
+    uint32_t base[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) base[b] = __ldcg(&B->base[b]) + __ldcg(&P.tilecnt[slot * 6 + b]);
+    scatter_range(P, P.idx[buf], P.idx[buf ^ 1u], p0, p1, base, false, 0u, 0);
+    __threadfence();
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) last = (atomicAdd(&B->scat_done, 1u) == tiles - 1) ? 1u : 0u;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    const uint32_t nl = __ldcg(&B->nl);
+    if (lane < 24) ws->child[lane] = __ldcg(&B->child[lane]);
+    __syncwarp();
+    finish_big(P, ws, t, nl, true, leaves);
+}
+
+// ---- the persistent kernel -------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T> P) {
+    __shared__ WarpScratch<T> wsall[WARPS_PER_CTA];
+    WarpScratch<T>* ws = &wsall[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    uint32_t leaves = 0;
+    for (;;) {
+        uint32_t ticket = 0, stop = 0;
+        if (lane == 0) {
+            ticket = atomicAdd(&P.ctl->head, 1u);
+            const uint32_t* seq = P.qseq + (ticket & P.qmask);
+            uint32_t spins = 0, ns = 32;
+            for (;;) {
+                if (ld_acquire(seq) == ticket + 1u) break;
+                if ((spins & 7u) == 0u) {
+                    if (ld_relaxed(&P.ctl->leaves_done) >= P.n || ld_relaxed(&P.ctl->error) != 0u) { stop = 1; break; }
+                }
+                if ((++spins & 1023u) == 0u) {
+                    if (global_timer_ns() - *(volatile unsigned long long*)&P.ctl->t_start > P.timeout_ns) {
+                        atomicExch(&P.ctl->error, (uint32_t)BVHGPU_ERR_TIMEOUT);
+                        stop = 1;
+                        break;
+                    }
+                }
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
+            }
+        }
+        stop = __shfl_sync(0xffffffffu, stop, 0);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (stop) break;
+        __threadfence();
+        QSlot<T> s;
+        load_struct_cg(s, P.q + (ticket & P.qmask));
+        if (s.kind == KIND_SEG) process_seg(P, ws, s.t, leaves);
+        else if (s.kind == KIND_BIN) process_bin_tile(P, ws, s.a, s.b, leaves);
+        else process_scatter_tile(P, ws, s.a, s.b, leaves);
+        if (leaves) {
+            __threadfence();
+            if (lane == 0) atomicAdd(&P.ctl->leaves_done, leaves);
+            leaves = 0;
+        }
+    }
+}
+
+// ---- prep: ABI layout -> device layout, NaN check, scene bounds (joint_aabb_of_shapes, utils.rs:97-109) ---
+template <class T>
+__global__ void __launch_bounds__(256) prep_kernel(const typename Traits<T>::Aabb* __restrict__ in, uint32_t n,
+                                                   typename Traits<T>::DAabb* __restrict__ out, uint32_t* __restrict__ idx0,
+                                                   typename Traits<T>::Key* rootkeys, uint32_t* nan_flag) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    __shared__ Key sk[12];
+    if (threadIdx.x < 12) sk[threadIdx.x] = key_is_min<T>(threadIdx.x) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+    __syncthreads();
+    Key k[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) k[e] = key_is_min<T>(e) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+    bool nan = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const T* p = reinterpret_cast<const T*>(in + i);
+        T mn[3], mx[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { mn[c] = p[c]; mx[c] = p[3 + c]; nan |= (mn[c] != mn[c]) | (mx[c] != mx[c]); }
+        typename Tr::DAabb d;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { d.min[c] = mn[c]; d.max[c] = mx[c]; }
+        if constexpr (sizeof(T) == 4) { d.pad0 = 0; d.pad1 = 0; }
+        out[i] = d;
+        if (idx0) idx0[i] = i;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const T ctr = center1(mn[c], mx[c]);
+            const Key kmn = f2key(mn[c]), kmx = f2key(mx[c]), kc = f2key(ctr);
+            k[c] = kmn < k[c] ? kmn : k[c];
+            k[3 + c] = kmx > k[3 + c] ? kmx : k[3 + c];
+            k[6 + c] = kc < k[6 + c] ? kc : k[6 + c];
+            k[9 + c] = kc > k[9 + c] ? kc : k[9 + c];
+        }
+    }
+    if (rootkeys) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            const Key r = key_is_min<T>(e) ? warp_min_key(k[e]) : warp_max_key(k[e]);
+            if (lane_id() == 0) { if (key_is_min<T>(e)) atomicMin(&sk[e], r); else atomicMax(&sk[e], r); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            if (key_is_min<T>(threadIdx.x)) atomicMin(&rootkeys[threadIdx.x], sk[threadIdx.x]);
+            else atomicMax(&rootkeys[threadIdx.x], sk[threadIdx.x]);
+        }
+    }
+    if (nan) atomicExch(nan_flag, 1u);
+}
+
+template <class T>
+__global__ void init_keys_kernel(typename Traits<T>::Key* rootkeys, BuildCtl* ctl, BuildStatus* status) {
+    using Tr = Traits<T>;
+    if (threadIdx.x < 12) rootkeys[threadIdx.x] = key_is_min<T>(threadIdx.x) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+    if (threadIdx.x == 0) {
+        ctl->head = ctl->tail = ctl->leaves_done = ctl->error = 0;
+        ctl->t_start = 0;
+        status->error = status->nan_found = status->tickets = status->leaves_done = 0;
+    }
+}
+
+template <class T> __global__ void init_root_kernel(BuildParams<T> P) {
+    BTask<T> t;
+    t.start = 0; t.count = P.n; t.node = 0; t.parent_buf = 0;      // root's parent_index is 0, bvh_impl.rs:80
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { t.ab[k] = key2f(P.rootkeys[k]); t.cb[k] = key2f(P.rootkeys[6 + k]); }
+    if (lane_id() == 0) P.ctl->t_start = global_timer_ns();
+    __syncwarp();
+    if (P.status->nan_found) {                                      // reference panics on NaN centroids: build nothing
+        if (lane_id() == 0) { P.ctl->error = (uint32_t)BVHGPU_ERR_NAN; }
+        return;
+    }
+    if (t.count > (uint32_t)TILE) create_big(P, t); else push_seg(P, t);
+}
+
+template <class T> __global__ void single_leaf_kernel(BuildParams<T> P) {
+    if (threadIdx.x == 0) { write_leaf(P, 0u, 0u, 0u, 0u); P.ctl->leaves_done = 1; }
+}
+
+template <class T> __global__ void finish_status_kernel(BuildCtl* ctl, BuildStatus* status, uint32_t n) {
+    if (threadIdx.x == 0) {
+        status->tickets = ctl->tail;
+        status->leaves_done = ctl->leaves_done;
+        uint32_t e = ctl->error;
+        if (status->nan_found) e = (uint32_t)BVHGPU_ERR_NAN;
+        if (e == 0 && ctl->leaves_done != n) e = (uint32_t)BVHGPU_ERR_INTERNAL;
+        status->error = e;
+    }
+}
+
+static uint32_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t)p; }
+
+template <class T>
+int convert_aabbs(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n,
+                  typename Traits<T>::DAabb* out, uint32_t* d_nan_flag) {
+    if (n == 0) return BVHGPU_OK;
+    const int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    prep_kernel<T><<<blocks, 256, 0, ctx->stream>>>(in_aabbs, n, out, nullptr, nullptr, d_nan_flag);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+template <class T>
+int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree) {
+    using Tr = Traits<T>;
+    cudaStream_t st = ctx->stream;
+    tree->ctx = ctx;
+    tree->n = n;
+    tree->n_nodes = n ? 2 * n - 1 : 0;
+    BVH_TRY(dalloc_t(ctx, &tree->d_status, 1));
+    BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), st));
+    if (n == 0) return BVHGPU_OK;
+    BVH_TRY(dalloc_t(ctx, &tree->d_aabb, n));
+    BVH_TRY(dalloc_t(ctx, &tree->d_nodes, tree->n_nodes));
+    BVH_TRY(dalloc_t(ctx, &tree->d_node_index, n));
+    BVH_TRY(dalloc_t(ctx, &tree->d_node_start, tree->n_nodes));
+
+    BuildParams<T> P{};
+    P.aabb = tree->d_aabb;
+    P.nodes = tree->d_nodes;
+    P.node_index = tree->d_node_index;
+    P.node_start = tree->d_node_start;
+    P.n = n;
+    P.status = tree->d_status;
+    P.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    const uint32_t qcap = next_pow2(std::max<uint64_t>(n, 1024) * 2);
+    P.qmask = qcap - 1;
+    const size_t nbig = (size_t)n / TILE + 2;
+    uint32_t *idx0 = nullptr, *idx1 = nullptr;
+    BVH_TRY(dalloc_t(ctx, &idx0, n));
+    BVH_TRY(dalloc_t(ctx, &idx1, n));
+    BVH_TRY(dalloc_t(ctx, &P.bkt, n));
+    BVH_TRY(dalloc_t(ctx, &P.q, qcap));
+    BVH_TRY(dalloc_t(ctx, &P.qseq, qcap));
+    BVH_TRY(dalloc_t(ctx, &P.big, nbig));
+    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 6));
+    BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
+    BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
+    P.idx[0] = idx0;
+    P.idx[1] = idx1;
+
+    init_keys_kernel<T><<<1, 32, 0, st>>>(P.rootkeys, P.ctl, P.status);
+    ctx->launches++;
+    const int pblocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    prep_kernel<T><<<pblocks, 256, 0, st>>>(in_aabbs, n, tree->d_aabb, idx0, P.rootkeys, &P.status->nan_found);
+    ctx->launches++;
+    if (n == 1) {
+        single_leaf_kernel<T><<<1, 32, 0, st>>>(P);
+        ctx->launches++;
+    } else {
+        BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
+        init_root_kernel<T><<<1, 32, 0, st>>>(P);
+        ctx->launches++;
+        int occ = 1;
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+        if (occ < 1) occ = 1;
+        // enough warps that every one has ~16 shapes of work, capped by what is co-resident
+        uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if (want < 1) want = 1;
+        const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
+        if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
+        build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+        ctx->launches++;
+        if (ctx->profile) { cudaEventRecord(ctx->ev_build[1], st); ctx->have_build = true; }
+    }
+    finish_status_kernel<T><<<1, 32, 0, st>>>(P.ctl, P.status, n);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    dfree(ctx, idx0); dfree(ctx, idx1); dfree(ctx, P.bkt); dfree(ctx, P.q); dfree(ctx, P.qseq);
+    dfree(ctx, P.big); dfree(ctx, P.tilecnt); dfree(ctx, P.ctl); dfree(ctx, P.rootkeys);
+    tree->status_pending = true;
+    return BVHGPU_OK;
+}
+
+template int build_exact_sah<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, Tree<float>*);
+template int build_exact_sah<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, Tree<double>*);
+template int convert_aabbs<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, DAabbF*, uint32_t*);
+template int convert_aabbs<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, DAabbD*, uint32_t*);
+
+}  // namespace bvhb200

@@ -1,0 +1,407 @@
+// bvh_b200/csrc/capi.cu -- the extern "C" surface declared in include/bvh_b200.h.
+#include "internal.h"
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+#include <new>
+#include <algorithm>
+
+namespace bvhb200 {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int dalloc(bvhgpu_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    BVH_CUDA_TRY(cudaMallocAsync(p, bytes, ctx->stream));
+    return BVHGPU_OK;
+}
+void dfree(bvhgpu_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// Resolve the deferred device status of a build (synchronises the stream once).
+template <class T> int resolve_status(Tree<T>* tree) {
+    if (!tree->status_pending) return BVHGPU_OK;
+    bvhgpu_ctx* ctx = tree->ctx;
+    BuildStatus h;
+    BVH_CUDA_TRY(cudaMemcpyAsync(&h, tree->d_status, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    tree->status_pending = false;
+    if (h.nan_found) { set_error("build: NaN coordinate in an input AABB (the reference panics here, src/bvh/bvh_node.rs:214-217)"); return BVHGPU_ERR_NAN; }
+    if (h.error == BVHGPU_ERR_TIMEOUT) { set_error("build: device watchdog fired (tickets=%u leaves=%u/%u)", h.tickets, h.leaves_done, tree->n); return BVHGPU_ERR_TIMEOUT; }
+    if (h.error) { set_error("build: device reported status %u (tickets=%u leaves=%u/%u)", h.error, h.tickets, h.leaves_done, tree->n); return (int)h.error; }
+    return BVHGPU_OK;
+}
+
+template int resolve_status<float>(Tree<float>*);
+template int resolve_status<double>(Tree<double>*);
+
+template <class T> static void tree_release(Tree<T>* t) {
+    if (!t) return;
+    bvhgpu_ctx* ctx = t->ctx;
+    if (ctx) {
+        dfree(ctx, t->d_aabb); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
+        dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
+    }
+}
+
+template <class T, class TreeT>
+static int build_impl(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* aabbs, size_t n, int mode, bool host_input, TreeT** out) {
+    if (!ctx || !out || (n && !aabbs)) { set_error("build: null argument"); return BVHGPU_ERR_INVALID; }
+    *out = nullptr;
+    if (n > (1ull << 30)) { set_error("build: n = %zu exceeds 2^30 shapes (u32 node indices)", n); return BVHGPU_ERR_INVALID; }
+    if (mode != BVHGPU_BUILD_EXACT_SAH) { set_error("build: mode %d not supported in this build (only BVHGPU_BUILD_EXACT_SAH)", mode); return BVHGPU_ERR_UNSUPPORTED; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    TreeT* tree = new (std::nothrow) TreeT();
+    if (!tree) { set_error("build: out of host memory"); return BVHGPU_ERR_INTERNAL; }
+    tree->ctx = ctx;
+    const typename Traits<T>::Aabb* d_in = aabbs;
+    typename Traits<T>::Aabb* staged = nullptr;
+    int rc = BVHGPU_OK;
+    if (host_input && n) {
+        rc = dalloc_t(ctx, &staged, n);
+        if (rc == BVHGPU_OK) {
+            cudaError_t e = cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { set_error("build: H2D copy failed: %s", cudaGetErrorString(e)); rc = BVHGPU_ERR_CUDA; }
+        }
+        d_in = staged;
+    }
+    if (rc == BVHGPU_OK) rc = build_exact_sah<T>(ctx, d_in, (uint32_t)n, tree);
+    if (staged) dfree(ctx, staged);
+    if (rc == BVHGPU_OK && host_input) rc = resolve_status(tree);     // host entry point reports errors eagerly
+    if (rc != BVHGPU_OK) { tree_release(tree); delete tree; return rc; }
+    *out = tree;
+    return BVHGPU_OK;
+}
+
+// Upload of an existing reference-layout Bvh: validate the preorder invariant on the host, derive the
+// per-node shape counts / range starts the device kernels rely on.
+template <class T, class TreeT>
+static int from_nodes_impl(bvhgpu_ctx* ctx, const typename Traits<T>::Node* nodes, size_t n_nodes,
+                           const typename Traits<T>::Aabb* aabbs, size_t n, TreeT** out) {
+    using Node = typename Traits<T>::Node;
+    if (!ctx || !out) { set_error("tree_from_nodes: null argument"); return BVHGPU_ERR_INVALID; }
+    *out = nullptr;
+    if ((n == 0) != (n_nodes == 0) || (n && n_nodes != 2 * n - 1)) { set_error("tree_from_nodes: n_nodes must be 2n-1"); return BVHGPU_ERR_INVALID; }
+    if (n > (1ull << 30)) { set_error("tree_from_nodes: too many shapes"); return BVHGPU_ERR_INVALID; }
+    if (n && (!nodes || !aabbs)) { set_error("tree_from_nodes: null argument"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    std::vector<Node> fixed(nodes, nodes + n_nodes);
+    std::vector<uint32_t> count(n_nodes), start(n_nodes), node_index(n, BVH_INVALID);
+    for (size_t ii = n_nodes; ii-- > 0;) {                       // children have larger indices in preorder
+        Node& nd = fixed[ii];
+        if (nd.child_l == BVH_INVALID) {
+            if (nd.shape >= n) { set_error("tree_from_nodes: leaf %zu has shape %u out of range", ii, nd.shape); return BVHGPU_ERR_INVALID; }
+            count[ii] = 1;
+        } else {
+            if (nd.child_l != ii + 1 || nd.child_l >= n_nodes || nd.child_r >= n_nodes || nd.child_r <= nd.child_l) {
+                set_error("tree_from_nodes: node %zu is not in the preorder layout Bvh::build emits (child_l must be i+1)", ii);
+                return BVHGPU_ERR_UNSUPPORTED;
+            }
+            if (nd.child_r != ii + 2 * (size_t)count[nd.child_l]) {
+                set_error("tree_from_nodes: node %zu: child_r != i + 2*n_l", ii);
+                return BVHGPU_ERR_UNSUPPORTED;
+            }
+            count[ii] = count[nd.child_l] + count[nd.child_r];
+            nd.shape = count[ii];
+        }
+    }
+    if (n_nodes && count[0] != n) { set_error("tree_from_nodes: tree does not cover all shapes"); return BVHGPU_ERR_INVALID; }
+    if (n_nodes) start[0] = 0;
+    for (size_t ii = 0; ii < n_nodes; ++ii) {
+        const Node& nd = fixed[ii];
+        if (nd.child_l == BVH_INVALID) { node_index[nd.shape] = (uint32_t)ii; continue; }
+        start[nd.child_l] = start[ii];
+        start[nd.child_r] = start[ii] + count[nd.child_l];
+        if (fixed[nd.child_l].parent != ii || fixed[nd.child_r].parent != ii) { set_error("tree_from_nodes: bad parent link under node %zu", ii); return BVHGPU_ERR_INVALID; }
+    }
+    for (size_t s = 0; s < n; ++s) if (node_index[s] == BVH_INVALID) { set_error("tree_from_nodes: shape %zu is in no leaf", s); return BVHGPU_ERR_INVALID; }
+
+    TreeT* tree = new (std::nothrow) TreeT();
+    if (!tree) { set_error("out of host memory"); return BVHGPU_ERR_INTERNAL; }
+    tree->ctx = ctx; tree->n = (uint32_t)n; tree->n_nodes = (uint32_t)n_nodes;
+    int rc = BVHGPU_OK;
+    typename Traits<T>::Aabb* staged = nullptr;
+    auto fail = [&](int code) { if (staged) dfree(ctx, staged); tree_release(tree); delete tree; return code; };
+    if ((rc = dalloc_t(ctx, &tree->d_status, 1)) != BVHGPU_OK) return fail(rc);
+    cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream);
+    if (n) {
+        if ((rc = dalloc_t(ctx, &tree->d_aabb, n)) != BVHGPU_OK) return fail(rc);
+        if ((rc = dalloc_t(ctx, &tree->d_nodes, n_nodes)) != BVHGPU_OK) return fail(rc);
+        if ((rc = dalloc_t(ctx, &tree->d_node_index, n)) != BVHGPU_OK) return fail(rc);
+        if ((rc = dalloc_t(ctx, &tree->d_node_start, n_nodes)) != BVHGPU_OK) return fail(rc);
+        if ((rc = dalloc_t(ctx, &staged, n)) != BVHGPU_OK) return fail(rc);
+        cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(tree->d_nodes, fixed.data(), n_nodes * sizeof(Node), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(tree->d_node_index, node_index.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(tree->d_node_start, start.data(), n_nodes * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if ((rc = convert_aabbs<T>(ctx, staged, (uint32_t)n, tree->d_aabb, &tree->d_status->nan_found)) != BVHGPU_OK) return fail(rc);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);       // the host vectors go out of scope
+        if (e != cudaSuccess) { set_error("tree_from_nodes: %s", cudaGetErrorString(e)); return fail(BVHGPU_ERR_CUDA); }
+        dfree(ctx, staged);
+        staged = nullptr;
+    }
+    *out = tree;
+    return BVHGPU_OK;
+}
+
+template <class T> static int tree_nodes_impl(Tree<T>* tree, typename Traits<T>::Node* out_nodes, uint32_t* out_node_index) {
+    if (!tree) { set_error("tree_nodes: null tree"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (tree->n == 0) return BVHGPU_OK;
+    if (out_nodes) BVH_CUDA_TRY(cudaMemcpyAsync(out_nodes, tree->d_nodes, sizeof(*out_nodes) * tree->n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_node_index) BVH_CUDA_TRY(cudaMemcpyAsync(out_node_index, tree->d_node_index, sizeof(uint32_t) * tree->n, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
+}
+
+template <class T> static int flatten_impl(Tree<T>* tree, typename Traits<T>::Flat* out, size_t cap, size_t* len) {
+    if (!tree) { set_error("flatten: null tree"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(build_flat(tree));
+    if (len) *len = tree->n_flat;
+    if (out) {
+        BVH_TRY(resolve_status(tree));
+        if (cap < tree->n_flat) { set_error("flatten: capacity %zu < %zu flat nodes", cap, tree->n_flat); return BVHGPU_ERR_CAPACITY; }
+        if (tree->n_flat) {
+            BVH_CUDA_TRY(cudaMemcpyAsync(out, tree->d_flat, sizeof(*out) * tree->n_flat, cudaMemcpyDeviceToHost, ctx->stream));
+            BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return BVHGPU_OK;
+}
+
+template <class T> static int ensure_result_buffers(Tree<T>* tree, size_t nrays, size_t hits_cap) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    if (tree->offsets_cap < nrays + 1) {
+        dfree(ctx, tree->d_offsets); tree->d_offsets = nullptr; tree->offsets_cap = 0;
+        BVH_TRY(dalloc_t(ctx, &tree->d_offsets, nrays + 1));
+        tree->offsets_cap = nrays + 1;
+    }
+    if (tree->hits_cap < hits_cap) {
+        dfree(ctx, tree->d_hits); tree->d_hits = nullptr; tree->hits_cap = 0;
+        BVH_TRY(dalloc_t(ctx, &tree->d_hits, hits_cap));
+        tree->hits_cap = hits_cap;
+    }
+    return BVHGPU_OK;
+}
+
+template <class T>
+static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>::Ray* rays, size_t nrays,
+                              uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total) {
+    if (!tree || (nrays && !rays) || !offsets) { set_error("traverse: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    typename Traits<T>::Ray* d_rays = nullptr;
+    if (nrays) {
+        BVH_TRY(dalloc_t(ctx, &d_rays, nrays));
+        BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(*rays) * nrays, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 4 * nrays), 1024);
+    size_t tot = 0;
+    int rc = BVHGPU_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_result_buffers(tree, nrays, want);
+        if (rc != BVHGPU_OK) break;
+        rc = traverse_device<T>(tree, mode, d_rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
+        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }   // grow once and redo
+        break;
+    }
+    dfree(ctx, d_rays);
+    if (total) *total = tot;
+    if (rc != BVHGPU_OK) return rc;
+    BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int ret = BVHGPU_OK;
+    if (hits && tot <= cap) {
+        if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(hits, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (tot > cap) {
+        set_error("traverse: %zu hits do not fit the caller's capacity %zu (use bvhgpu_traverse_fetch_*)", tot, cap);
+        ret = BVHGPU_ERR_CAPACITY;
+    }
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ret;
+}
+
+template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t cap) {
+    if (!tree || !hits) { set_error("traverse_fetch: null argument"); return BVHGPU_ERR_INVALID; }
+    if (cap < tree->last_total) { set_error("traverse_fetch: capacity %zu < %zu hits", cap, tree->last_total); return BVHGPU_ERR_CAPACITY; }
+    if (tree->last_total == 0) return BVHGPU_OK;
+    if (!tree->d_hits || tree->hits_cap < tree->last_total) { set_error("traverse_fetch: no retained result"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_CUDA_TRY(cudaMemcpyAsync(hits, tree->d_hits, sizeof(uint32_t) * tree->last_total, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
+}
+
+template <class T>
+static int refit_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n) {
+    if (!tree || (n && !aabbs)) { set_error("refit: null argument"); return BVHGPU_ERR_INVALID; }
+    if (n != tree->n) { set_error("refit: %zu AABBs for a tree over %u shapes", n, tree->n); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (n == 0) return BVHGPU_OK;
+    typename Traits<T>::Aabb* staged = nullptr;
+    BVH_TRY(dalloc_t(ctx, &staged, n));
+    BVH_CUDA_TRY(cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream));
+    BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
+    BVH_TRY(convert_aabbs<T>(ctx, staged, (uint32_t)n, tree->d_aabb, &tree->d_status->nan_found));
+    dfree(ctx, staged);
+    BVH_TRY(refit(tree));
+    tree->status_pending = true;
+    return resolve_status(tree);
+}
+
+}  // namespace bvhb200
+
+using namespace bvhb200;
+
+#define BVH_EXPORT extern "C" __attribute__((visibility("default")))
+
+BVH_EXPORT const char* bvhgpu_last_error(void) { return g_last_error.c_str(); }
+BVH_EXPORT const char* bvhgpu_version(void) { return "bvh_b200 0.1.0 (sm_100a)"; }
+
+BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
+    if (!out) { set_error("create: null out"); return BVHGPU_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("create: no CUDA device (%s); libbvh_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return BVHGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("create: device %d out of range (0..%d)", device, count - 1); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BVH_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error("create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor); return BVHGPU_ERR_UNSUPPORTED; }
+    bvhgpu_ctx* ctx = new (std::nothrow) bvhgpu_ctx();
+    if (!ctx) { set_error("create: out of host memory"); return BVHGPU_ERR_INTERNAL; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    BVH_CUDA_TRY(cudaMallocHost((void**)&ctx->h_pinned, 256 * sizeof(uint32_t)));
+    for (int i = 0; i < 2; ++i) { BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_walk[i])); BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_build[i])); }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;                       // keep freed blocks cached: alloc/free pairs stay cheap
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return BVHGPU_OK;
+}
+BVH_EXPORT void bvhgpu_destroy(bvhgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_walk[i]) cudaEventDestroy(ctx->ev_walk[i]); if (ctx->ev_build[i]) cudaEventDestroy(ctx->ev_build[i]); }
+    delete ctx;
+}
+BVH_EXPORT int bvhgpu_set_stream(bvhgpu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) { set_error("set_stream: null ctx"); return BVHGPU_ERR_INVALID; }
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_synchronize(bvhgpu_ctx* ctx) {
+    if (!ctx) { set_error("synchronize: null ctx"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
+}
+BVH_EXPORT uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+BVH_EXPORT int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) { set_error("set_option: null argument"); return BVHGPU_ERR_INVALID; }
+    if (!strcmp(name, "traverse_slots")) { ctx->traverse_slots = value; return BVHGPU_OK; }
+    if (!strcmp(name, "profile")) { ctx->profile = value; return BVHGPU_OK; }
+    set_error("set_option: unknown option '%s'", name);
+    return BVHGPU_ERR_INVALID;
+}
+
+BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out) {
+    if (!ctx || !name || !out) { set_error("get_metric: null argument"); return BVHGPU_ERR_INVALID; }
+    cudaEvent_t* ev = nullptr;
+    if (!strcmp(name, "walk_ms") && ctx->have_walk) ev = ctx->ev_walk;
+    else if (!strcmp(name, "build_ms") && ctx->have_build) ev = ctx->ev_build;
+    if (!ev) { set_error("get_metric: '%s' not recorded (set option profile=1 and run the call first)", name); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_CUDA_TRY(cudaEventSynchronize(ev[1]));
+    float ms = 0.f;
+    BVH_CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    *out = (double)ms;
+    return BVHGPU_OK;
+}
+
+#define DEFINE_API(T, SUF, TREE, AABB, RAY, NODE, FLAT)                                                                   \
+    BVH_EXPORT int bvhgpu_build_##SUF(bvhgpu_ctx* ctx, const AABB* aabbs, size_t n, int mode, TREE** out) {              \
+        return build_impl<T, TREE>(ctx, aabbs, n, mode, true, out);                                                       \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_build_dev_##SUF(bvhgpu_ctx* ctx, const void* dev_aabbs, size_t n, int mode, TREE** out) {      \
+        return build_impl<T, TREE>(ctx, (const AABB*)dev_aabbs, n, mode, false, out);                                     \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_tree_from_nodes_##SUF(bvhgpu_ctx* ctx, const NODE* nodes, size_t n_nodes, const AABB* aabbs,   \
+                                                size_t n, TREE** out) {                                                   \
+        return from_nodes_impl<T, TREE>(ctx, nodes, n_nodes, aabbs, n, out);                                              \
+    }                                                                                                                     \
+    BVH_EXPORT void bvhgpu_tree_free_##SUF(TREE* tree) {                                                                  \
+        if (!tree) return;                                                                                                \
+        if (tree->ctx) cudaSetDevice(tree->ctx->device);                                                                  \
+        tree_release<T>(tree);                                                                                            \
+        delete tree;                                                                                                      \
+    }                                                                                                                     \
+    BVH_EXPORT size_t bvhgpu_tree_num_shapes_##SUF(const TREE* tree) { return tree ? tree->n : 0; }                       \
+    BVH_EXPORT size_t bvhgpu_tree_num_nodes_##SUF(const TREE* tree) { return tree ? tree->n_nodes : 0; }                  \
+    BVH_EXPORT int bvhgpu_tree_nodes_##SUF(TREE* tree, NODE* out_nodes, uint32_t* out_node_index) {                       \
+        return tree_nodes_impl<T>(tree, out_nodes, out_node_index);                                                       \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_flatten_##SUF(TREE* tree, FLAT* out, size_t cap, size_t* len) {                                 \
+        return flatten_impl<T>(tree, out, cap, len);                                                                      \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_##SUF(TREE* tree, int mode, const RAY* rays, size_t nrays, uint32_t* offsets,          \
+                                         uint32_t* hits, size_t cap, size_t* total) {                                     \
+        return traverse_host_impl<T>(tree, mode, rays, nrays, offsets, hits, cap, total);                                 \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_fetch_##SUF(TREE* tree, uint32_t* hits, size_t cap) { return fetch_impl<T>(tree, hits, cap); } \
+    BVH_EXPORT int bvhgpu_traverse_dev_##SUF(TREE* tree, int mode, const void* dev_rays, size_t nrays, void* dev_offsets, \
+                                             void* dev_hits, size_t cap, size_t* total) {                                 \
+        if (!tree || !dev_offsets || (nrays && !dev_rays)) { set_error("traverse_dev: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
+        if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \
+        out2[0] = tree->last_visits; out2[1] = tree->last_total;                                                          \
+        return BVHGPU_OK;                                                                                                 \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_rays_new_dev_##SUF(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays) { \
+        if (!ctx || (n && (!dev_origins || !dev_directions || !dev_rays))) { set_error("rays_new: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(ctx->device));                                                                         \
+        return rays_new_device<T>(ctx, (const T*)dev_origins, (const T*)dev_directions, n, (RAY*)dev_rays);               \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_sah_cost_##SUF(TREE* tree, double* out2) {                                                      \
+        if (!tree || !out2) { set_error("sah_cost: null argument"); return BVHGPU_ERR_INVALID; }                          \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        BVH_TRY(resolve_status<T>(tree));                                                                                 \
+        return sah_cost<T>(tree, out2);                                                                                   \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_refit_##SUF(TREE* tree, const AABB* aabbs, size_t n) { return refit_impl<T>(tree, aabbs, n); }
+
+DEFINE_API(float, f32x3, bvhgpu_tree3f, bvh_aabb3f, bvh_ray3f, bvh_node3f, bvh_flat3f)
+DEFINE_API(double, f64x3, bvhgpu_tree3d, bvh_aabb3d, bvh_ray3d, bvh_node3d, bvh_flat3d)

@@ -1,0 +1,216 @@
+// bvh_b200/csrc/flatten.cu -- Bvh::flatten (src/flat_bvh.rs:60-143, 240-251, 312-319) as a closed-form
+// map over the preorder node array, the device-only traversal records, whole-tree SAH cost and refit.
+//
+// Closed form (DESIGN.md "flatten"): the reference's recursive flatten pushes, for every non-root
+// Bvh node i, a navigator FlatNode and, for leaves, a leaf FlatNode right behind it.  Because
+// Bvh.nodes is in preorder with child_l = i+1, the navigator of node i lands at
+//     nav(i) = (i - 1) + start(i)          start(i) = number of leaves before i = first shape position
+// with entry = nav+1 and exit = nav + 3*count(i) - 1.  One thread per node, no recursion, no scan.
+#include "internal.h"
+
+namespace bvhb200 {
+
+template <class T>
+__global__ void __launch_bounds__(256) flat_kernel(const typename Traits<T>::Node* __restrict__ nodes,
+                                                   const uint32_t* __restrict__ node_start, uint32_t n_nodes,
+                                                   typename Traits<T>::Flat* __restrict__ flat) {
+    using Tr = Traits<T>;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);      // parent, child_l, child_r, shape/count
+    const bool leaf = meta.y == BVH_INVALID;
+    if (i == 0) {
+        if (leaf) {                                                      // root leaf: flat_bvh.rs:129-141 only
+            typename Tr::Flat f;
+            for (int k = 0; k < 3; ++k) { f.aabb.min[k] = Tr::inf(); f.aabb.max[k] = -Tr::inf(); }
+            f.entry_index = BVH_INVALID; f.exit_index = 1; f.shape_index = meta.w;
+            flat[0] = f;
+        }
+        return;
+    }
+    const uint32_t nav = (i - 1) + node_start[i];
+    const uint32_t count = leaf ? 1u : meta.w;
+    const typename Tr::Node& par = nodes[meta.x];
+    const bool is_left = par.child_l == i;
+    typename Tr::Flat f;
+    for (int k = 0; k < 3; ++k) {
+        f.aabb.min[k] = is_left ? par.l_aabb.min[k] : par.r_aabb.min[k];
+        f.aabb.max[k] = is_left ? par.l_aabb.max[k] : par.r_aabb.max[k];
+    }
+    f.entry_index = nav + 1; f.exit_index = nav + 3 * count - 1; f.shape_index = BVH_INVALID;   // flat_bvh.rs:80-88
+    flat[nav] = f;
+    if (leaf) {
+        typename Tr::Flat g;
+        for (int k = 0; k < 3; ++k) { g.aabb.min[k] = Tr::inf(); g.aabb.max[k] = -Tr::inf(); }
+        g.entry_index = BVH_INVALID; g.exit_index = nav + 2; g.shape_index = meta.w;            // flat_bvh.rs:129-141
+        flat[nav + 1] = g;
+    }
+}
+
+// Traversal records: record r = node r+1 of the preorder array (the root has no AABB of its own).
+//   hit  -> next record r+1 (left child / leaf reported)
+//   miss -> skip = first record after the node's subtree
+template <class T>
+__global__ void __launch_bounds__(256) trec_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes,
+                                                   const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                   typename Traits<T>::TNode* __restrict__ trec) {
+    using Tr = Traits<T>;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    typename Tr::TNode r;
+    if (n_nodes == 1) {                       // root leaf: the shape's own AABB is tested (bvh_node.rs:314)
+        T mn[3], mx[3];
+        load_aabb(aabb + nodes[0].shape, mn, mx);
+        for (int k = 0; k < 3; ++k) { r.min[k] = mn[k]; r.max[k] = mx[k]; }
+        r.skip = 1; r.shape = nodes[0].shape;
+        if constexpr (sizeof(T) == 8) { r.pad[0] = r.pad[1] = 0; }
+        trec[0] = r;
+        return;
+    }
+    if (i == 0) return;
+    const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);
+    const bool leaf = meta.y == BVH_INVALID;
+    const typename Tr::Node& par = nodes[meta.x];
+    const bool is_left = par.child_l == i;
+    for (int k = 0; k < 3; ++k) {
+        r.min[k] = is_left ? par.l_aabb.min[k] : par.r_aabb.min[k];
+        r.max[k] = is_left ? par.l_aabb.max[k] : par.r_aabb.max[k];
+    }
+    const uint32_t count = leaf ? 1u : meta.w;
+    r.skip = (i - 1) + (2 * count - 1);
+    r.shape = leaf ? meta.w : BVH_INVALID;
+    if constexpr (sizeof(T) == 8) { r.pad[0] = r.pad[1] = 0; }
+    trec[i - 1] = r;
+}
+
+template <class T> int build_traversal_records(Tree<T>* tree) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    if (tree->n == 0) { tree->n_trec = 0; return BVHGPU_OK; }
+    const uint32_t n_trec = tree->n == 1 ? 1u : tree->n_nodes - 1;
+    if (!tree->d_tnodes) BVH_TRY(dalloc_t(ctx, &tree->d_tnodes, n_trec));
+    tree->n_trec = n_trec;
+    trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->d_aabb, tree->d_tnodes);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+template <class T> int build_flat(Tree<T>* tree) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    tree->n_flat = tree->n == 0 ? 0 : (tree->n == 1 ? 1 : 3 * (size_t)tree->n - 2);
+    tree->have_flat = true;
+    if (tree->n == 0) return BVHGPU_OK;
+    if (!tree->d_flat) BVH_TRY(dalloc_t(ctx, &tree->d_flat, tree->n_flat));
+    flat_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_start, tree->n_nodes, tree->d_flat);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+// ---- whole-tree SAH cost: sum over non-root nodes of SA(aabb in parent) / SA(root) ----
+template <class T>
+__global__ void __launch_bounds__(256) sah_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes, double* out2) {
+    __shared__ double sp[8], sg[8];
+    double p = 0.0, g = 0.0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const typename Traits<T>::Node& nd = nodes[i];
+        if (nd.child_l == BVH_INVALID) continue;
+        for (int side = 0; side < 2; ++side) {
+            const auto& a = side ? nd.r_aabb : nd.l_aabb;
+            const double x = (double)a.max[0] - (double)a.min[0], y = (double)a.max[1] - (double)a.min[1], z = (double)a.max[2] - (double)a.min[2];
+            p += 2.0 * (x * x + y * y + z * z);
+            g += 2.0 * (x * y + y * z + z * x);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { p += __shfl_xor_sync(0xffffffffu, p, o); g += __shfl_xor_sync(0xffffffffu, g, o); }
+    if (lane_id() == 0) { sp[threadIdx.x >> 5] = p; sg[threadIdx.x >> 5] = g; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tp = 0, tg = 0;
+        for (int w = 0; w < 8; ++w) { tp += sp[w]; tg += sg[w]; }
+        atomicAdd(out2, tp);
+        atomicAdd(out2 + 1, tg);
+    }
+}
+
+template <class T> int sah_cost(Tree<T>* tree, double* out2) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    out2[0] = out2[1] = 0.0;
+    if (tree->n < 2) return BVHGPU_OK;
+    double* d = nullptr;
+    BVH_TRY(dalloc_t(ctx, &d, 2));
+    BVH_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream));
+    const int blocks = (int)std::min<uint64_t>((tree->n_nodes + 255) / 256, (uint64_t)ctx->sm_count * 4);
+    sah_kernel<T><<<blocks, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, d);
+    ctx->launches++;
+    double h[2];
+    typename Traits<T>::Node root;
+    BVH_CUDA_TRY(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaMemcpyAsync(&root, tree->d_nodes, sizeof(root), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d);
+    double s[3];
+    for (int k = 0; k < 3; ++k) {
+        const double mn = std::min((double)root.l_aabb.min[k], (double)root.r_aabb.min[k]);
+        const double mx = std::max((double)root.l_aabb.max[k], (double)root.r_aabb.max[k]);
+        s[k] = mx - mn;
+    }
+    out2[0] = h[0] / (2.0 * (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]));
+    out2[1] = h[1] / (2.0 * (s[0] * s[1] + s[1] * s[2] + s[2] * s[0]));
+    return BVHGPU_OK;
+}
+
+// ---- refit: bottom-up recomputation of the child AABBs from the (new) shape AABBs ---------------------
+// (the data-parallel part of Bvh::update_shapes: fix_aabbs_ascending, src/bvh/optimization.rs:317-351).
+// One thread per shape climbs from its leaf; the second thread to reach a node carries on.
+template <class T>
+__global__ void __launch_bounds__(256) refit_kernel(typename Traits<T>::Node* nodes, const uint32_t* __restrict__ node_index,
+                                                    const typename Traits<T>::DAabb* __restrict__ aabb, uint32_t n, uint32_t* arrivals) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    T mn[3], mx[3];
+    load_aabb(aabb + s, mn, mx);
+    uint32_t node = node_index[s];
+    while (node != 0) {
+        const uint32_t p = __ldcg(&nodes[node].parent);
+        typename Traits<T>::Node* pn = nodes + p;
+        const bool is_left = __ldcg(&pn->child_l) == node;
+        auto* dst = is_left ? &pn->l_aabb : &pn->r_aabb;
+        for (int k = 0; k < 3; ++k) { __stcg(&dst->min[k], mn[k]); __stcg(&dst->max[k], mx[k]); }
+        __threadfence();
+        if (atomicAdd(arrivals + p, 1u) == 0u) return;      // sibling subtree not finished yet
+        __threadfence();
+        const auto* sib = is_left ? &pn->r_aabb : &pn->l_aabb;
+        for (int k = 0; k < 3; ++k) {
+            const T smn = __ldcg(&sib->min[k]), smx = __ldcg(&sib->max[k]);
+            mn[k] = smn < mn[k] ? smn : mn[k];
+            mx[k] = smx > mx[k] ? smx : mx[k];
+        }
+        node = p;
+    }
+}
+
+template <class T> int refit(Tree<T>* tree) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    if (tree->n < 2) return tree->n == 1 ? build_traversal_records(tree) : (int)BVHGPU_OK;
+    uint32_t* arrivals = nullptr;
+    BVH_TRY(dalloc_t(ctx, &arrivals, tree->n_nodes));
+    BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * tree->n_nodes, ctx->stream));
+    refit_kernel<T><<<(tree->n + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, tree->n, arrivals);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    dfree(ctx, arrivals);
+    BVH_TRY(build_traversal_records(tree));
+    if (tree->have_flat) BVH_TRY(build_flat(tree));
+    return BVHGPU_OK;
+}
+
+#define INST(T)                                           \
+    template int build_traversal_records<T>(Tree<T>*);    \
+    template int build_flat<T>(Tree<T>*);                 \
+    template int sah_cost<T>(Tree<T>*, double*);          \
+    template int refit<T>(Tree<T>*);
+INST(float)
+INST(double)
+
+}  // namespace bvhb200

@@ -1,0 +1,110 @@
+// bvh_b200/csrc/internal.h -- host-side structures shared by the translation units of libbvh_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <cstdio>
+#include "common.cuh"
+
+namespace bvhb200 {
+
+void set_error(const char* fmt, ...);
+
+#define BVH_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::bvhb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return BVHGPU_ERR_CUDA;                                                                 \
+        }                                                                                           \
+    } while (0)
+
+#define BVH_TRY(expr)                  \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != BVHGPU_OK) return _s; \
+    } while (0)
+
+}  // namespace bvhb200
+
+// Device status block a build writes (read back lazily).
+struct BuildStatus {
+    uint32_t error;        // bvhgpu_status raised on the device (timeout / internal)
+    uint32_t nan_found;    // prep kernel saw a NaN coordinate
+    uint32_t tickets;      // queue tickets handed out (diagnostics)
+    uint32_t leaves_done;  // must equal n at the end
+};
+
+struct bvhgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    int64_t traverse_slots = 4;    // per-ray hit slots of the single-pass traversal (0 = two-pass)
+    int64_t build_tile = 0;        // reserved
+    uint32_t* h_pinned = nullptr;  // small pinned read-back area (256 words)
+    int64_t profile = 0;           // bracket dominant kernels with events
+    cudaEvent_t ev_walk[2] = {nullptr, nullptr};
+    cudaEvent_t ev_build[2] = {nullptr, nullptr};
+    bool have_walk = false, have_build = false;
+};
+
+namespace bvhb200 {
+
+template <class T> struct Tree {
+    using Tr = Traits<T>;
+    bvhgpu_ctx* ctx = nullptr;
+    uint32_t n = 0;          // shapes
+    uint32_t n_nodes = 0;    // 2n-1
+    typename Tr::DAabb* d_aabb = nullptr;     // [n]      shape AABBs (padded device layout)
+    typename Tr::Node* d_nodes = nullptr;     // [2n-1]   Bvh.nodes, reference preorder layout
+    uint32_t* d_node_index = nullptr;         // [n]      leaf node of every shape
+    uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
+    typename Tr::TNode* d_tnodes = nullptr;   // [n_trec] traversal records
+    uint32_t n_trec = 0;
+    typename Tr::Flat* d_flat = nullptr;      // [n_flat] reference-layout FlatBvh (built on demand)
+    size_t n_flat = 0;
+    bool have_flat = false;
+    // deferred build status
+    BuildStatus* d_status = nullptr;
+    BuildStatus* h_status = nullptr;          // pinned
+    bool status_pending = false;
+    // retained result of the last traversal
+    uint32_t* d_offsets = nullptr; size_t offsets_cap = 0;
+    uint32_t* d_hits = nullptr;    size_t hits_cap = 0;
+    size_t last_total = 0, last_nrays = 0;
+    uint64_t last_visits = 0;
+};
+
+// Resolve the deferred device status of a build / refit (synchronises the stream once).
+template <class T> int resolve_status(Tree<T>* tree);
+
+// ---- memory (stream-ordered pool) ----
+int dalloc(bvhgpu_ctx* ctx, void** p, size_t bytes);
+void dfree(bvhgpu_ctx* ctx, void* p);
+template <class P> inline int dalloc_t(bvhgpu_ctx* ctx, P** p, size_t count) { return dalloc(ctx, (void**)p, count * sizeof(P)); }
+
+// ---- build_sah.cu ----
+// in_aabbs: device pointer to n AABBs in the C-ABI layout (24 B / 48 B).  Fills tree->d_aabb, d_nodes,
+// d_node_index, d_node_start (allocated here).  Asynchronous; errors are reported via tree->d_status.
+template <class T> int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree);
+// Converts ABI-layout AABBs to the device layout only (used by tree_from_nodes and refit).
+template <class T> int convert_aabbs(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n,
+                                     typename Traits<T>::DAabb* out, uint32_t* d_nan_flag);
+
+// ---- flatten.cu ----
+template <class T> int build_traversal_records(Tree<T>* tree);   // d_tnodes
+template <class T> int build_flat(Tree<T>* tree);                // d_flat (reference FlatNode layout)
+template <class T> int sah_cost(Tree<T>* tree, double* out2);
+template <class T> int refit(Tree<T>* tree);                     // recompute child AABBs bottom-up from d_aabb
+
+// ---- traverse.cu ----
+template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, size_t nrays,
+                                       uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
+template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
+                                       typename Traits<T>::Ray* d_rays);
+
+}  // namespace bvhb200
+
+struct bvhgpu_tree3f : bvhb200::Tree<float> {};
+struct bvhgpu_tree3d : bvhb200::Tree<double> {};

@@ -1,0 +1,283 @@
+// bvh_b200/csrc/traverse.cu -- batched Ray traversal: Bvh::traverse (src/bvh/bvh_impl.rs:104-119,
+// src/bvh/bvh_node.rs:288-319) and FlatBvh::traverse (src/flat_bvh.rs:396-431) for whole ray batches,
+// with the crate's slab test (src/ray/intersect_default.rs:16-37) reproduced operation for operation.
+//
+// One ray per thread walks the preorder traversal records without a stack: a record holds the AABB
+// the node has in its parent, `skip` (first record behind the node's subtree) and the shape index of
+// a leaf.  hit -> next record, miss -> skip.  The visiting order is exactly the reference's
+// left-first DFS, so per-ray hit lists come out in the reference's order.
+//
+// Output is CSR (offsets[nrays+1], hits[total]).  Single-pass scheme: the walk stores the first K
+// hits of every ray in slot-major scratch ([K][nrays], coalesced across a warp) and counts all of
+// them; an exclusive scan turns counts into offsets; the emit kernel copies the slots into place and
+// re-walks only rays with more than K hits.  K = 0 degenerates to the classic count / scan / fill.
+#include "internal.h"
+
+namespace bvhb200 {
+
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;     // 2048 counts per block
+
+// ---- slab test: intersect_default.rs:16-37 --------------------------------------------------------
+template <class T> __device__ __forceinline__ T tmin2(T a, T b);
+template <> __device__ __forceinline__ float tmin2(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double tmin2(double a, double b) { return fmin(a, b); }
+template <class T> __device__ __forceinline__ T tmax2(T a, T b);
+template <> __device__ __forceinline__ float tmax2(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmax2(double a, double b) { return fmax(a, b); }
+
+template <class T>
+__device__ __forceinline__ bool slab_hit(const T o[3], const T inv[3], const T mn[3], const T mx[3]) {
+    // lbr = (aabb.min - origin) * inv_direction ; rtr = (aabb.max - origin) * inv_direction   (:19-20)
+    const T l0 = mul_rn(sub_rn(mn[0], o[0]), inv[0]), r0 = mul_rn(sub_rn(mx[0], o[0]), inv[0]);
+    const T l1 = mul_rn(sub_rn(mn[1], o[1]), inv[1]), r1 = mul_rn(sub_rn(mx[1], o[1]), inv[1]);
+    const T l2 = mul_rn(sub_rn(mn[2], o[2]), inv[2]), r2 = mul_rn(sub_rn(mx[2], o[2]), inv[2]);
+    // has_nan(lbr) | has_nan(rtr) => no intersection (:22-28).  (x != y is true iff unordered or different;
+    // the pairwise isnan tests compile to 3 unordered-compare instructions.)
+    const bool nan = (l0 != l0) | (r0 != r0) | (l1 != l1) | (r1 != r1) | (l2 != l2) | (r2 != r2);
+    // NaN-free from here on, so fmin/fmax are the plain component-wise inf/sup (:30-33).
+    const T tmin = tmax2(tmax2(tmin2(l0, r0), tmin2(l1, r1)), tmin2(l2, r2));
+    const T tmax = tmin2(tmin2(tmax2(l0, r0), tmax2(l1, r1)), tmax2(l2, r2));
+    const T lo = tmin > T(0) ? tmin : T(0);                     // fast_max(tmin, 0), utils.rs:52-54
+    return !nan && tmax >= lo;                                  // :35
+}
+
+// ---- record fetch ------------------------------------------------------------------------------------
+__device__ __forceinline__ void fetch(const TNodeF* __restrict__ p, float mn[3], float mx[3], uint32_t& skip, uint32_t& shape) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    mn[0] = a.x; mn[1] = a.y; mn[2] = a.z; skip = __float_as_uint(a.w);
+    mx[0] = b.x; mx[1] = b.y; mx[2] = b.z; shape = __float_as_uint(b.w);
+}
+__device__ __forceinline__ void fetch(const TNodeD* __restrict__ p, double mn[3], double mx[3], uint32_t& skip, uint32_t& shape) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    const double2 c = __ldg(reinterpret_cast<const double2*>(p) + 2);
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(p) + 3);
+    mn[0] = a.x; mn[1] = a.y; mn[2] = b.x; mx[0] = b.y; mx[1] = c.x; mx[2] = c.y; skip = d.x; shape = d.y;
+}
+
+// The walk.  `emit(shape)` is called for every reported shape in reference order.
+template <class T, bool FLAT, class Emit>
+__device__ __forceinline__ uint32_t walk(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                         const typename Traits<T>::DAabb* __restrict__ aabb,
+                                         const T o[3], const T inv[3], Emit emit) {
+    uint32_t i = 0, visits = 0;
+    while (i < n_rec) {
+        T mn[3], mx[3];
+        uint32_t skip, shape;
+        fetch(trec + i, mn, mx, skip, shape);
+        ++visits;
+        if (slab_hit(o, inv, mn, mx)) {
+            if (shape != BVH_INVALID) {
+                bool report = true;
+                if (FLAT) {                       // flat_bvh.rs:412-416: the leaf re-tests shapes[shape].aabb()
+                    T smn[3], smx[3];
+                    load_aabb(aabb + shape, smn, smx);
+                    report = slab_hit(o, inv, smn, smx);
+                }
+                if (report) emit(shape);
+            }
+            i = i + 1;
+        } else {
+            i = skip;
+        }
+    }
+    return visits;
+}
+
+template <class T> __device__ __forceinline__ void load_ray(const typename Traits<T>::Ray* __restrict__ rays, size_t r, T o[3], T inv[3]) {
+    const T* p = reinterpret_cast<const T*>(rays + r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = __ldg(p + k); inv[k] = __ldg(p + 6 + k); }
+}
+
+// Pass 1: count all hits of every ray, keep the first K in slot-major scratch.
+template <class T, bool FLAT>
+__global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                         const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                         const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
+                                                         uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
+                                                         unsigned long long* __restrict__ visit_total) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t visits = 0;
+    if (r < nrays) {
+        T o[3], inv[3];
+        load_ray<T>(rays, r, o, inv);
+        uint32_t cnt = 0;
+        visits = walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
+            if (cnt < K) slots[(size_t)cnt * nrays + r] = shape;
+            ++cnt;
+        });
+        counts[r] = cnt;
+    }
+    visits = __reduce_add_sync(0xffffffffu, visits);
+    if (lane_id() == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
+}
+
+// Exclusive scan of counts, phase A: per-block local exclusive offsets + block totals.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ counts, uint32_t n,
+                                                                  uint32_t* __restrict__ local, unsigned long long* __restrict__ blocksum) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0u; s += v[k]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    uint32_t run = woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) local[base + k] = run; run += v[k]; }
+    if (threadIdx.x == SCAN_THREADS - 1) blocksum[blockIdx.x] = (unsigned long long)(woff + incl);
+}
+// Phase B: one block turns block totals into exclusive block offsets (64-bit) and the grand total.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* __restrict__ blocksum, uint32_t nblocks,
+                                                           unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
+        const uint32_t b = b0 + threadIdx.x;
+        const unsigned long long v = b < nblocks ? blocksum[b] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+        const unsigned long long carry = carry_s;
+        if (b < nblocks) blocksum[b] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+// Pass 2: final offsets + hit lists.  Rays with <= K hits copy their slots, the rest walk again.
+template <class T, bool FLAT>
+__global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                   const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                   const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
+                                                   const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
+                                                   const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
+                                                   const unsigned long long* __restrict__ total,
+                                                   uint32_t* __restrict__ offsets, uint32_t* __restrict__ hits, unsigned long long cap) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) { const unsigned long long t = *total; offsets[nrays] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t; }
+    if (r >= nrays) return;
+    const unsigned long long off = blocksum[r / SCAN_TILE] + local[r];
+    offsets[r] = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
+    const uint32_t c = counts[r];
+    if (c == 0 || hits == nullptr) return;
+    if (c <= K) {
+        for (uint32_t k = 0; k < c; ++k) if (off + k < cap) hits[off + k] = slots[(size_t)k * nrays + r];
+    } else {
+        T o[3], inv[3];
+        load_ray<T>(rays, r, o, inv);
+        unsigned long long w = off;
+        walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) { if (w < cap) hits[w] = shape; ++w; });
+    }
+}
+
+template <class T>
+int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, size_t nrays,
+                    uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (nrays > 0x7FFFFFFFull) { set_error("traverse: nrays %zu exceeds 2^31-1", nrays); return BVHGPU_ERR_INVALID; }
+    if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("traverse: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
+    tree->last_nrays = nrays;
+    if (nrays == 0) {
+        if (d_offsets) BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t), st));
+        if (total) *total = 0;
+        tree->last_total = 0;
+        return BVHGPU_OK;
+    }
+    if (tree->n == 0) {                                          // empty Bvh: no hits (bvh_impl.rs:109-112)
+        BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nrays + 1), st));
+        if (total) *total = 0;
+        tree->last_total = 0;
+        return BVHGPU_OK;
+    }
+    BVH_TRY(resolve_status(tree));                               // never walk a tree whose build failed
+    if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const uint32_t R = (uint32_t)nrays;
+    const uint32_t K = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(ctx->traverse_slots, 64));
+    const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
+    unsigned long long* sums = nullptr;       // [nblk] block offsets, [nblk] total, [nblk+1] visits
+    BVH_TRY(dalloc_t(ctx, &counts, R));
+    BVH_TRY(dalloc_t(ctx, &local, R));
+    if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
+    const int grid = (R + 255) / 256;
+    const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
+    if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
+    if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, sums + nblk + 1);
+    else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, sums + nblk + 1);
+    if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    ctx->launches += 4;
+    BVH_CUDA_TRY(cudaGetLastError());
+    int rc = BVHGPU_OK;
+    if (total) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
+        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaStreamSynchronize(st));
+        *total = (size_t)h[0];
+        tree->last_total = (size_t)h[0];
+        tree->last_visits = h[1];
+        if (h[0] > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", h[0]); rc = BVHGPU_ERR_CAPACITY; }
+        else if (d_hits && h[0] > cap) { set_error("traverse: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
+    }
+    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums);
+    return rc;
+}
+
+// ---- Ray::new for a batch (src/ray/ray_impl.rs:70-80) -------------------------------------------------
+template <class T> __device__ __forceinline__ T sqrt_rn(T x);
+template <> __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }
+template <> __device__ __forceinline__ double sqrt_rn(double x) { return __dsqrt_rn(x); }
+
+template <class T>
+__global__ void __launch_bounds__(256) rays_new_kernel(const T* __restrict__ origins, const T* __restrict__ dirs, size_t n,
+                                                       typename Traits<T>::Ray* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
+    const T nrm = sqrt_rn(add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz)));   // [3p] nalgebra normalize
+    typename Traits<T>::Ray r;
+    const T d[3] = {div_rn(dx, nrm), div_rn(dy, nrm), div_rn(dz, nrm)};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.origin[k] = origins[3 * i + k]; r.direction[k] = d[k]; r.inv_direction[k] = div_rn(T(1), d[k]); }
+    out[i] = r;
+}
+
+template <class T>
+int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n, typename Traits<T>::Ray* d_rays) {
+    if (n == 0) return BVHGPU_OK;
+    rays_new_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_origins, d_dirs, n, d_rays);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int rays_new_device<float>(bvhgpu_ctx*, const float*, const float*, size_t, bvh_ray3f*);
+template int rays_new_device<double>(bvhgpu_ctx*, const double*, const double*, size_t, bvh_ray3d*);
+
+}  // namespace bvhb200

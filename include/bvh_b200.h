@@ -1,0 +1,180 @@
+/* ============================================================================
+ * include/bvh_b200.h -- C ABI of libbvh_b200.so
+ *
+ * B200-native (sm_100a) replacement for the ONE data-parallel hot path of the
+ * Rust crate svenstaro/bvh 0.12.0:
+ *
+ *     Bvh::build  ->  Bvh::flatten  ->  batched Ray traversal
+ *
+ * This header is the drop-in boundary: plain pointers and sizes only, so a Rust
+ * shim (`impl BoundingHierarchy<T,3> for GpuBvh<T>`) can bind
+ * it with `extern "C"`.  Every entry point cites the reference interface it
+ * replaces (file:line relative to the reference checkout).
+ *
+ * There is NO CPU fallback behind any of these calls: without a CUDA device
+ * `bvhgpu_create` fails with BVHGPU_ERR_CUDA.
+ *
+ * Conventions
+ *   - all functions return a bvhgpu_status (0 = ok); `bvhgpu_last_error()` gives
+ *     the message for the calling thread.  The reference panics on the same
+ *     conditions (NaN centroid: src/bvh/bvh_node.rs:214-217); the shim turns a
+ *     non-zero status into `panic!`.
+ *   - `*_dev_*` variants take DEVICE pointers, enqueue on the context's stream
+ *     and do not synchronise unless they must return a host value.
+ *   - n == 0 and n == 1 behave as the reference does (empty tree / root leaf,
+ *     src/bvh/bvh_impl.rs:57-59, src/bvh/bvh_node.rs:95-104, 314).
+ * ========================================================================== */
+#ifndef BVH_B200_H
+#define BVH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVHGPU_INVALID_INDEX 0xFFFFFFFFu /* u32::MAX sentinel, src/flat_bvh.rs:36-45 */
+
+/* ---- POD mirrors (Rust's Aabb / Ray / BvhNode / FlatNode are not repr(C)) ---- */
+
+/* Aabb<f32,3> / Aabb<f64,3>: src/aabb/aabb_impl.rs:10-16 */
+typedef struct { float min[3]; float max[3]; } bvh_aabb3f;    /* 24 B */
+typedef struct { double min[3]; double max[3]; } bvh_aabb3d;  /* 48 B */
+
+/* Ray<T,3>: src/ray/ray_impl.rs:17-29 (direction already normalised, inv = 1/direction) */
+typedef struct { float origin[3]; float direction[3]; float inv_direction[3]; } bvh_ray3f;     /* 36 B */
+typedef struct { double origin[3]; double direction[3]; double inv_direction[3]; } bvh_ray3d;  /* 72 B */
+
+/* BvhNode<T,3> (enum, src/bvh/bvh_node.rs:21-47) flattened:
+ *   Leaf: child_l == child_r == BVHGPU_INVALID_INDEX, shape = shape_index, AABBs = Aabb::empty()
+ *   Node: child_l / child_r = child node indices, shape = number of shapes under the node
+ *         (extra information the reference does not store), l_aabb / r_aabb = child AABBs.
+ * Indices are u32 (the reference uses usize; FlatNode already limits trees to u32). */
+typedef struct { uint32_t parent, child_l, child_r, shape; bvh_aabb3f l_aabb, r_aabb; } bvh_node3f;  /*  64 B */
+typedef struct { uint32_t parent, child_l, child_r, shape; bvh_aabb3d l_aabb, r_aabb; } bvh_node3d;  /* 112 B */
+
+/* FlatNode<T,3>: src/flat_bvh.rs:17-46 */
+typedef struct { bvh_aabb3f aabb; uint32_t entry_index, exit_index, shape_index; } bvh_flat3f;             /* 36 B */
+typedef struct { bvh_aabb3d aabb; uint32_t entry_index, exit_index, shape_index, _pad; } bvh_flat3d;      /* 64 B */
+
+typedef enum {
+    BVHGPU_OK = 0,
+    BVHGPU_ERR_INVALID = 1,     /* bad argument */
+    BVHGPU_ERR_CUDA = 2,        /* CUDA runtime error / no device */
+    BVHGPU_ERR_NAN = 3,         /* NaN in an input AABB (reference: panic, bvh_node.rs:214-217) */
+    BVHGPU_ERR_CAPACITY = 4,    /* caller buffer too small; *total / *len holds the needed size */
+    BVHGPU_ERR_TIMEOUT = 5,     /* device watchdog fired */
+    BVHGPU_ERR_UNSUPPORTED = 6,
+    BVHGPU_ERR_INTERNAL = 7
+} bvhgpu_status;
+
+typedef enum {
+    BVHGPU_BUILD_EXACT_SAH = 0, /* bit-identical to Bvh::build (6-bucket SAH, src/bvh/bvh_node.rs:81-279) */
+    BVHGPU_BUILD_LBVH = 1       /* Morton/Karras LBVH: same hit sets, different topology */
+} bvhgpu_build_mode;
+
+typedef enum {
+    BVHGPU_TRAVERSE_BVH = 0,    /* Bvh::traverse semantics     (src/bvh/bvh_node.rs:288-319): leaves are not re-tested */
+    BVHGPU_TRAVERSE_FLAT = 1    /* FlatBvh::traverse semantics (src/flat_bvh.rs:396-431): reached leaves re-test the shape AABB */
+} bvhgpu_traverse_mode;
+
+typedef struct bvhgpu_ctx bvhgpu_ctx;       /* one per device: stream, scratch pool           */
+typedef struct bvhgpu_tree3f bvhgpu_tree3f; /* device-resident Bvh<f32,3> (+ FlatBvh, shape AABBs) */
+typedef struct bvhgpu_tree3d bvhgpu_tree3d; /* device-resident Bvh<f64,3>                      */
+
+/* ---- context ------------------------------------------------------------------ */
+int bvhgpu_create(int device, bvhgpu_ctx** out);
+void bvhgpu_destroy(bvhgpu_ctx* ctx);
+const char* bvhgpu_last_error(void);
+const char* bvhgpu_version(void);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+int bvhgpu_set_stream(bvhgpu_ctx* ctx, void* cuda_stream);
+int bvhgpu_synchronize(bvhgpu_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
+/* Tunables: "traverse_slots" (per-ray hit slots of the single-pass path, 0 = two-pass count/fill),
+ * "profile" (1: bracket the dominant kernels with CUDA events, read back with bvhgpu_get_metric). */
+int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value);
+/* Measurements of the last profiled call on this context: "walk_ms" (traversal walk kernel),
+ * "build_ms" (persistent SAH build kernel).  Synchronises on the recorded events. */
+int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out);
+
+/* ---- build: replaces BoundingHierarchy::build / build_par for Bvh ----------------
+ * (src/bounding_hierarchy.rs:158-177, src/bvh/bvh_impl.rs:40-96, src/bvh/bvh_node.rs:81-279).
+ * `aabbs[i]` is `shapes[i].aabb()` (Bounded::aabb, src/aabb/aabb_impl.rs:55) gathered by the shim.
+ * The tree stays on the device; fetch Bvh.nodes / the per-shape node indices with
+ * bvhgpu_tree_nodes_*.  build_par == build (rayon is off the hot path). */
+int bvhgpu_build_f32x3(bvhgpu_ctx* ctx, const bvh_aabb3f* aabbs, size_t n, int mode, bvhgpu_tree3f** out);
+int bvhgpu_build_f64x3(bvhgpu_ctx* ctx, const bvh_aabb3d* aabbs, size_t n, int mode, bvhgpu_tree3d** out);
+int bvhgpu_build_dev_f32x3(bvhgpu_ctx* ctx, const void* dev_aabbs, size_t n, int mode, bvhgpu_tree3f** out);
+int bvhgpu_build_dev_f64x3(bvhgpu_ctx* ctx, const void* dev_aabbs, size_t n, int mode, bvhgpu_tree3d** out);
+
+/* Upload an existing reference-layout Bvh (`Bvh.nodes` in the preorder layout Bvh::build emits:
+ * child_l == i+1, src/bvh/bvh_node.rs:138-142) together with the shapes' AABBs. */
+int bvhgpu_tree_from_nodes_f32x3(bvhgpu_ctx* ctx, const bvh_node3f* nodes, size_t n_nodes,
+                                 const bvh_aabb3f* aabbs, size_t n, bvhgpu_tree3f** out);
+int bvhgpu_tree_from_nodes_f64x3(bvhgpu_ctx* ctx, const bvh_node3d* nodes, size_t n_nodes,
+                                 const bvh_aabb3d* aabbs, size_t n, bvhgpu_tree3d** out);
+
+void bvhgpu_tree_free_f32x3(bvhgpu_tree3f* tree);
+void bvhgpu_tree_free_f64x3(bvhgpu_tree3d* tree);
+size_t bvhgpu_tree_num_shapes_f32x3(const bvhgpu_tree3f* tree);
+size_t bvhgpu_tree_num_shapes_f64x3(const bvhgpu_tree3d* tree);
+size_t bvhgpu_tree_num_nodes_f32x3(const bvhgpu_tree3f* tree);   /* 2n-1 (0 for n == 0) */
+size_t bvhgpu_tree_num_nodes_f64x3(const bvhgpu_tree3d* tree);
+
+/* Materialise `Bvh.nodes` (pub field, src/bvh/bvh_impl.rs:27-33) and the leaf node index of every
+ * shape (BHShape::set_bh_node_index, src/bounding_hierarchy.rs:58; written at src/bvh/bvh_node.rs:103).
+ * Either pointer may be NULL. */
+int bvhgpu_tree_nodes_f32x3(bvhgpu_tree3f* tree, bvh_node3f* out_nodes, uint32_t* out_node_index);
+int bvhgpu_tree_nodes_f64x3(bvhgpu_tree3d* tree, bvh_node3d* out_nodes, uint32_t* out_node_index);
+
+/* ---- flatten: replaces Bvh::flatten (src/flat_bvh.rs:60-143, 240-251, 312-319) -----
+ * Writes the FlatBvh (3n-2 FlatNodes for n >= 2, 1 for n == 1, 0 for n == 0) into `out`
+ * (may be NULL to only build the device copy) and its length into *len. */
+int bvhgpu_flatten_f32x3(bvhgpu_tree3f* tree, bvh_flat3f* out, size_t cap, size_t* len);
+int bvhgpu_flatten_f64x3(bvhgpu_tree3d* tree, bvh_flat3d* out, size_t cap, size_t* len);
+
+/* ---- traverse: batched Bvh::traverse / FlatBvh::traverse for Ray queries -----------
+ * (src/bvh/bvh_impl.rs:104-119, src/bvh/bvh_node.rs:288-319, src/flat_bvh.rs:396-431,
+ *  slab test src/ray/intersect_default.rs:16-37).
+ * Output is CSR: hits of ray r are hits[offsets[r] .. offsets[r+1]) = shape indices in the
+ * reference's DFS (left-first) order.  If the hit list does not fit `cap`, offsets and *total
+ * are still valid, the call returns BVHGPU_ERR_CAPACITY and bvhgpu_traverse_fetch_* can copy the
+ * retained result without traversing again.  Shape AABBs are the ones given at build time. */
+int bvhgpu_traverse_f32x3(bvhgpu_tree3f* tree, int mode, const bvh_ray3f* rays, size_t nrays,
+                          uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_traverse_f64x3(bvhgpu_tree3d* tree, int mode, const bvh_ray3d* rays, size_t nrays,
+                          uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_traverse_fetch_f32x3(bvhgpu_tree3f* tree, uint32_t* hits, size_t cap);
+int bvhgpu_traverse_fetch_f64x3(bvhgpu_tree3d* tree, uint32_t* hits, size_t cap);
+/* Device-resident variant: rays / offsets / hits are device pointers.  `total` may be NULL
+ * (no host synchronisation); hits beyond `cap` are dropped and reported through *total. */
+int bvhgpu_traverse_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_rays, size_t nrays,
+                              void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+int bvhgpu_traverse_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_rays, size_t nrays,
+                              void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+/* Counters of the last traversal on this tree: [0] node records visited, [1] hits. */
+int bvhgpu_traverse_stats_f32x3(bvhgpu_tree3f* tree, uint64_t* out2);
+int bvhgpu_traverse_stats_f64x3(bvhgpu_tree3d* tree, uint64_t* out2);
+
+/* Ray::new for a batch (src/ray/ray_impl.rs:70-80): normalise, inv = 1/direction. Device pointers. */
+int bvhgpu_rays_new_dev_f32x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);
+int bvhgpu_rays_new_dev_f64x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);
+
+/* ---- whole-tree SAH cost (definition: DESIGN.md; the reference only has the per-split cost,
+ * src/bvh/bvh_node.rs:236-238).  out2[0]: with the reference's surface_area (2*|size|^2,
+ * src/aabb/aabb_impl.rs:551-554), out2[1]: geometric area. */
+int bvhgpu_sah_cost_f32x3(bvhgpu_tree3f* tree, double* out2);
+int bvhgpu_sah_cost_f64x3(bvhgpu_tree3d* tree, double* out2);
+
+/* ---- refit: bottom-up AABB update after shapes moved (the data-parallel part of
+ * Bvh::update_shapes, src/bvh/optimization.rs:304-351 fix_aabbs_ascending).  Topology is kept. */
+int bvhgpu_refit_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n);
+int bvhgpu_refit_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVH_B200_H */

@@ -1,0 +1,291 @@
+"""GPU parity tests: libbvh_b200.so (through the C ABI) against the CPU oracle, bit-exact.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.scenes import rays_for, scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from bvh_b200 import api as A
+
+    return A
+
+
+def _nodes_equal(a, b):
+    """Bitwise on integers, float equality on AABBs (only the sign of a zero may differ)."""
+    for f in ("parent", "child_l", "child_r", "shape"):
+        if not np.array_equal(a[f], b[f]):
+            return False
+    for f in ("l_aabb", "r_aabb"):
+        for g in ("min", "max"):
+            if not np.array_equal(a[f][g], b[f][g]):
+                return False
+    return True
+
+
+def _flat_equal(a, b):
+    if len(a) != len(b):
+        return False
+    for f in ("entry_index", "exit_index", "shape_index"):
+        if not np.array_equal(a[f], b[f]):
+            return False
+    return np.array_equal(a["aabb"]["min"], b["aabb"]["min"]) and np.array_equal(a["aabb"]["max"], b["aabb"]["max"])
+
+
+SCENES_F32 = ["empty", "cubes1", "boxes21", "random2", "random3", "random31", "random32", "random33", "random255", "random256",
+              "random257", "random513", "random1000", "random5000", "cubes100", "cubes1000", "points200", "points3000",
+              "line700", "huge64", "huge2000", "skew40", "skew3000"]
+
+
+@pytest.mark.parametrize("name", SCENES_F32)
+def test_build_flatten_parity_f32(api, name):
+    shapes = scene(name)
+    want = O.build(shapes)
+    bvh = api.Bvh.build(shapes)
+    assert bvh.num_shapes == len(shapes)
+    assert _nodes_equal(bvh.nodes, want.nodes), name
+    assert np.array_equal(bvh.node_index, want.node_index)
+    flat = bvh.flatten()
+    assert _flat_equal(flat.nodes, O.flatten(want.nodes)), name
+    if name.startswith("huge"):
+        assert want.nosplit_fallthrough > 0
+    if name.startswith("points"):
+        assert want.degenerate_splits > 0
+    bvh.free()
+
+
+@pytest.mark.parametrize("name", ["empty", "cubes1", "boxes21", "random33", "random257", "random3000", "cubes200", "points500", "huge300", "skew500"])
+def test_build_flatten_parity_f64(api, name):
+    shapes = scene(name, "f64")
+    want = O.build(shapes, "f64")
+    bvh = api.Bvh.build(shapes, prec="f64")
+    assert _nodes_equal(bvh.nodes, want.nodes), name
+    assert np.array_equal(bvh.node_index, want.node_index)
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes, "f64")), name
+    bvh.free()
+
+
+def _check_traverse(api, bvh, want_nodes, shapes, rays, prec="f32"):
+    from bvh_b200 import capi
+
+    flat = O.flatten(want_nodes, prec)
+    r_rec = O.traverse(want_nodes, shapes, rays, O.MODE_RECURSIVE, prec)
+    r_flat = O.traverse(flat, shapes, rays, O.MODE_FLAT, prec)
+    for slots in (4, 0, 1):                       # single-pass, two-pass, forced overflow re-walk
+        bvh.ctx.set_option("traverse_slots", slots)
+        off, hits = bvh.traverse_batch(rays, mode=capi.TRAVERSE_BVH)
+        assert np.array_equal(off.astype(np.uint64), r_rec.offsets), slots
+        assert np.array_equal(hits, r_rec.hits), slots
+        off, hits = bvh.traverse_batch(rays, mode=capi.TRAVERSE_FLAT)
+        assert np.array_equal(off.astype(np.uint64), r_flat.offsets), slots
+        assert np.array_equal(hits, r_flat.hits), slots
+    bvh.ctx.set_option("traverse_slots", 4)
+    visits, total = bvh.traverse_stats()
+    assert total == len(r_flat.hits)
+
+
+@pytest.mark.parametrize("name", ["cubes1", "boxes21", "random2", "random257", "random5000", "cubes1000", "points3000", "huge2000", "skew3000"])
+def test_traverse_parity_f32(api, name):
+    shapes = scene(name)
+    want = O.build(shapes)
+    bvh = api.Bvh.build(shapes)
+    rays = rays_for(shapes, 3000, seed=1, axis_aligned=300)
+    _check_traverse(api, bvh, want.nodes, shapes, rays)
+    bvh.free()
+
+
+@pytest.mark.parametrize("name", ["boxes21", "random3000", "cubes200", "huge300"])
+def test_traverse_parity_f64(api, name):
+    shapes = scene(name, "f64")
+    want = O.build(shapes, "f64")
+    bvh = api.Bvh.build(shapes, prec="f64")
+    rays = rays_for(shapes, 2000, "f64", seed=2, axis_aligned=200)
+    _check_traverse(api, bvh, want.nodes, shapes, rays, "f64")
+    bvh.free()
+
+
+def test_empty_tree_and_empty_batch(api):
+    e = scene("empty")
+    bvh = api.Bvh.build(e)
+    assert len(bvh.nodes) == 0 and len(bvh.flatten()) == 0
+    rays = rays_for(e, 10)
+    off, hits = bvh.traverse_batch(rays)
+    assert off.tolist() == [0] * 11 and len(hits) == 0
+    shapes = scene("boxes21")
+    b2 = api.Bvh.build(shapes)
+    off, hits = b2.traverse_batch(rays[:0])
+    assert off.tolist() == [0] and len(hits) == 0
+
+
+def test_reference_kats_through_the_api(api):
+    """The reference's own fixed-scene tests (testbase.rs:174-225, bvh_impl.rs:665-690) driven through the product API."""
+    import json, os
+
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+    class UnitBox:                                  # testbase.rs:66-103
+        def __init__(self, id, pos):
+            self.id, self.pos, self.node_index = id, np.array(pos, dtype=np.float32), 0
+
+        def aabb(self):
+            return self.pos + np.float32(-0.5), self.pos + np.float32(0.5)
+
+        def set_bh_node_index(self, i):
+            self.node_index = i
+
+    boxes = [UnitBox(x, (x, 0.0, 0.0)) for x in range(-10, 11)]
+    for builder in (api.Bvh.build, api.Bvh.build_par):
+        bvh = builder(boxes)
+        assert [b.node_index for b in boxes] == G["derived"]["aligned_boxes_21_node_index"]
+        flat = bvh.flatten()
+        for case in G["aligned_boxes_21"]["rays"]:
+            ray = api.Ray.new([case["origin"]], [case["direction"]])
+            for got in (bvh.traverse(ray, boxes), list(bvh.traverse_iterator(ray, boxes)), flat.traverse(ray, boxes)):
+                assert sorted(b.id for b in got) == sorted(case["hit_ids"])
+    for case in G["one_node_bvh"]["cases"]:
+        one = [UnitBox(0, case["box_center"])]
+        bvh = api.Bvh.build(one)
+        ray = api.Ray.new([case["origin"]], [case["direction"]])
+        assert len(bvh.traverse(ray, one)) == case["hits"]
+        assert len(list(bvh.traverse_iterator(ray, one))) == case["hits"]
+        assert len(bvh.flatten().traverse(ray, one)) == case["hits"]
+    k = G["sah_pairing"]
+    three = [UnitBox(i, c) for i, c in enumerate(k["box_centers"])]
+    bvh = api.Bvh.build(three)
+    a, b = k["same_parent"]
+    assert bvh.nodes[three[a].node_index]["parent"] == bvh.nodes[three[b].node_index]["parent"]
+
+
+def test_ray_new_parity(api):
+    rng = np.random.default_rng(5)
+    o = rng.uniform(-1e5, 1e5, (5000, 3))
+    d = rng.uniform(-1e5, 1e5, (5000, 3))
+    d[:50, 0] = 0.0
+    d[50:60, 1:] = 0.0
+    for prec in ("f32", "f64"):
+        got = api.Ray.new(o, d, prec)
+        want = O.ray_new(o, d, prec)
+        for f in ("origin", "direction", "inv_direction"):
+            assert np.array_equal(got[f], want[f], equal_nan=True), (prec, f)
+
+
+def test_tree_from_nodes_roundtrip(api):
+    shapes = scene("cubes100")
+    want = O.build(shapes)
+    bvh = api.Bvh.from_nodes(want.nodes, shapes)
+    assert _nodes_equal(bvh.nodes, want.nodes)
+    assert np.array_equal(bvh.node_index, want.node_index)
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes))
+    rays = rays_for(shapes, 2000, seed=3)
+    _check_traverse(api, bvh, want.nodes, shapes, rays)
+    # a node array that is not in preorder layout is refused, not mis-traversed
+    from bvh_b200 import capi
+    bad = want.nodes.copy()
+    bad[0]["child_l"], bad[0]["child_r"] = bad[0]["child_r"], bad[0]["child_l"]
+    with pytest.raises(capi.BvhGpuError):
+        api.Bvh.from_nodes(bad, shapes)
+
+
+def test_nan_input_is_an_error(api):
+    from bvh_b200 import capi
+
+    shapes = scene("random1000").copy()
+    shapes["min"][123][1] = np.nan
+    with pytest.raises(capi.BvhGpuError) as e:
+        api.Bvh.build(shapes)
+    assert e.value.status == capi.ERR_NAN
+
+
+def test_sah_cost_matches_oracle(api):
+    shapes = scene("cubes1000")
+    want = O.build(shapes)
+    bvh = api.Bvh.build(shapes)
+    got, ref = bvh.sah_cost(), O.sah_cost(want.nodes)
+    assert got[0] == pytest.approx(ref[0], rel=1e-12) and got[1] == pytest.approx(ref[1], rel=1e-12)
+
+
+def test_refit_keeps_the_tree_valid(api):
+    """bvhgpu_refit = the data-parallel part of update_shapes (optimization.rs:304-351): after moving
+    shapes the tree must be consistent and tight again (optimization.rs:648-669 asserts exactly that)."""
+    shapes = scene("cubes1000").copy()
+    bvh = api.Bvh.build(shapes)
+    assert O.is_consistent(bvh.nodes, shapes) and O.is_tight(bvh.nodes)
+    rng = np.random.default_rng(9)
+    moved = rng.choice(len(shapes), 9000, replace=False)
+    delta = rng.uniform(-5000, 5000, (9000, 3)).astype(np.float32)
+    shapes["min"][moved] += delta
+    shapes["max"][moved] += delta
+    assert not O.is_consistent(bvh.nodes, shapes)
+    topo = bvh.nodes[["parent", "child_l", "child_r", "shape"]].copy()
+    bvh.refit(shapes)
+    assert O.is_consistent(bvh.nodes, shapes) and O.is_tight(bvh.nodes)
+    assert np.array_equal(bvh.nodes[["parent", "child_l", "child_r", "shape"]], topo)
+    # traversal of the refitted tree == oracle traversal of the same node array
+    rays = rays_for(shapes, 2000, seed=4)
+    _check_traverse(api, bvh, bvh.nodes, shapes, rays)
+
+
+def test_config2_full_size(api):
+    """BASELINE.json configs[1]: 120k-triangle scene, 1M create_ray rays: bit-exact build + flatten, identical
+    hit lists for all 1M rays (the oracle needs a few seconds for this)."""
+    shapes = O.create_n_cubes(10_000)
+    want = O.build(shapes)
+    bvh = api.Bvh.build(shapes)
+    assert _nodes_equal(bvh.nodes, want.nodes)
+    assert np.array_equal(bvh.node_index, want.node_index)
+    flat = O.flatten(want.nodes)
+    assert _flat_equal(bvh.flatten().nodes, flat)
+    rays, _ = O.create_rays(1_000_000)
+    r = O.traverse(flat, shapes, rays, O.MODE_FLAT, threads=O.hardware_threads())
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    assert len(hits) / len(rays) == 2.0          # survey fingerprint (derived)
+
+
+def test_large_build_properties(api):
+    """1.2M shapes (beyond what the reference benches): GPU == oracle, plus the size-independent invariants."""
+    shapes = O.create_n_cubes(100_000)
+    bvh = api.Bvh.build(shapes)
+    nodes, idx = bvh.nodes, bvh.node_index
+    n = len(shapes)
+    leaves = nodes["child_l"] == O.U32_MAX
+    assert leaves.sum() == n and np.array_equal(np.sort(nodes["shape"][leaves]), np.arange(n))
+    assert np.array_equal(nodes["shape"][idx], np.arange(n))
+    assert O.is_consistent(nodes, shapes) and O.is_tight(nodes)
+    want = O.build(shapes, threads=O.hardware_threads())
+    assert _nodes_equal(nodes, want.nodes)
+
+
+def test_device_pointer_entry_points(api):
+    import torch
+
+    from bvh_b200 import capi
+    from bvh_b200.dtypes import AABB3F, RAY3F
+
+    shapes = scene("cubes1000")
+    want = O.build(shapes)
+    rays = rays_for(shapes, 5000, seed=6)
+    dev = torch.device("cuda", 0)
+    ctx = api.Context.default()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        d_aabb = torch.from_numpy(shapes.view(np.uint8).reshape(-1)).to(dev)
+        d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev)
+        d_off = torch.empty(len(rays) + 1, dtype=torch.int32, device=dev)
+        d_hits = torch.empty(16 * len(rays), dtype=torch.int32, device=dev)
+        bvh = api.Bvh.build_dev(d_aabb.data_ptr(), len(shapes))
+        total = bvh.traverse_dev(d_rays.data_ptr(), len(rays), d_off.data_ptr(), d_hits.data_ptr(), d_hits.numel(), want_total=True)
+        r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE)
+        assert total == len(r.hits)
+        assert np.array_equal(d_off.cpu().numpy().view(np.uint32).astype(np.uint64), r.offsets)
+        assert np.array_equal(d_hits[:total].cpu().numpy().view(np.uint32), r.hits)
+        assert _nodes_equal(bvh.nodes, want.nodes)
+    finally:
+        ctx.set_stream(None)
