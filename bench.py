@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on BASELINE.json configs[1]:
+120 000-triangle random-cube scene (create_n_cubes(10 000), src/testbase.rs:608-615), 1 M create_ray rays
+(src/testbase.rs:687-691), f32/3D.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path's query side over one ray batch: batched Bvh::traverse of 1 M rays
+against the device-resident tree, producing the CSR hit lists (at N > 1 every rank traverses its own
+1 M-ray shard of the seed chain and the per-rank hit lists are all-gathered over NCCL inside the step:
+weak scaling).  `value` = rays of all ranks / max-over-ranks mean step time, inputs resident in HBM.
+The build side (Bvh::build + flatten, Mprims/s) is timed in the same run and reported under "build".
+`e2e` is the same traversal through the host-pointer C-ABI call (pinned host rays in, host CSR out).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CUBES = 10_000           # 120 000 triangles
+N_RAYS = 1_000_000
+METRIC = "traversal_Mrays_per_s"
+UNIT = "Mrays/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU path (the C++ restatement in oracle/: the Rust crate cannot be built in this
+    image), all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    threads = O.hardware_threads()
+    shapes = O.create_n_cubes(N_CUBES)
+    res = O.build(shapes, threads=threads)
+    sample = 250_000
+    rays, _ = O.create_rays(sample)
+    for _ in range(args.warmup):
+        O.traverse(res.nodes, shapes, rays[:20_000], O.MODE_RECURSIVE, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads)      # Bvh::traverse, rays split over all cores
+    dt = (time.perf_counter() - t0) / args.steps
+    tb = []
+    for _ in range(3):
+        t1 = time.perf_counter(); O.build(shapes, threads=threads); tb.append(time.perf_counter() - t1)
+    value = sample / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: create_n_cubes(10000) = 120000 triangles, create_ray rays from seed 0, Bvh::traverse (recursive)",
+                   "rays_per_step": sample, "note": "C++ restatement of the reference (oracle/), no Rust toolchain in the image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} rays/step x {args.steps} steps, rays split evenly over {threads} threads"},
+        "build": {"value": len(shapes) / min(tb) / 1e6, "unit": "Mprims/s", "cores": threads, "what": "Bvh::build_par analogue (fork-join, grain 64), best of 3"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bvh_b200 import api, capi, scenes
+    from bvh_b200.dist import allgather_csr
+    from bvh_b200.dtypes import RAY3F
+
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- inputs: generated on the host once, resident in HBM before anything is timed -------------------
+    aabbs = scenes.create_n_cubes_aabbs(N_CUBES)
+    n = len(aabbs)
+    d_aabbs = torch.from_numpy(aabbs.view(np.uint8).reshape(-1)).to(dev)
+    o, d = scenes.ray_endpoints(N_RAYS, first_ray=rank * N_RAYS)          # rank r owns rays [r*1M, (r+1)*1M) of the seed chain
+    d_o, d_d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+    d_rays = torch.empty(N_RAYS * RAY3F.itemsize, dtype=torch.uint8, device=dev)
+    capi.check(capi.lib().bvhgpu_rays_new_dev_f32x3(ctx._h, d_o.data_ptr(), d_d.data_ptr(), N_RAYS, d_rays.data_ptr()))   # Ray::new on the device
+    cap = 8 * N_RAYS
+    d_off = torch.empty(N_RAYS + 1, dtype=torch.int32, device=dev)
+    d_hits = torch.empty(cap, dtype=torch.int32, device=dev)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    bvh = api.Bvh.build_dev(d_aabbs.data_ptr(), n)
+    bvh.flatten()
+    ctx.synchronize()
+    ctx.set_option("profile", 1)
+
+    def step():
+        total = bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap, want_total=(world > 1))
+        if world > 1:      # the path's one exchange step: all-gather of the hit lists (NCCL over NVLink)
+            allgather_csr(d_off.to(torch.int64), d_hits, total)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    walk_ms = []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        if rank == 0:
+            walk_ms.append(ctx.get_metric("walk_ms"))
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    value = world * N_RAYS / (step_ms * 1e-3) / 1e6
+
+    if world > 1:
+        if rank == 0:
+            line = _base_line(args, value, step_ms, launches, clocks)
+            line["config"]["parallelism"] = f"ray batch sharded over {world} GPUs (1M rays each), tree replicated, NCCL all-gather of CSR hit lists inside the step"
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
+
+    # ---- single GPU extras: roofline of the dominant kernel, build, e2e, cpu baseline -------------------
+    visits, hits_total = _stats_after_sync_traverse(bvh, d_rays, d_off, d_hits, cap)
+    walk = sum(walk_ms) / len(walk_ms)
+    alg_bytes = N_RAYS * 36 + visits * 32 + N_RAYS * 4 + hits_total * 4        # DESIGN.md "algorithmic bytes, traversal"
+    peak, peak_src = _peaks()
+    achieved = alg_bytes / (walk * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "walk_count_kernel<float,false>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _ncu_traffic(), "peak_source": peak_src, "bytes_per_launch": alg_bytes, "kernel_ms": walk,
+                "node_visits_per_ray": visits / N_RAYS, "note": "tree (7.7 MB) is L2-resident by construction; bytes are algorithmic, not DRAM"}
+
+    # build: Bvh::build (+ flatten) of the 120k scene, device-resident AABBs, events around each build
+    ctx.set_option("profile", 0)
+    bt = []
+    for k in range(3 + 10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        b2 = api.Bvh.build_dev(d_aabbs.data_ptr(), n)
+        b2.flatten_dev()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        b2.free()
+        if k >= 3:
+            bt.append(e0.elapsed_time(e1))
+    bt.sort()
+    build_ms = bt[len(bt) // 2]
+
+    # e2e: the host-pointer C-ABI call, pinned host buffers, H2D + traverse + D2H inside the timed region
+    h_rays = torch.empty(N_RAYS * RAY3F.itemsize, dtype=torch.uint8).pin_memory()
+    h_rays.copy_(d_rays.cpu())
+    h_off = torch.empty(N_RAYS + 1, dtype=torch.int32).pin_memory()
+    h_hits = torch.empty(cap, dtype=torch.int32).pin_memory()
+    import ctypes as C
+    tot = C.c_size_t(0)
+    fn = capi.lib().bvhgpu_traverse_f32x3
+
+    def e2e_step():
+        capi.check(fn(bvh._h, capi.TRAVERSE_BVH, h_rays.data_ptr(), N_RAYS, h_off.data_ptr(), h_hits.data_ptr(), cap, C.byref(tot)))
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()                       # synchronous call: returns when offsets + hits are in host memory
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e = {"value": N_RAYS / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": N_RAYS * 36, "d2h_bytes_per_step": (N_RAYS + 1) * 4 + int(tot.value) * 4,
+           "ms_per_step": e2e_s * 1e3}
+
+    line = _base_line(args, value, step_ms, launches, clocks)
+    line["roofline"] = roofline
+    line["e2e"] = e2e
+    line["build"] = {"value": n / (build_ms * 1e-3) / 1e6, "unit": "Mprims/s", "ms": build_ms, "what": "Bvh::build (exact SAH, bit-identical) + flatten, 120000 shapes, AABBs resident in HBM, median of 10"}
+    line["cpu_baseline"] = _cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+def _stats_after_sync_traverse(bvh, d_rays, d_off, d_hits, cap):
+    bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap, want_total=True)
+    return bvh.traverse_stats()
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the walk kernel from the committed ncu capture (profiles/), if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("walk_count_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def _base_line(args, value, step_ms, launches, clocks):
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: create_n_cubes(10000) = 120000 triangles, 1M create_ray rays per GPU from seed 0, batched Bvh::traverse -> CSR hit lists",
+                   "rays_per_gpu": N_RAYS, "shapes": 12 * N_CUBES, "l2": "512 MB flush write between timed iterations", "builder": "exact_sah"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+
+
+def _cpu_baseline():
+    from oracle import oracle as O
+
+    threads = O.hardware_threads()
+    shapes = O.create_n_cubes(N_CUBES)
+    res = O.build(shapes, threads=threads)
+    sample = 1_000_000 if threads >= 16 else 250_000
+    rays, _ = O.create_rays(sample)
+    O.traverse(res.nodes, shapes, rays[:50_000], O.MODE_RECURSIVE, threads=threads)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or time.perf_counter() - t0 < 10.0:
+        O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads)
+        reps += 1
+        if reps >= 40:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    t1 = time.perf_counter(); O.build(shapes, threads=1); b1 = time.perf_counter() - t1
+    tb = []
+    for _ in range(3):
+        t1 = time.perf_counter(); O.build(shapes, threads=threads); tb.append(time.perf_counter() - t1)
+    return {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample} of the 1M rays x {reps} reps, Bvh::traverse (recursive), rays split evenly over {threads} threads",
+            "build_Mprims_per_s_1thread": len(shapes) / b1 / 1e6, "build_Mprims_per_s_all_threads": len(shapes) / min(tb) / 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -208,6 +208,12 @@ class Bvh:
         capi.check(getattr(capi.lib(), f"bvhgpu_flatten_{self._d['suffix']}")(self._h, _ptr(out), cap, C.byref(ln)))
         return FlatBvh(self, out[: ln.value])
 
+    def flatten_dev(self) -> int:
+        """Build the FlatBvh on the device only (no host copy, asynchronous); returns its length."""
+        ln = C.c_size_t(0)
+        capi.check(getattr(capi.lib(), f"bvhgpu_flatten_{self._d['suffix']}")(self._h, None, 0, C.byref(ln)))
+        return ln.value
+
     # ---- traversal ---------------------------------------------------------------------------------
     def traverse_batch(self, rays: np.ndarray, mode: int = capi.TRAVERSE_BVH, cap: int | None = None):
         """CSR (offsets u32[nrays+1], hits u32[total]); hits of a ray are in the reference's DFS order."""
