@@ -96,7 +96,7 @@ def run_reference(args):
     threads = O.hardware_threads()
     shapes = O.create_n_cubes(N_CUBES)
     res = O.build(shapes, threads=threads)
-    sample = 250_000
+    sample = 1_000_000
     rays, _ = O.create_rays(sample)
     for _ in range(args.warmup):
         O.traverse(res.nodes, shapes, rays[:20_000], O.MODE_RECURSIVE, threads=threads)
@@ -159,7 +159,7 @@ def run_b200(args):
     d_hits = torch.empty(cap, dtype=torch.int32, device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
-    bvh = api.Bvh.build_dev(d_aabbs.data_ptr(), n)
+    bvh = api.Bvh.build_dev(d_aabbs.data_ptr(), n, ctx=ctx)
     bvh.flatten()
     ctx.synchronize()
     ctx.set_option("profile", 1)
@@ -228,7 +228,7 @@ def run_b200(args):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        b2 = api.Bvh.build_dev(d_aabbs.data_ptr(), n)
+        b2 = api.Bvh.build_dev(d_aabbs.data_ptr(), n, ctx=ctx)
         b2.flatten_dev()
         e1.record(stream)
         torch.cuda.synchronize(dev)

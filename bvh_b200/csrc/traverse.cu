@@ -43,19 +43,23 @@ __device__ __forceinline__ bool slab_hit(const T o[3], const T inv[3], const T m
     return !nan && tmax >= lo;                                  // :35
 }
 
-// ---- record fetch ------------------------------------------------------------------------------------
+// ---- record fetch: ONE 256-bit load per record (LDG.E.256, sm_100a) -------------------------------------
+// A divergent warp pays one L1 tag lookup ("wavefront") per distinct line per load instruction, and this
+// kernel is L1-wavefront bound, so a single 32-byte load instead of two 16-byte loads halves the cost.
 __device__ __forceinline__ void fetch(const TNodeF* __restrict__ p, float mn[3], float mx[3], uint32_t& skip, uint32_t& shape) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    mn[0] = a.x; mn[1] = a.y; mn[2] = a.z; skip = __float_as_uint(a.w);
-    mx[0] = b.x; mx[1] = b.y; mx[2] = b.z; shape = __float_as_uint(b.w);
+    float sk, sh;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(mn[0]), "=f"(mn[1]), "=f"(mn[2]), "=f"(sk), "=f"(mx[0]), "=f"(mx[1]), "=f"(mx[2]), "=f"(sh)
+                 : "l"(p));
+    skip = __float_as_uint(sk);
+    shape = __float_as_uint(sh);
 }
 __device__ __forceinline__ void fetch(const TNodeD* __restrict__ p, double mn[3], double mx[3], uint32_t& skip, uint32_t& shape) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    const double2 c = __ldg(reinterpret_cast<const double2*>(p) + 2);
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(p) + 3);
-    mn[0] = a.x; mn[1] = a.y; mn[2] = b.x; mx[0] = b.y; mx[1] = c.x; mx[2] = c.y; skip = d.x; shape = d.y;
+    double w;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mn[0]), "=d"(mn[1]), "=d"(mn[2]), "=d"(mx[0]) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx[1]), "=d"(mx[2]), "=d"(w), "=d"(w) : "l"(reinterpret_cast<const char*>(p) + 32));
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p) + 48));
+    skip = t.x; shape = t.y;
 }
 
 // The walk.  `emit(shape)` is called for every reported shape in reference order.
