@@ -48,6 +48,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -59,7 +66,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc:
@@ -69,7 +76,11 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        inside = [l for (t, l) in self.lines if self.t0 is not None and self.t0 - 0.15 <= t <= (self.t1 or t) + 0.15]
+        window = "timed region"
+        if not inside:                     # region shorter than the sampling period: fall back to the whole (loaded) run
+            inside, window = [l for (_, l) in self.lines], "warm-up + timed region"
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -81,7 +92,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -143,7 +154,8 @@ def run_b200(args):
     from bvh_b200.dtypes import RAY3F
 
     ctx = api.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)            # everything timed runs on this one stream (torch events see it)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # ---- inputs: generated on the host once, resident in HBM before anything is timed -------------------
@@ -175,17 +187,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
     barrier()
-
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     walk_ms = []
     barrier()
+    sampler.mark_begin()
     for k in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the event pair)
         ev[k][0].record(stream)
@@ -194,6 +206,7 @@ def run_b200(args):
         if rank == 0:
             walk_ms.append(ctx.get_metric("walk_ms"))
     barrier()
+    sampler.mark_end()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop()
     step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
@@ -323,7 +336,7 @@ def _cpu_baseline():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

@@ -47,7 +47,11 @@ class Context:
         return cls._default[device]
 
     def set_stream(self, cuda_stream_handle: int | None):
-        capi.check(capi.lib().bvhgpu_set_stream(self._h, C.c_void_p(cuda_stream_handle or 0)))
+        """Enqueue on the given cudaStream_t handle (0 = CUDA's legacy default stream); None = the context's own stream."""
+        if cuda_stream_handle is None:
+            capi.check(capi.lib().bvhgpu_reset_stream(self._h))
+        else:
+            capi.check(capi.lib().bvhgpu_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
 
     def synchronize(self):
         capi.check(capi.lib().bvhgpu_synchronize(self._h))

@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
     L.bvhgpu_destroy.argtypes = [vp]
     L.bvhgpu_destroy.restype = None
     L.bvhgpu_set_stream.argtypes = [vp, vp]
+    L.bvhgpu_reset_stream.argtypes = [vp]
     L.bvhgpu_synchronize.argtypes = [vp]
     L.bvhgpu_launch_count.argtypes = [vp]
     L.bvhgpu_launch_count.restype = C.c_uint64

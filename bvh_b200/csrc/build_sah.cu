@@ -21,6 +21,8 @@
 // follow the reference rule child_l = i+1, child_r = i + 2*n_l (bvh_node.rs:138-142), so the
 // output array IS the reference's preorder `Bvh.nodes`.
 #include "internal.h"
+#include <vector>
+#include <cstdlib>
 
 namespace bvhb200 {
 
@@ -79,6 +81,8 @@ template <class T> struct BuildParams {
     BuildStatus* status;
     uint32_t n;
     unsigned long long timeout_ns;
+    uint4* trace;                   // optional task log (BVHGPU_TRACE=file): {kind<<28|count, node/sid, t0_ns, t1_ns}
+    uint32_t trace_cap;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -510,10 +514,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T
         if (lane == 0) {
             ticket = atomicAdd(&P.ctl->head, 1u);
             const uint32_t* seq = P.qseq + (ticket & P.qmask);
-            uint32_t spins = 0, ns = 32;
+            uint32_t spins = 0, ns = 64;
             for (;;) {
-                if (ld_acquire(seq) == ticket + 1u) break;
-                if ((spins & 7u) == 0u) {
+                // relaxed poll: an acquire load would invalidate this SM's whole L1 (CCTL.IVALL) on every spin
+                if (ld_relaxed(seq) == ticket + 1u) break;
+                if ((spins & 3u) == 0u) {
                     if (ld_relaxed(&P.ctl->leaves_done) >= P.n || ld_relaxed(&P.ctl->error) != 0u) { stop = 1; break; }
                 }
                 if ((++spins & 1023u) == 0u) {
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T
                     }
                 }
                 __nanosleep(ns);
-                if (ns < 512) ns <<= 1;
+                if (ns < 1024) ns <<= 1;
             }
         }
         stop = __shfl_sync(0xffffffffu, stop, 0);
@@ -533,9 +538,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T
         __threadfence();
         QSlot<T> s;
         load_struct_cg(s, P.q + (ticket & P.qmask));
+        unsigned long long tr0 = 0;
+        if (P.trace) tr0 = global_timer_ns();
         if (s.kind == KIND_SEG) process_seg(P, ws, s.t, leaves);
         else if (s.kind == KIND_BIN) process_bin_tile(P, ws, s.a, s.b, leaves);
         else process_scatter_tile(P, ws, s.a, s.b, leaves);
+        if (P.trace && lane == 0 && ticket < P.trace_cap) {
+            const unsigned long long base = *(volatile unsigned long long*)&P.ctl->t_start;
+            P.trace[ticket] = make_uint4((s.kind << 28) | (s.kind == KIND_SEG ? s.t.count : s.b), s.kind == KIND_SEG ? s.t.node : s.a,
+                                         (uint32_t)(tr0 - base), (uint32_t)(global_timer_ns() - base));
+        }
         if (leaves) {
             __threadfence();
             if (lane == 0) atomicAdd(&P.ctl->leaves_done, leaves);
@@ -685,6 +697,12 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
     P.idx[0] = idx0;
     P.idx[1] = idx1;
+    const char* trace_path = getenv("BVHGPU_TRACE");
+    if (trace_path && n > 1) {
+        P.trace_cap = 4u * n + 4096u;
+        BVH_TRY(dalloc_t(ctx, &P.trace, P.trace_cap));
+        BVH_CUDA_TRY(cudaMemsetAsync(P.trace, 0, sizeof(uint4) * P.trace_cap, st));
+    }
 
     init_keys_kernel<T><<<1, 32, 0, st>>>(P.rootkeys, P.ctl, P.status);
     ctx->launches++;
@@ -713,6 +731,13 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     finish_status_kernel<T><<<1, 32, 0, st>>>(P.ctl, P.status, n);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
+    if (P.trace) {                          // debugging aid: dump the task log (synchronises)
+        std::vector<uint4> h(P.trace_cap);
+        BVH_CUDA_TRY(cudaMemcpyAsync(h.data(), P.trace, sizeof(uint4) * P.trace_cap, cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(uint4), h.size(), f); fclose(f); }
+        dfree(ctx, P.trace);
+    }
     dfree(ctx, idx0); dfree(ctx, idx1); dfree(ctx, P.bkt); dfree(ctx, P.q); dfree(ctx, P.qseq);
     dfree(ctx, P.big); dfree(ctx, P.tilecnt); dfree(ctx, P.ctl); dfree(ctx, P.rootkeys);
     tree->status_pending = true;

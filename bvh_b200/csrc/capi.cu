@@ -317,7 +317,12 @@ BVH_EXPORT void bvhgpu_destroy(bvhgpu_ctx* ctx) {
 }
 BVH_EXPORT int bvhgpu_set_stream(bvhgpu_ctx* ctx, void* cuda_stream) {
     if (!ctx) { set_error("set_stream: null ctx"); return BVHGPU_ERR_INVALID; }
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_reset_stream(bvhgpu_ctx* ctx) {
+    if (!ctx) { set_error("reset_stream: null ctx"); return BVHGPU_ERR_INVALID; }
+    ctx->stream = ctx->own_stream;
     return BVHGPU_OK;
 }
 BVH_EXPORT int bvhgpu_synchronize(bvhgpu_ctx* ctx) {

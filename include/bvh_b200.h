@@ -88,8 +88,10 @@ int bvhgpu_create(int device, bvhgpu_ctx** out);
 void bvhgpu_destroy(bvhgpu_ctx* ctx);
 const char* bvhgpu_last_error(void);
 const char* bvhgpu_version(void);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+/* Enqueue on an externally owned cudaStream_t (e.g. torch's current stream; 0 is CUDA's legacy default
+ * stream and is honoured as such).  bvhgpu_reset_stream returns to the context's own stream. */
 int bvhgpu_set_stream(bvhgpu_ctx* ctx, void* cuda_stream);
+int bvhgpu_reset_stream(bvhgpu_ctx* ctx);
 int bvhgpu_synchronize(bvhgpu_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);

@@ -315,13 +315,13 @@ inline BuildStats build_par(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, 
 
     auto worker = [&](unsigned tid) {
         std::array<std::vector<uint32_t>, 6> scratch;
-        BuildStats& ls = tstats[tid];
+        BuildStats ls;                              // thread-local copy: no false sharing in the hot loop
         for (;;) {
             BuildArgs<T> a;
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return !queue.empty() || outstanding == 0; });
-                if (queue.empty()) return;
+                if (queue.empty()) { tstats[tid] = ls; return; }
                 a = queue.back();
                 queue.pop_back();
             }

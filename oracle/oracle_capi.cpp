@@ -24,16 +24,23 @@ uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3
     std::vector<int> ok(threads, 1);
     auto work = [&](unsigned t) {
         const uint64_t lo = nrays * t / threads, hi = nrays * (t + 1) / threads;
-        std::vector<uint32_t> out;
-        counts[t].reserve(hi - lo);
+        std::vector<uint32_t> out, mine;
+        std::vector<uint64_t> cnt;
+        TraverseStats ls;                        // thread-local: no false sharing in the hot loop
+        int lok = 1;
+        cnt.reserve(hi - lo);
         for (uint64_t r = lo; r < hi; ++r) {
             out.clear();
-            if (mode == 0) traverse_recursive((const Node<T>*)tree, n_tree, shapes, rays[r], out, &tst[t]);
-            else if (mode == 1) traverse_flat((const FlatNode<T>*)tree, n_tree, shapes, rays[r], out, &tst[t]);
-            else if (!traverse_iterator((const Node<T>*)tree, n_tree, shapes, rays[r], out)) ok[t] = 0;
-            counts[t].push_back(out.size());
-            lists[t].insert(lists[t].end(), out.begin(), out.end());
+            if (mode == 0) traverse_recursive((const Node<T>*)tree, n_tree, shapes, rays[r], out, &ls);
+            else if (mode == 1) traverse_flat((const FlatNode<T>*)tree, n_tree, shapes, rays[r], out, &ls);
+            else if (!traverse_iterator((const Node<T>*)tree, n_tree, shapes, rays[r], out)) lok = 0;
+            cnt.push_back(out.size());
+            mine.insert(mine.end(), out.begin(), out.end());
         }
+        counts[t].swap(cnt);
+        lists[t].swap(mine);
+        tst[t] = ls;
+        ok[t] = lok;
     };
     if (threads == 1) work(0);
     else {
