@@ -111,13 +111,11 @@ def run_reference(args):
     rays, _ = O.create_rays(sample)
     for _ in range(args.warmup):
         O.traverse(res.nodes, shapes, rays[:20_000], O.MODE_RECURSIVE, threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads)      # Bvh::traverse, rays split over all cores
-    dt = (time.perf_counter() - t0) / args.steps
-    tb = []
-    for _ in range(3):
-        t1 = time.perf_counter(); O.build(shapes, threads=threads); tb.append(time.perf_counter() - t1)
+    dt = 0.0
+    for _ in range(args.steps):      # Bvh::traverse, rays split over all cores; time = thread create .. join inside C++
+        dt += O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads).seconds
+    dt /= args.steps
+    tb = [O.build(shapes, threads=threads).seconds for _ in range(3)]
     value = sample / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -317,17 +315,15 @@ def _cpu_baseline():
     sample = 1_000_000 if threads >= 16 else 250_000
     rays, _ = O.create_rays(sample)
     O.traverse(res.nodes, shapes, rays[:50_000], O.MODE_RECURSIVE, threads=threads)
-    reps, t0 = 0, time.perf_counter()
+    reps, t0, secs = 0, time.perf_counter(), 0.0
     while reps < 3 or time.perf_counter() - t0 < 10.0:
-        O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads)
+        secs += O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE, threads=threads).seconds
         reps += 1
         if reps >= 40:
             break
-    dt = (time.perf_counter() - t0) / reps
-    t1 = time.perf_counter(); O.build(shapes, threads=1); b1 = time.perf_counter() - t1
-    tb = []
-    for _ in range(3):
-        t1 = time.perf_counter(); O.build(shapes, threads=threads); tb.append(time.perf_counter() - t1)
+    dt = secs / reps
+    b1 = O.build(shapes, threads=1).seconds
+    tb = [O.build(shapes, threads=threads).seconds for _ in range(3)]
     return {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{sample} of the 1M rays x {reps} reps, Bvh::traverse (recursive), rays split evenly over {threads} threads",
             "build_Mprims_per_s_1thread": len(shapes) / b1 / 1e6, "build_Mprims_per_s_all_threads": len(shapes) / min(tb) / 1e6}

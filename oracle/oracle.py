@@ -68,6 +68,7 @@ def lib():
         _lib.orc_traverse_batch_f32.restype = C.c_uint64
         _lib.orc_traverse_batch_f64.restype = C.c_uint64
         _lib.orc_splitmix64.restype = C.c_uint64
+        _lib.orc_last_build_ns.restype = C.c_uint64
         _lib.orc_hardware_threads.restype = C.c_uint32
         _lib.orc_sizeof.restype = C.c_uint32
         # struct layout must agree with the numpy dtypes
@@ -93,6 +94,7 @@ class BuildResult:
     degenerate_splits: int
     max_depth: int
     nosplit_fallthrough: int
+    seconds: float = 0.0       # wall time inside the C++ build (no numpy allocation)
 
 
 def build(aabbs: np.ndarray, prec: str = "f32", threads: int = 1) -> BuildResult:
@@ -107,7 +109,7 @@ def build(aabbs: np.ndarray, prec: str = "f32", threads: int = 1) -> BuildResult
         getattr(lib(), f"orc_build_{prec}")(_p(aabbs), C.c_uint32(n), _p(nodes), _p(node_index), _p(stats))
     else:
         getattr(lib(), f"orc_build_par_{prec}")(_p(aabbs), C.c_uint32(n), _p(nodes), _p(node_index), _p(stats), C.c_uint32(threads))
-    return BuildResult(nodes, node_index, int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3]))
+    return BuildResult(nodes, node_index, int(stats[0]), int(stats[1]), int(stats[2]), int(stats[3]), lib().orc_last_build_ns() * 1e-9)
 
 
 def flatten(nodes: np.ndarray, prec: str = "f32") -> np.ndarray:
@@ -134,6 +136,7 @@ class TraverseResult:
     slab_tests: int
     leaf_visits: int
     iter_overflow: bool
+    seconds: float = 0.0       # wall time of the traversal section inside C++ (thread create .. join)
 
 
 def traverse(tree: np.ndarray, shapes: np.ndarray, rays: np.ndarray, mode: int = MODE_FLAT, prec: str = "f32",
@@ -145,18 +148,18 @@ def traverse(tree: np.ndarray, shapes: np.ndarray, rays: np.ndarray, mode: int =
     rays = np.ascontiguousarray(rays, dtype=d["ray"])
     nrays = len(rays)
     offsets = np.zeros(nrays + 1, dtype=np.uint64)
-    stats = np.zeros(4, dtype=np.uint64)
+    stats = np.zeros(5, dtype=np.uint64)
     ovf = C.c_int(0)
-    cap = max(16 * nrays, 1024)
+    cap = max(4 * nrays, 1024)
     fn = getattr(lib(), f"orc_traverse_batch_{prec}")
     while True:
-        hits = np.zeros(cap, dtype=np.uint32)
+        hits = np.empty(cap, dtype=np.uint32)
         total = fn(C.c_int(mode), _p(tree), C.c_uint32(len(tree)), _p(shapes), _p(rays), C.c_uint64(nrays),
                    _p(offsets), _p(hits), C.c_uint64(cap), _p(stats), C.c_uint32(threads), C.byref(ovf))
         if total <= cap:
             break
         cap = int(total)
-    return TraverseResult(offsets, hits[:total].copy(), int(stats[0]), int(stats[1]), int(stats[2]), bool(ovf.value))
+    return TraverseResult(offsets, hits[:total].copy(), int(stats[0]), int(stats[1]), int(stats[2]), bool(ovf.value), int(stats[4]) * 1e-9)
 
 
 def is_consistent(nodes, shapes, prec="f32") -> bool:

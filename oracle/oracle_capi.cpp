@@ -42,12 +42,14 @@ uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3
         tst[t] = ls;
         ok[t] = lok;
     };
+    const auto tic = std::chrono::steady_clock::now();
     if (threads == 1) work(0);
     else {
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t);
         for (auto& th : pool) th.join();
     }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count();
     uint64_t total = 0, r = 0;
     for (unsigned t = 0; t < threads; ++t) {
         for (uint64_t c : counts[t]) { if (offsets) offsets[r] = total; total += c; ++r; }
@@ -62,6 +64,7 @@ uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3
     if (stats) {
         stats[0] = stats[1] = stats[2] = stats[3] = 0;
         for (auto& s : tst) { stats[0] += s.node_visits; stats[1] += s.slab_tests; stats[2] += s.leaf_visits; stats[3] += s.hits; }
+        stats[4] = (uint64_t)(secs * 1e9);          // wall time of the traversal section (thread create .. join), ns
     }
     if (overflow32) { *overflow32 = 0; for (int o : ok) if (!o) *overflow32 = 1; }
     return total;
@@ -74,17 +77,23 @@ void tri_aabbs(const T* tris, uint64_t n, Aabb3<T>* out) {
 
 }  // namespace
 
+static uint64_t g_last_build_ns = 0;
+
 #define ORC_API extern "C" __attribute__((visibility("default")))
 
 #define DEFINE_FOR(T, SUF)                                                                                   \
     ORC_API void orc_build_##SUF(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index,   \
                                  uint64_t* stats4) {                                                         \
+        const auto tic = std::chrono::steady_clock::now();                                                   \
         BuildStats st = build(shapes, n, nodes, node_index);                                                 \
+        g_last_build_ns = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count() * 1e9); \
         if (stats4) { stats4[0] = st.prim_visits; stats4[1] = st.degenerate_splits; stats4[2] = st.max_depth; stats4[3] = st.nosplit_fallthrough; } \
     }                                                                                                        \
     ORC_API void orc_build_par_##SUF(const Aabb3<T>* shapes, uint32_t n, Node<T>* nodes, uint32_t* node_index, \
                                      uint64_t* stats4, uint32_t threads) {                                   \
+        const auto tic = std::chrono::steady_clock::now();                                                   \
         BuildStats st = build_par(shapes, n, nodes, node_index, threads);                                    \
+        g_last_build_ns = (uint64_t)(std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count() * 1e9); \
         if (stats4) { stats4[0] = st.prim_visits; stats4[1] = st.degenerate_splits; stats4[2] = st.max_depth; stats4[3] = st.nosplit_fallthrough; } \
     }                                                                                                        \
     ORC_API uint64_t orc_flatten_##SUF(const Node<T>* nodes, uint32_t n_nodes, FlatNode<T>* out, uint64_t cap) { \
@@ -95,9 +104,9 @@ void tri_aabbs(const T* tris, uint64_t n, Aabb3<T>* out) {
     }                                                                                                        \
     ORC_API uint64_t orc_traverse_batch_##SUF(int mode, const void* tree, uint32_t n_tree, const Aabb3<T>* shapes, \
                                               const Ray3<T>* rays, uint64_t nrays, uint64_t* offsets,        \
-                                              uint32_t* hits, uint64_t cap, uint64_t* stats4, uint32_t threads, \
+                                              uint32_t* hits, uint64_t cap, uint64_t* stats5, uint32_t threads, \
                                               int* iter_overflow) {                                          \
-        return traverse_batch<T>(mode, tree, n_tree, shapes, rays, nrays, offsets, hits, cap, stats4, threads, iter_overflow); \
+        return traverse_batch<T>(mode, tree, n_tree, shapes, rays, nrays, offsets, hits, cap, stats5, threads, iter_overflow); \
     }                                                                                                        \
     ORC_API int orc_is_consistent_##SUF(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes) {    \
         return is_consistent(nodes, n_nodes, shapes) ? 1 : 0;                                                \
@@ -140,6 +149,7 @@ void tri_aabbs(const T* tris, uint64_t n, Aabb3<T>* out) {
 DEFINE_FOR(float, f32)
 DEFINE_FOR(double, f64)
 
+ORC_API uint64_t orc_last_build_ns() { return g_last_build_ns; }
 ORC_API uint64_t orc_splitmix64(uint64_t* seed) { return splitmix64(*seed); }
 ORC_API uint32_t orc_hardware_threads() { return std::thread::hardware_concurrency(); }
 ORC_API uint32_t orc_sizeof(int what) {
