@@ -206,22 +206,16 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
-    typename Traits<T>::Ray* d_rays = nullptr;
-    if (nrays) {
-        BVH_TRY(dalloc_t(ctx, &d_rays, nrays));
-        BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(*rays) * nrays, cudaMemcpyHostToDevice, ctx->stream));
-    }
     size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 4 * nrays), 1024);
     size_t tot = 0;
     int rc = BVHGPU_OK;
     for (int attempt = 0; attempt < 2; ++attempt) {
         rc = ensure_result_buffers(tree, nrays, want);
         if (rc != BVHGPU_OK) break;
-        rc = traverse_device<T>(tree, mode, d_rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
+        rc = traverse_device<T>(tree, mode, nullptr, rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
         if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }   // grow once and redo
         break;
     }
-    dfree(ctx, d_rays);
     if (total) *total = tot;
     if (rc != BVHGPU_OK) return rc;
     BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -298,6 +292,10 @@ BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
     ctx->stream = ctx->own_stream;
     BVH_CUDA_TRY(cudaMallocHost((void**)&ctx->h_pinned, 256 * sizeof(uint32_t)));
     for (int i = 0; i < 2; ++i) { BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_walk[i])); BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_build[i])); }
+    BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
+    for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long thr = ~0ull;                       // keep freed blocks cached: alloc/free pairs stay cheap
@@ -311,6 +309,10 @@ BVH_EXPORT void bvhgpu_destroy(bvhgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
+    if (ctx->ev_total) cudaEventDestroy(ctx->ev_total);
+    for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_walk[i]) cudaEventDestroy(ctx->ev_walk[i]); if (ctx->ev_build[i]) cudaEventDestroy(ctx->ev_build[i]); }
     delete ctx;
@@ -388,7 +390,7 @@ BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out)
                                              void* dev_hits, size_t cap, size_t* total) {                                 \
         if (!tree || !dev_offsets || (nrays && !dev_rays)) { set_error("traverse_dev: null argument"); return BVHGPU_ERR_INVALID; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
-        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
         if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \

@@ -47,7 +47,12 @@ struct bvhgpu_ctx {
     cudaEvent_t ev_walk[2] = {nullptr, nullptr};
     cudaEvent_t ev_build[2] = {nullptr, nullptr};
     bool have_walk = false, have_build = false;
+    // host-pointer traversal: H2D chunks on a second stream, overlapped with the walks
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_order = nullptr, ev_total = nullptr;
+    cudaEvent_t ev_chunk[16] = {};
 };
+#define BVH_MAX_CHUNKS 16u
 
 namespace bvhb200 {
 
@@ -99,8 +104,9 @@ template <class T> int sah_cost(Tree<T>* tree, double* out2);
 template <class T> int refit(Tree<T>* tree);                     // recompute child AABBs bottom-up from d_aabb
 
 // ---- traverse.cu ----
-template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, size_t nrays,
-                                       uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
+// d_rays: rays on the device, or nullptr with h_rays = rays in host memory (chunked, overlapped H2D).
+template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays,
+                                       size_t nrays, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
                                        typename Traits<T>::Ray* d_rays);
 

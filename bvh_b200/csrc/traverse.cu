@@ -102,11 +102,14 @@ template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                                          const typename Traits<T>::DAabb* __restrict__ aabb,
                                                          const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
+                                                         uint32_t first, uint32_t count,
                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
                                                          unsigned long long* __restrict__ visit_total) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    // rays [first, first+count) of a batch of nrays (the host-pointer entry point feeds the batch in chunks
+    // so that the H2D copy of chunk c+1 overlaps the walk of chunk c)
+    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t visits = 0;
-    if (r < nrays) {
+    if (r < first + count) {
         T o[3], inv[3];
         load_ray<T>(rays, r, o, inv);
         uint32_t cnt = 0;
@@ -193,8 +196,9 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
 }
 
 template <class T>
-int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, size_t nrays,
+int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays, size_t nrays,
                     uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total) {
+    using Ray = typename Traits<T>::Ray;
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
     if (nrays > 0x7FFFFFFFull) { set_error("traverse: nrays %zu exceeds 2^31-1", nrays); return BVHGPU_ERR_INVALID; }
@@ -219,35 +223,60 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;       // [nblk] block offsets, [nblk] total, [nblk+1] visits
+    Ray* staged = nullptr;
     BVH_TRY(dalloc_t(ctx, &counts, R));
     BVH_TRY(dalloc_t(ctx, &local, R));
     if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
     BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
     BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
-    const int grid = (R + 255) / 256;
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
-    if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
-    if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, sums + nblk + 1);
-    else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, sums + nblk + 1);
-    if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
+    auto launch_walk = [&](const Ray* rays, uint32_t first, uint32_t count) {
+        const int grid = (count + 255) / 256;
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+        ctx->launches++;
+    };
+    if (h_rays) {
+        // Host rays: chunked H2D on the copy stream, walk of chunk c overlaps the copy of chunk c+1.
+        BVH_TRY(dalloc_t(ctx, &staged, R));
+        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));                        // copy stream starts after the allocation point
+        BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
+        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 65536));
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
+            BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));
+            BVH_CUDA_TRY(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+            BVH_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+            launch_walk(staged, lo, hi - lo);
+        }
+        d_rays = staged;
+    } else {
+        if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
+        launch_walk(d_rays, 0, R);
+        if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
+    }
+    const int grid = (R + 255) / 256;
     scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
+    if (total) {                                                  // the total is known before the hit lists are written
+        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
+    }
     if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
     else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
-    ctx->launches += 4;
+    ctx->launches += 3;
     BVH_CUDA_TRY(cudaGetLastError());
     int rc = BVHGPU_OK;
     if (total) {
-        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
-        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        BVH_CUDA_TRY(cudaStreamSynchronize(st));
+        BVH_CUDA_TRY(cudaEventSynchronize(ctx->ev_total));        // emit_kernel keeps running while the host reads the total
         *total = (size_t)h[0];
         tree->last_total = (size_t)h[0];
         tree->last_visits = h[1];
         if (h[0] > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", h[0]); rc = BVHGPU_ERR_CAPACITY; }
         else if (d_hits && h[0] > cap) { set_error("traverse: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
     }
-    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums);
+    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums); if (staged) dfree(ctx, staged);
     return rc;
 }
 
@@ -279,8 +308,8 @@ int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t
     return BVHGPU_OK;
 }
 
-template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
-template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 template int rays_new_device<float>(bvhgpu_ctx*, const float*, const float*, size_t, bvh_ray3f*);
 template int rays_new_device<double>(bvhgpu_ctx*, const double*, const double*, size_t, bvh_ray3d*);
 
