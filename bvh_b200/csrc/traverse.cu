@@ -241,7 +241,7 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         BVH_TRY(dalloc_t(ctx, &staged, R));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));                        // copy stream starts after the allocation point
         BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
-        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 65536));
+        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 250000));   // a walk launch costs ~0.1 ms whatever its size: keep chunks big
         for (uint32_t c = 0; c < nchunks; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
             BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));

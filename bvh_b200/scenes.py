@@ -77,3 +77,17 @@ def ray_endpoints(n: int, first_ray: int = 0, prec: str = "f32", bounds=None):
     u = _splitmix_outputs(2 * first_ray, 2 * n)
     pts = _next_point3(u, bmin, bmax, F)
     return np.ascontiguousarray(pts[0::2]), np.ascontiguousarray(pts[1::2])
+
+
+def pinhole_rays(width: int = 2048, height: int = 2048, prec: str = "f32"):
+    """The coherent primary-ray batch of BASELINE.json configs[2]: pinhole camera at
+    (-15, 2, 0) looking down +x, up = +y, right = +z, 60 degree vertical field of view, row-major pixels.
+    Returns (origins, directions) for Ray::new; all arithmetic in T."""
+    F = BY_PREC[prec]["scalar"]
+    tan_half = F(np.tan(np.deg2rad(30.0)))
+    j, i = np.meshgrid(np.arange(height, dtype=F), np.arange(width, dtype=F), indexing="ij")
+    u = ((i + F(0.5)) / F(width) * F(2) - F(1)) * tan_half * F(width / height)
+    v = (F(1) - (j + F(0.5)) / F(height) * F(2)) * tan_half
+    d = np.stack([np.ones_like(u), v, u], axis=-1).reshape(-1, 3).astype(F)
+    o = np.broadcast_to(np.array([-15.0, 2.0, 0.0], dtype=F), d.shape).copy()
+    return o, d

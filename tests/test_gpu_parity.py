@@ -291,3 +291,74 @@ def test_device_pointer_entry_points(api):
         assert _nodes_equal(bvh.nodes, want.nodes)
     finally:
         ctx.set_stream(None)
+
+
+# ---- the other BASELINE.json configurations as parity cases -------------------------------------------------------
+def test_sponza_build_and_coherent_rays(api):
+    """configs[2]: Sponza (66 450 triangles through the reference loader), 2048 x 2048 coherent pinhole rays."""
+    from bvh_b200 import scenes as S
+    from tests.scenes import sponza
+
+    shapes = sponza()
+    assert len(shapes) == 66_450
+    want = O.build(shapes, threads=O.hardware_threads())
+    bvh = api.Bvh.build(shapes)
+    assert _nodes_equal(bvh.nodes, want.nodes) and np.array_equal(bvh.node_index, want.node_index)
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes))
+    o, d = S.pinhole_rays(2048, 2048)
+    rays = api.Ray.new(o, d)
+    assert np.array_equal(rays["inv_direction"], O.ray_new(o, d)["inv_direction"], equal_nan=True)
+    r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, threads=O.hardware_threads())
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    assert len(hits) > 4 * len(rays)                 # dense scene: many hits per ray, exercises the > K-slots re-walk
+
+
+def test_sponza_incoherent_shard(api):
+    """configs[3]: Sponza, create_ray rays inside the scene bounds (testbase.rs:628-631, 687-691): one 2 M-ray shard."""
+    from bvh_b200 import scenes as S
+    from tests.scenes import sponza
+
+    shapes = sponza()
+    bmin, bmax = shapes["min"].min(axis=0), shapes["max"].max(axis=0)
+    want = O.build(shapes, threads=O.hardware_threads())
+    bvh = api.Bvh.build(shapes)
+    first = 6_000_000                                  # the shard rank 3 of 8 would own
+    o, d = S.ray_endpoints(2_000_000, first_ray=first, bounds=(bmin, bmax))
+    rays = api.Ray.new(o, d)
+    r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, threads=O.hardware_threads())
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    # the vectorised chain == the scalar chain for a shard that does not start at ray 0
+    b = np.zeros(1, dtype=O.AABB3F); b["min"], b["max"] = bmin, bmax
+    seed_rays, _ = O.create_rays(1000, bounds=b)
+    o0, d0 = S.ray_endpoints(1000, 0, bounds=(bmin, bmax))
+    assert np.array_equal(seed_rays["origin"], o0)
+
+
+def test_config5_ten_million_f64(api):
+    """configs[4]: 10 M triangles, f64: full exact-SAH build bit-identical to the oracle, SAH cost equal,
+    then move 1 % of the shapes, refit, and check the reference's consistency + tightness invariants."""
+    from bvh_b200 import scenes as S
+
+    shapes = S.create_n_cubes_aabbs(833_334, "f64")[:10_000_000]
+    want = O.build(shapes, "f64", threads=O.hardware_threads())
+    bvh = api.Bvh.build(shapes, prec="f64")
+    nodes = bvh.nodes
+    assert _nodes_equal(nodes, want.nodes)
+    assert np.array_equal(bvh.node_index, want.node_index)
+    got, ref = bvh.sah_cost(), O.sah_cost(want.nodes, "f64")
+    assert got[0] == pytest.approx(ref[0], rel=1e-9) and got[1] == pytest.approx(ref[1], rel=1e-9)
+    rng = np.random.default_rng(11)
+    moved = rng.choice(len(shapes), len(shapes) // 100, replace=False)
+    delta = rng.uniform(-10.0, 10.0, (len(moved), 3))          # max offset 10.0 as in optimization.rs:702
+    shapes = shapes.copy()
+    shapes["min"][moved] += delta
+    shapes["max"][moved] += delta
+    bvh.refit(shapes)
+    nodes = bvh.nodes
+    assert O.is_consistent(nodes, shapes, "f64") and O.is_tight(nodes, "f64")
+    # SAH cost after refit vs a fresh oracle rebuild of the moved scene: stated tolerance 10 % (SURVEY 8d)
+    rebuilt = O.build(shapes, "f64", threads=O.hardware_threads())
+    c_refit, c_rebuild = bvh.sah_cost()[0], O.sah_cost(rebuilt.nodes, "f64")[0]
+    assert c_refit <= 1.10 * c_rebuild, (c_refit, c_rebuild)
