@@ -29,7 +29,8 @@ namespace bvhb200 {
 constexpr int TILE = 256;              // shapes per tile task of a multi-warp segment
 constexpr int WARPS_PER_CTA = 8;
 constexpr int LOCAL_STACK = 24;        // per-warp DFS stack (entries)
-constexpr uint32_t LOCAL_MAX = 32;     // right children up to this size stay on the warp's own stack
+constexpr uint32_t LOCAL_MAX = 6;      // right children up to this size stay on the warp's own stack; larger ones go to
+                                       // the global queue: idle warps are plentiful, the critical path is what matters
 constexpr uint32_t KIND_SEG = 0, KIND_BIN = 1, KIND_SCATTER = 2;
 
 template <class T> struct __align__(16) BTask {
@@ -56,8 +57,6 @@ template <class T> struct __align__(16) WarpScratch {
     uint32_t cnt[8];
     T child[24];
     BTask<T> stack[LOCAL_STACK];
-    T pf[9][32];                                // warp_subtree: register permutation staging (aabb min/max, centroid)
-    uint32_t pid[32];
 };
 struct BuildCtl {
     uint32_t head, tail, leaves_done, error;
@@ -351,214 +350,12 @@ __device__ __forceinline__ void dispatch_children(const BuildParams<T>& P, BTask
     }
 }
 
-// ---- warp_subtree: a range of <= 32 shapes is finished entirely in registers ----------------------------
-// Lane p holds the shape at position p of the range (id, AABB, centroid) and the descriptor of the node that
-// currently owns position p.  All nodes of one tree level are split simultaneously: bucket statistics per
-// (node, bucket) group with __match_any_sync + REDUX on order-preserving keys, the 5 split costs with two
-// sweeps over the 6 buckets, the stable partition as a lane permutation.  No index-buffer traffic at all;
-// the only global accesses are the initial gather and the node / leaf writes.
-__device__ __forceinline__ uint32_t group_min(uint32_t mask, uint32_t v) { return __reduce_min_sync(mask, v); }
-__device__ __forceinline__ uint32_t group_max(uint32_t mask, uint32_t v) { return __reduce_max_sync(mask, v); }
-__device__ __forceinline__ unsigned long long group_min(uint32_t mask, unsigned long long v) {
-    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-    const uint32_t mh = __reduce_min_sync(mask, hi);
-    const uint32_t ml = __reduce_min_sync(mask, hi == mh ? lo : 0xFFFFFFFFu);
-    return ((unsigned long long)mh << 32) | ml;
-}
-__device__ __forceinline__ unsigned long long group_max(uint32_t mask, unsigned long long v) {
-    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-    const uint32_t mh = __reduce_max_sync(mask, hi);
-    const uint32_t ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
-    return ((unsigned long long)mh << 32) | ml;
-}
-template <class K> __device__ __forceinline__ K shfl_key(K v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-template <class T>
-__device__ void warp_subtree(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t& leaves) {
-    using Tr = Traits<T>;
-    using Key = typename Tr::Key;
-    const uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = lane_id(), lt = lanemask_lt();
-    const uint32_t buf = t.parent_buf >> 31;
-    const Key KMIN = Tr::KEY_POS_INF, KMAX = Tr::KEY_NEG_INF;
-    const T K6 = sub_rn(T(6), T(0.01));
-    // the shape at my position
-    uint32_t id = 0;
-    T mn[3], mx[3], c[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { mn[k] = Tr::inf(); mx[k] = -Tr::inf(); c[k] = T(0); }
-    bool active = lane < t.count;
-    if (active) {
-        id = __ldcg(P.idx[buf] + t.start + lane);
-        load_aabb(P.aabb + id, mn, mx);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) c[k] = center1(mn[k], mx[k]);
-    }
-    // the node that owns my position
-    uint32_t s0 = 0, cnt = t.count, node = t.node, parent = t.parent_buf & 0x7FFFFFFFu;
-    T ab[6], cb[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { ab[k] = t.ab[k]; cb[k] = t.cb[k]; }
-
-    while (__ballot_sync(FULL, active)) {
-        const uint32_t segmask = active ? ((cnt >= 32 ? FULL : ((1u << cnt) - 1u)) << s0) : (1u << lane);
-        // split axis / extent (aabb_impl.rs:594-596, bvh_node.rs:107-114)
-        int axis = 0;
-        T ext = sub_rn(cb[3], cb[0]), cbmin = cb[0];
-        { const T sy = sub_rn(cb[4], cb[1]), sz = sub_rn(cb[5], cb[2]);
-          if (sy > ext) { axis = 1; ext = sy; cbmin = cb[1]; }
-          if (sz > ext) { axis = 2; ext = sz; cbmin = cb[2]; } }
-        const bool degenerate = ext < Tr::eps();
-        int b = 0;
-        if (active) {
-            if (degenerate) b = (lane - s0) < cnt / 2 ? 0 : 1;
-            else {
-                const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
-                b = (int)mul_rn(div_rn(sub_rn(ca, cbmin), ext), K6);
-                b = b < 0 ? 0 : (b > 5 ? 5 : b);
-            }
-        }
-        // Bucket::add_aabb per (node, bucket) group
-        const uint32_t gmask = __match_any_sync(FULL, active ? ((s0 << 3) | (uint32_t)b) : (0x100u | lane));
-        Key g[12];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            g[k] = group_min(gmask, f2key(mn[k]));
-            g[3 + k] = group_max(gmask, f2key(mx[k]));
-            const Key kc = f2key(c[k]);
-            g[6 + k] = group_min(gmask, kc);
-            g[9 + k] = group_max(gmask, kc);
-        }
-        // forward sweep: a[s] = T(n(L_s)) * SA(L_s);  backward sweep: r[s] = T(n(R_s)) * SA(R_s)   (bvh_node.rs:231-238)
-        T a[5], r[5];
-        {
-            Key L[6] = {KMIN, KMIN, KMIN, KMAX, KMAX, KMAX};
-            uint32_t nL = 0;
-#pragma unroll
-            for (int bb = 0; bb < 5; ++bb) {
-                const uint32_t mb = __ballot_sync(FULL, active && b == bb) & segmask;
-                const int src = mb ? (__ffs(mb) - 1) : (int)lane;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const Key v = shfl_key(g[k], src);
-                    if (mb) { if (k < 3) L[k] = v < L[k] ? v : L[k]; else L[k] = v > L[k] ? v : L[k]; }
-                }
-                nL += __popc(mb);
-                T lmn[3], lmx[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { lmn[k] = key2f(L[k]); lmx[k] = key2f(L[3 + k]); }
-                a[bb] = mul_rn((T)nL, surface_area(lmn, lmx));
-            }
-            Key R[6] = {KMIN, KMIN, KMIN, KMAX, KMAX, KMAX};
-            uint32_t nR = 0;
-#pragma unroll
-            for (int bb = 5; bb >= 1; --bb) {
-                const uint32_t mb = __ballot_sync(FULL, active && b == bb) & segmask;
-                const int src = mb ? (__ffs(mb) - 1) : (int)lane;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const Key v = shfl_key(g[k], src);
-                    if (mb) { if (k < 3) R[k] = v < R[k] ? v : R[k]; else R[k] = v > R[k] ? v : R[k]; }
-                }
-                nR += __popc(mb);
-                T rmn[3], rmx[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { rmn[k] = key2f(R[k]); rmx[k] = key2f(R[3 + k]); }
-                r[bb - 1] = mul_rn((T)nR, surface_area(rmn, rmx));
-            }
-        }
-        int best = 0;
-        bool found = degenerate;
-        if (!degenerate) {
-            const T sap = surface_area(ab, ab + 3);
-            T min_cost = Tr::inf();
-#pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const T cost = div_rn(add_rn(a[s], r[s]), sap);
-                if (cost < min_cost) { best = s; min_cost = cost; found = true; }
-            }
-        }
-        // bounds of the chosen children + the stable partition (bvh_node.rs:242-272)
-        Key LL[12], RR[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) { LL[k] = RR[k] = key_is_min<T>(k) ? KMIN : KMAX; }
-        uint32_t nl = 0, run = s0, dest = lane;
-#pragma unroll
-        for (int bb = 0; bb < 6; ++bb) {
-            const uint32_t mb = __ballot_sync(FULL, active && b == bb) & segmask;
-            const int src = mb ? (__ffs(mb) - 1) : (int)lane;
-            const bool toL = bb <= best;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) {
-                const Key v = shfl_key(g[k], src);
-                if (mb) {
-                    if (key_is_min<T>(k)) { if (toL) LL[k] = v < LL[k] ? v : LL[k]; else RR[k] = v < RR[k] ? v : RR[k]; }
-                    else                  { if (toL) LL[k] = v > LL[k] ? v : LL[k]; else RR[k] = v > RR[k] ? v : RR[k]; }
-                }
-            }
-            const uint32_t cbk = __popc(mb);
-            if (toL) nl += cbk;
-            if (active && !degenerate && b == bb) dest = run + __popc(mb & lt);
-            run += cbk;
-        }
-        if (!found) {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) { LL[k] = RR[k] = key_is_min<T>(k) ? KMIN : KMAX; }
-        }
-        const uint32_t cl = node + 1, cr = node + 2 * nl;
-        if (active && lane == s0) {                                  // the node itself (bvh_node.rs:138-151)
-            typename Tr::Node nd;
-            nd.parent = parent; nd.child_l = cl; nd.child_r = cr; nd.shape = cnt;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                nd.l_aabb.min[k] = key2f(LL[k]); nd.l_aabb.max[k] = key2f(LL[3 + k]);
-                nd.r_aabb.min[k] = key2f(RR[k]); nd.r_aabb.max[k] = key2f(RR[3 + k]);
-            }
-            store_struct_cg(P.nodes + node, nd);
-            P.node_start[node] = t.start + s0;
-        }
-        // move the shapes to their new positions
-        __syncwarp();
-        ws->pid[dest] = id;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { ws->pf[k][dest] = mn[k]; ws->pf[3 + k][dest] = mx[k]; ws->pf[6 + k][dest] = c[k]; }
-        __syncwarp();
-        id = ws->pid[lane];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { mn[k] = ws->pf[k][lane]; mx[k] = ws->pf[3 + k][lane]; c[k] = ws->pf[6 + k][lane]; }
-        // descend: my position now belongs to the left or the right child
-        bool leaf = false;
-        if (active) {
-            const bool left = (lane - s0) < nl;
-            parent = node;
-            if (left) { cnt = nl; node = cl; }
-            else      { s0 += nl; cnt -= nl; node = cr; }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { ab[k] = key2f(left ? LL[k] : RR[k]); cb[k] = key2f(left ? LL[6 + k] : RR[6 + k]); }
-            if (cnt == 1) {                                          // bvh_node.rs:95-104
-                write_leaf(P, node, parent, id, t.start + lane);
-                leaf = true;
-                active = false;
-            }
-        }
-        leaves += __popc(__ballot_sync(FULL, leaf));
-    }
-}
-
 // ---- SEG: one warp owns the whole range; depth-first continuation ------------------------------------
 template <class T>
 __device__ void process_seg(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T> t, uint32_t& leaves) {
     using Tr = Traits<T>;
     int sp = 0;
     for (;;) {
-        if (t.count <= 32) {                                 // small range: the whole subtree in registers
-            warp_subtree(P, ws, t, leaves);
-            if (sp == 0) return;
-            --sp;
-            t = ws->stack[sp];
-            __syncwarp();
-            continue;
-        }
         int axis; T ext, cbmin;
         split_axis(t, axis, ext, cbmin);
         const bool degenerate = ext < Tr::eps();            // bvh_node.rs:114
