@@ -176,10 +176,9 @@ def run_b200(args):
     ctx.set_option("profile", 1)
 
     def step():
-        total = bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap, want_total=(world > 1))
+        bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap)
         if world > 1:      # the path's one exchange step: all-gather of the hit lists (NCCL over NVLink)
-            allgather_csr(d_off.to(torch.int64), d_hits, total)
-        return total
+            allgather_csr(d_off, d_hits)
 
     def barrier():
         if world > 1:

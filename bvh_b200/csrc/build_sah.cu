@@ -651,6 +651,25 @@ template <class T> __global__ void finish_status_kernel(BuildCtl* ctl, BuildStat
     }
 }
 
+template <class T> __global__ void init_rootkeys_kernel(typename Traits<T>::Key* rootkeys) {
+    using Tr = Traits<T>;
+    if (threadIdx.x < 12) rootkeys[threadIdx.x] = key_is_min<T>(threadIdx.x) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+}
+
+// ABI -> device AABB layout + NaN check + scene bounds (AABB and centroid) as keys; shared with lbvh.cu.
+template <class T>
+int prep_only(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, typename Traits<T>::DAabb* out,
+              typename Traits<T>::Key* rootkeys, BuildStatus* status) {
+    init_rootkeys_kernel<T><<<1, 32, 0, ctx->stream>>>(rootkeys);
+    const int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    prep_kernel<T><<<blocks, 256, 0, ctx->stream>>>(in_aabbs, n, out, nullptr, rootkeys, &status->nan_found);
+    ctx->launches += 2;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+template int prep_only<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, DAabbF*, uint32_t*, BuildStatus*);
+template int prep_only<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, DAabbD*, unsigned long long*, BuildStatus*);
+
 static uint32_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t)p; }
 
 template <class T>

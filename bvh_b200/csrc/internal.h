@@ -97,6 +97,9 @@ template <class T> int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>
 template <class T> int convert_aabbs(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n,
                                      typename Traits<T>::DAabb* out, uint32_t* d_nan_flag);
 
+// ---- lbvh.cu ----
+template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree);
+
 // ---- flatten.cu ----
 template <class T> int build_traversal_records(Tree<T>* tree);   // d_tnodes
 template <class T> int build_flat(Tree<T>* tree);                // d_flat (reference FlatNode layout)

@@ -19,29 +19,47 @@ def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allgather_csr(offsets: torch.Tensor, hits: torch.Tensor, total: int, group=None):
-    """offsets: int64/int32 [n_local+1] local CSR offsets, hits: [>= total] local hit indices.
-    Returns (global_offsets int64 [n_global+1], global_hits [H_global]) in rank order == ray order."""
+def allgather_csr(offsets: torch.Tensor, hits: torch.Tensor, total: int | None = None, group=None):
+    """offsets: [n_local+1] local CSR offsets (offsets[-1] == number of local hits), hits: [>= n_hits] local hit
+    indices.  Returns (global_offsets int64 [n_global+1], global_hits [H_global]) in rank order == ray order.
+
+    One host synchronisation (the gathered totals size the hit all-gather); the local total is read from
+    offsets[-1] on the device, so the caller does not need it on the host."""
     world = dist.get_world_size(group)
     dev = offsets.device
     n_local = offsets.numel() - 1
-    meta = torch.tensor([n_local, int(total)], dtype=torch.int64, device=dev)
-    metas = [torch.empty_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    metas = torch.stack(metas).cpu()
-    n_each, h_each = metas[:, 0].tolist(), metas[:, 1].tolist()
+    meta = torch.empty(2, dtype=torch.int64, device=dev)
+    meta[0] = n_local
+    meta[1] = offsets[-1] if total is None else int(total)
+    all_meta = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_meta, meta, group=group)
+    all_meta = all_meta.view(world, 2)
+    host = all_meta.cpu()                                   # the one sync of the exchange step
+    n_each, h_each = host[:, 0].tolist(), host[:, 1].tolist()
     max_n, max_h = max(n_each), max(max(h_each), 1)
-    # padded all-gathers (one for the counts, one for the hit indices)
-    counts = torch.zeros(max_n, dtype=torch.int64, device=dev)
-    counts[:n_local] = (offsets[1:] - offsets[:-1]).to(torch.int64)
-    all_counts = torch.empty(world * max_n, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_counts, counts, group=group)
-    pad_hits = torch.zeros(max_h, dtype=hits.dtype, device=dev)
-    pad_hits[: int(total)] = hits[: int(total)]
+    # per-rank offsets (padded only if the shards are uneven)
+    if min(n_each) == max_n:
+        off_in = offsets
+    else:
+        off_in = torch.zeros(max_n + 1, dtype=offsets.dtype, device=dev)
+        off_in[: n_local + 1] = offsets
+    all_off = torch.empty(world * (max_n + 1), dtype=offsets.dtype, device=dev)
+    dist.all_gather_into_tensor(all_off, off_in, group=group)
+    # hit lists: every rank sends its first max_h entries (entries beyond its own total are ignored by the receiver)
+    if hits.numel() >= max_h:
+        hit_in = hits[:max_h]
+    else:
+        hit_in = torch.zeros(max_h, dtype=hits.dtype, device=dev)
+        hit_in[: hits.numel()] = hits
     all_hits = torch.empty(world * max_h, dtype=hits.dtype, device=dev)
-    dist.all_gather_into_tensor(all_hits, pad_hits, group=group)
-    g_counts = torch.cat([all_counts[r * max_n: r * max_n + n_each[r]] for r in range(world)])
+    dist.all_gather_into_tensor(all_hits, hit_in.contiguous(), group=group)
+    # assemble the global CSR: rebase each rank's offsets by the hits of the ranks before it
+    base = torch.cumsum(all_meta[:, 1], 0) - all_meta[:, 1]
+    g_off = all_off.view(world, max_n + 1)[:, :max_n].to(torch.int64) + base[:, None]
+    if min(n_each) == max_n:
+        g_off = g_off.reshape(-1)
+    else:
+        g_off = torch.cat([g_off[r, : n_each[r]] for r in range(world)])
+    g_off = torch.cat([g_off, all_meta[:, 1].sum().reshape(1)])
     g_hits = torch.cat([all_hits[r * max_h: r * max_h + h_each[r]] for r in range(world)])
-    g_off = torch.zeros(g_counts.numel() + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(g_counts, 0, out=g_off[1:])
     return g_off, g_hits

@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
         local = O.traverse(res.nodes, shapes, rays[lo:hi], O.MODE_RECURSIVE)
         off = torch.from_numpy(local.offsets.astype(np.int64))
         hits = torch.from_numpy(np.concatenate([local.hits, np.zeros(7, np.uint32)]).astype(np.int64))   # over-allocated buffer
-        g_off, g_hits = allgather_csr(off, hits, len(local.hits))
+        g_off, g_hits = allgather_csr(off, hits, len(local.hits) if rank == 0 else None)   # rank 1 lets it read offsets[-1]
         full = O.traverse(res.nodes, shapes, rays, O.MODE_RECURSIVE)
         ok = np.array_equal(g_off.numpy().astype(np.uint64), full.offsets) and np.array_equal(g_hits.numpy().astype(np.uint32), full.hits)
         q.put((rank, bool(ok), lo, hi))

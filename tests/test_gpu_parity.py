@@ -362,3 +362,52 @@ def test_config5_ten_million_f64(api):
     rebuilt = O.build(shapes, "f64", threads=O.hardware_threads())
     c_refit, c_rebuild = bvh.sah_cost()[0], O.sah_cost(rebuilt.nodes, "f64")[0]
     assert c_refit <= 1.10 * c_rebuild, (c_refit, c_rebuild)
+
+
+# ---- BVHGPU_BUILD_LBVH: different topology, same layout rule, same hit sets ------------------------------------------
+@pytest.mark.parametrize("name", ["cubes1", "random2", "random3", "random33", "random1000", "cubes1000", "points3000", "line700", "skew3000", "huge300"])
+def test_lbvh_mode_is_a_valid_reference_layout_bvh(api, name):
+    from bvh_b200 import capi
+
+    shapes = scene(name)
+    bvh = api.Bvh.build(shapes, mode=capi.BUILD_LBVH)
+    nodes, idx = bvh.nodes, bvh.node_index
+    n = len(shapes)
+    assert len(nodes) == 2 * n - 1
+    leaves = nodes["child_l"] == O.U32_MAX
+    assert leaves.sum() == n and np.array_equal(np.sort(nodes["shape"][leaves]), np.arange(n))
+    assert np.array_equal(nodes["shape"][idx], np.arange(n))
+    assert O.is_consistent(nodes, shapes) and O.is_tight(nodes)          # the reference's own acceptance checks
+    # preorder rule child_l = i+1, child_r = i + 2*n_l: the host-side validator of tree_from_nodes accepts it
+    again = api.Bvh.from_nodes(nodes, shapes)
+    assert np.array_equal(again.node_index, idx)
+    # flatten() of that tree == the literal reference recursion applied to the same node array
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(nodes))
+    # traversal of the LBVH tree == oracle traversal of the same node array (sequences), and == the exact-SAH tree (sets)
+    rays = rays_for(shapes, 2000, seed=8)
+    r = O.traverse(nodes, shapes, rays, O.MODE_RECURSIVE)
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    if not name.startswith("huge"):
+        ref = O.build(shapes)
+        rr = O.traverse(ref.nodes, shapes, rays, O.MODE_RECURSIVE)
+        for a, b in zip(O.per_ray_lists(r.offsets, r.hits), O.per_ray_lists(rr.offsets, rr.hits)):
+            assert sorted(a.tolist()) == sorted(b.tolist())
+
+
+def test_lbvh_sah_cost_ratio_config2(api):
+    """every lbvh result reports C_gpu / C_oracle (stated tolerance: informational in round 1)."""
+    from bvh_b200 import capi
+
+    shapes = O.create_n_cubes(10_000)
+    exact = api.Bvh.build(shapes)
+    lbvh = api.Bvh.build(shapes, mode=capi.BUILD_LBVH)
+    ce, cl = exact.sah_cost(), lbvh.sah_cost()
+    print(f"SAH cost (pseudo-area) exact {ce[0]:.4f} lbvh {cl[0]:.4f} ratio {cl[0] / ce[0]:.3f}; geometric ratio {cl[1] / ce[1]:.3f}")
+    assert cl[0] / ce[0] < 3.0
+    rays, _ = O.create_rays(200_000)
+    a = exact.traverse_batch(rays)
+    b = lbvh.traverse_batch(rays)
+    assert np.array_equal(a[0], b[0])                    # same hit counts per ray
+    for x, y in zip(O.per_ray_lists(a[0], a[1])[:5000], O.per_ray_lists(b[0], b[1])[:5000]):
+        assert sorted(x.tolist()) == sorted(y.tolist())
