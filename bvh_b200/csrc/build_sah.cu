@@ -127,37 +127,51 @@ __device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T
                                           bool degenerate, uint32_t half, bool store_bkt, uint32_t& last_id, int& last_b) {
     const uint32_t lane = lane_id();
     const T K = sub_rn(T(6), T(0.01));                 // T::from(NUM_BUCKETS) - T::from(0.01), bvh_node.rs:214-215
-    for (uint32_t base = p0; base < p1; base += 32) {
-        const uint32_t pos = base + lane;
-        uint32_t id = 0;
-        int b = 0;
-        if (pos < p1) {
-            id = __ldcg(src + pos);
-            T mn[3], mx[3], c[3];
-            load_aabb(P.aabb + id, mn, mx);
+    constexpr int U = 4;                               // chunks in flight: index loads, then AABB gathers, then the math
+    for (uint32_t base = p0; base < p1; base += 32 * U) {
+        uint32_t id[U];
+        T mn[U][3], mx[U][3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) c[k] = center1(mn[k], mx[k]);
-            if (degenerate) {
-                b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
-            } else {
-                const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
-                const T rel = div_rn(sub_rn(ca, cbmin), ext);
-                b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
-                b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
-            }
-            if (store_bkt) P.bkt[pos] = (uint8_t)b;
-            typename Traits<T>::Key* kb = ws->keys + b * 12;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                atomicMin(kb + k, f2key(mn[k]));
-                atomicMax(kb + 3 + k, f2key(mx[k]));
-                atomicMin(kb + 6 + k, f2key(c[k]));
-                atomicMax(kb + 9 + k, f2key(c[k]));
-            }
-            atomicAdd(&ws->cnt[b], 1u);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            id[u] = pos < p1 ? __ldcg(src + pos) : 0u;
         }
-        last_id = id;
-        last_b = b;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            if (pos < p1) load_aabb(P.aabb + id[u], mn[u], mx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            if (base + 32 * u >= p1) break;            // warp-uniform
+            int b = 0;
+            if (pos < p1) {
+                T c[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[k] = center1(mn[u][k], mx[u][k]);
+                if (degenerate) {
+                    b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
+                } else {
+                    const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
+                    const T rel = div_rn(sub_rn(ca, cbmin), ext);
+                    b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
+                    b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
+                }
+                if (store_bkt) P.bkt[pos] = (uint8_t)b;
+                typename Traits<T>::Key* kb = ws->keys + b * 12;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    atomicMin(kb + k, f2key(mn[u][k]));
+                    atomicMax(kb + 3 + k, f2key(mx[u][k]));
+                    atomicMin(kb + 6 + k, f2key(c[k]));
+                    atomicMax(kb + 9 + k, f2key(c[k]));
+                }
+                atomicAdd(&ws->cnt[b], 1u);
+            }
+            last_id = id[u];
+            last_b = b;
+        }
     }
     __syncwarp();
 }
@@ -226,20 +240,30 @@ __device__ __forceinline__ void scatter_range(const BuildParams<T>& P, const uin
                                               uint32_t cached_id, int cached_b) {
     const uint32_t lane = lane_id();
     const uint32_t lt = lanemask_lt();
-    for (uint32_t bpos = p0; bpos < p1; bpos += 32) {
-        const uint32_t pos = bpos + lane;
-        const bool valid = pos < p1;
-        uint32_t id = cached_id;
-        int b = cached_b;
-        if (!use_cached && valid) { id = __ldcg(src + pos); b = (int)__ldcg(P.bkt + pos); }
-        uint32_t dest = 0;
+    constexpr int U = 4;
+    for (uint32_t bpos = p0; bpos < p1; bpos += 32 * U) {
+        uint32_t id[U];
+        int bk[U];
 #pragma unroll
-        for (int bb = 0; bb < 6; ++bb) {
-            const uint32_t m = __ballot_sync(0xffffffffu, valid && b == bb);
-            if (b == bb) dest = base[bb] + __popc(m & lt);
-            base[bb] += __popc(m);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = bpos + 32 * u + lane;
+            id[u] = cached_id; bk[u] = cached_b;
+            if (!use_cached && pos < p1) { id[u] = __ldcg(src + pos); bk[u] = (int)__ldcg(P.bkt + pos); }
         }
-        if (valid) __stcg(dst + dest, id);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (bpos + 32 * u >= p1) break;            // warp-uniform
+            const uint32_t pos = bpos + 32 * u + lane;
+            const bool valid = pos < p1;
+            uint32_t dest = 0;
+#pragma unroll
+            for (int bb = 0; bb < 6; ++bb) {
+                const uint32_t m = __ballot_sync(0xffffffffu, valid && bk[u] == bb);
+                if (bk[u] == bb) dest = base[bb] + __popc(m & lt);
+                base[bb] += __popc(m);
+            }
+            if (valid) __stcg(dst + dest, id[u]);
+        }
     }
     __syncwarp();
 }
@@ -306,13 +330,14 @@ template <class T> __device__ __forceinline__ void push_seg(const BuildParams<T>
     }
     __syncwarp();
 }
-template <class T> __device__ __forceinline__ void push_tiles(const BuildParams<T>& P, uint32_t kind, uint32_t sid, uint32_t tiles) {
+template <class T> __device__ __forceinline__ void push_tiles(const BuildParams<T>& P, uint32_t kind, uint32_t sid, uint32_t tiles, const BTask<T>& t) {
     uint32_t base = 0;
     if (lane_id() == 0) base = atomicAdd(&P.ctl->tail, tiles);
     base = __shfl_sync(0xffffffffu, base, 0);
     // payloads first, ONE fence, then the sequence words: a fence per slot would serialise the publication
     for (uint32_t j = lane_id(); j < tiles; j += 32) {
         const uint32_t slot = (base + j) & P.qmask;
+        store_struct_cg(&P.q[slot].t, t);              // the task travels in the slot: no dependent load of the segment state
         __stcg(reinterpret_cast<uint4*>(&P.q[slot].kind), make_uint4(kind, sid, j, 0u));
     }
     __threadfence();
@@ -330,7 +355,6 @@ template <class T> __device__ __forceinline__ void create_big(const BuildParams<
     BigSeg<T>* B = P.big + t.start / TILE;
     const uint32_t tiles = (t.count + TILE - 1) / TILE;
     const uint32_t lane = lane_id();
-    if (lane == 0) store_struct_cg(&B->t, t);
     for (int e = lane; e < 72; e += 32) __stcg(&B->keys[e], key_is_min<T>(e) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF);
     if (lane < 6) __stcg(&B->cnt[lane], 0u);
     if (lane == 6) __stcg(&B->tiles, tiles);
@@ -339,7 +363,7 @@ template <class T> __device__ __forceinline__ void create_big(const BuildParams<
     __threadfence();
     __syncwarp();
     __threadfence();
-    push_tiles(P, KIND_BIN, t.start / TILE, tiles);
+    push_tiles(P, KIND_BIN, t.start / TILE, tiles, t);
 }
 
 template <class T>
@@ -404,13 +428,11 @@ __device__ void finish_big(const BuildParams<T>& P, WarpScratch<T>* ws, const BT
 }
 
 template <class T>
-__device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, uint32_t sid, uint32_t k, uint32_t& leaves) {
+__device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t sid, uint32_t k, uint32_t& leaves) {
     using Tr = Traits<T>;
     BigSeg<T>* B = P.big + sid;
     const uint32_t lane = lane_id();
-    BTask<T> t;
-    load_struct_cg(t, &B->t);
-    const uint32_t tiles = __ldcg(&B->tiles);
+    const uint32_t tiles = (t.count + TILE - 1) / TILE;
     int axis; T ext, cbmin;
     split_axis(t, axis, ext, cbmin);
     const bool degenerate = ext < Tr::eps();
@@ -430,7 +452,7 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, ui
     const uint32_t slot = tile_slot(p0, k == 0);
     if (lane < 6) {
         const uint32_t c = ws->cnt[lane];
-        __stcg(&P.tilecnt[slot * 6 + lane], c);
+        __stcg(&P.tilecnt[slot * 8 + lane], c);
         if (c) atomicAdd(&B->cnt[lane], c);
     }
     __threadfence();
@@ -456,35 +478,51 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, ui
     if (lane < 6) __stcg(&B->base[lane], basev);
     if (lane == 6) __stcg(&B->nl, nl);
     if (lane < 24) __stcg(&B->child[lane], ws->child[lane]);
-    // exclusive prefix of the per-tile bucket counts (keeps the multi-warp partition stable)
-    uint32_t running[6] = {0, 0, 0, 0, 0, 0};
-    for (uint32_t j0 = 0; j0 < tiles; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        const bool valid = j < tiles;
-        const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+    // exclusive prefix of the per-tile bucket counts (keeps the multi-warp partition stable).  Blocked: lane L owns
+    // tiles [L*m, (L+1)*m); all loads of a pass are independent, so they pipeline instead of forming a latency chain.
+    {
+        const uint32_t m = (tiles + 31) / 32;
+        uint32_t sum[6] = {0, 0, 0, 0, 0, 0};
+        for (uint32_t q = 0; q < m; ++q) {
+            const uint32_t j = lane * m + q;
+            if (j < tiles) {
+                const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
+                const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
+                sum[0] += a.x; sum[1] += a.y; sum[2] += a.z; sum[3] += a.w; sum[4] += c.x; sum[5] += c.y;
+            }
+        }
+        uint32_t run[6];
 #pragma unroll
         for (int b = 0; b < 6; ++b) {
-            const uint32_t c = valid ? __ldcg(&P.tilecnt[sj * 6 + b]) : 0u;
-            uint32_t incl = c;
+            uint32_t incl = sum[b];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
-            if (valid) __stcg(&P.tilecnt[sj * 6 + b], running[b] + incl - c);
-            running[b] += __shfl_sync(0xffffffffu, incl, 31);
+            run[b] = incl - sum[b];
+        }
+        for (uint32_t q = 0; q < m; ++q) {
+            const uint32_t j = lane * m + q;
+            if (j < tiles) {
+                const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
+                const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
+                __stcg(reinterpret_cast<uint4*>(P.tilecnt + sj * 8), make_uint4(run[0], run[1], run[2], run[3]));
+                __stcg(reinterpret_cast<uint2*>(P.tilecnt + sj * 8 + 4), make_uint2(run[4], run[5]));
+                run[0] += a.x; run[1] += a.y; run[2] += a.z; run[3] += a.w; run[4] += c.x; run[5] += c.y;
+            }
         }
     }
     __threadfence();
     __syncwarp();
     __threadfence();
-    push_tiles(P, KIND_SCATTER, sid, tiles);
+    push_tiles(P, KIND_SCATTER, sid, tiles, t);
 }
 
 template <class T>
-__device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws, uint32_t sid, uint32_t k, uint32_t& leaves) {
+__device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t sid, uint32_t k, uint32_t& leaves) {
     BigSeg<T>* B = P.big + sid;
     const uint32_t lane = lane_id();
-    BTask<T> t;
-    load_struct_cg(t, &B->t);
-    const uint32_t tiles = __ldcg(&B->tiles);
+    const uint32_t tiles = (t.count + TILE - 1) / TILE;
     const uint32_t buf = t.parent_buf >> 31;
     const uint32_t p0 = t.start + k * TILE;
     const uint32_t pend = t.start + t.count;
@@ -492,7 +530,7 @@ __device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws
     const uint32_t slot = tile_slot(p0, k == 0);
     uint32_t base[6];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) base[b] = __ldcg(&B->base[b]) + __ldcg(&P.tilecnt[slot * 6 + b]);
+    for (int b = 0; b < 6; ++b) base[b] = __ldcg(&B->base[b]) + __ldcg(&P.tilecnt[slot * 8 + b]);
     scatter_range(P, P.idx[buf], P.idx[buf ^ 1u], p0, p1, base, false, 0u, 0);
     __threadfence();
     __syncwarp();
@@ -534,7 +572,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T
                     }
                 }
                 __nanosleep(ns);
-                if (ns < 1024) ns <<= 1;
+                if (ns < 256) ns <<= 1;
             }
         }
         stop = __shfl_sync(0xffffffffu, stop, 0);
@@ -546,8 +584,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T
         unsigned long long tr0 = 0;
         if (P.trace) tr0 = global_timer_ns();
         if (s.kind == KIND_SEG) process_seg(P, ws, s.t, leaves);
-        else if (s.kind == KIND_BIN) process_bin_tile(P, ws, s.a, s.b, leaves);
-        else process_scatter_tile(P, ws, s.a, s.b, leaves);
+        else if (s.kind == KIND_BIN) process_bin_tile(P, ws, s.t, s.a, s.b, leaves);
+        else process_scatter_tile(P, ws, s.t, s.a, s.b, leaves);
         if (P.trace && lane == 0 && ticket < P.trace_cap) {
             const unsigned long long base = *(volatile unsigned long long*)&P.ctl->t_start;
             P.trace[ticket] = make_uint4((s.kind << 28) | (s.kind == KIND_SEG ? s.t.count : s.b), s.kind == KIND_SEG ? s.t.node : s.a,
@@ -716,7 +754,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     BVH_TRY(dalloc_t(ctx, &P.q, qcap));
     BVH_TRY(dalloc_t(ctx, &P.qseq, qcap));
     BVH_TRY(dalloc_t(ctx, &P.big, nbig));
-    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 6));
+    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 8));
     BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
     BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
     P.idx[0] = idx0;
