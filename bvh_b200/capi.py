@@ -15,6 +15,16 @@ BUILD_EXACT_SAH, BUILD_LBVH = 0, 1
 TRAVERSE_BVH, TRAVERSE_FLAT = 0, 1
 
 
+MAX_PEERS, MAILBOX_BYTES, IPC_HANDLE_BYTES = 8, 1024, 64
+
+
+class Shard(C.Structure):
+    """bvhgpu_shard (include/bvh_b200.h)."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int),
+                ("peer_offsets", C.c_void_p * MAX_PEERS), ("peer_hits", C.c_void_p * MAX_PEERS), ("peer_mailbox", C.c_void_p * MAX_PEERS),
+                ("seq", C.c_uint64), ("rays_before", C.c_size_t), ("nrays_global", C.c_size_t), ("cap", C.c_size_t)]
+
+
 class BvhGpuError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"bvhgpu status {status}: {message}")
@@ -55,6 +65,11 @@ def lib() -> C.CDLL:
     L.bvhgpu_launch_count.restype = C.c_uint64
     L.bvhgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.bvhgpu_get_metric.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.bvhgpu_peer_alloc.argtypes = [vp, sz, C.POINTER(vp), vp]
+    L.bvhgpu_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.bvhgpu_peer_close.argtypes = [vp, vp]
+    L.bvhgpu_peer_free.argtypes = [vp, vp]
+    L.bvhgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
     for s in ("f32x3", "f64x3"):
         getattr(L, f"bvhgpu_build_{s}").argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
         getattr(L, f"bvhgpu_build_dev_{s}").argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
@@ -70,6 +85,7 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_traverse_fetch_{s}").argtypes = [vp, vp, sz]
         getattr(L, f"bvhgpu_traverse_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_stats_{s}").argtypes = [vp, u64p]
+        getattr(L, f"bvhgpu_traverse_sharded_dev_{s}").argtypes = [vp, i32, vp, sz, C.POINTER(Shard)]
         getattr(L, f"bvhgpu_rays_new_dev_{s}").argtypes = [vp, vp, vp, sz, vp]
         getattr(L, f"bvhgpu_sah_cost_{s}").argtypes = [vp, C.POINTER(C.c_double)]
         getattr(L, f"bvhgpu_refit_{s}").argtypes = [vp, vp, sz]

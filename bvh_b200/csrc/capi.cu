@@ -356,6 +356,44 @@ BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out)
     return BVHGPU_OK;
 }
 
+BVH_EXPORT int bvhgpu_peer_alloc(bvhgpu_ctx* ctx, size_t bytes, void** dev_ptr, void* handle64) {
+    if (!ctx || !dev_ptr || !handle64) { set_error("peer_alloc: null argument"); return BVHGPU_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == BVHGPU_IPC_HANDLE_BYTES, "ipc handle size");
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_CUDA_TRY(cudaMalloc(dev_ptr, bytes ? bytes : 16));
+    BVH_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes ? bytes : 16));
+    BVH_CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, *dev_ptr));
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_peer_open(bvhgpu_ctx* ctx, const void* handle64, void** dev_ptr) {
+    if (!ctx || !dev_ptr || !handle64) { set_error("peer_open: null argument"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    BVH_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_peer_close(bvhgpu_ctx* ctx, void* dev_ptr) {
+    if (!ctx) { set_error("peer_close: null ctx"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (dev_ptr) BVH_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_peer_free(bvhgpu_ctx* ctx, void* dev_ptr) {
+    if (!ctx) { set_error("peer_free: null ctx"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (dev_ptr) BVH_CUDA_TRY(cudaFree(dev_ptr));
+    return BVHGPU_OK;
+}
+
+BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (!ctx || (bytes && (!host_dst || !dev_src))) { set_error("memcpy_d2h: null argument"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (bytes) BVH_CUDA_TRY(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
+}
+
 #define DEFINE_API(T, SUF, TREE, AABB, RAY, NODE, FLAT)                                                                   \
     BVH_EXPORT int bvhgpu_build_##SUF(bvhgpu_ctx* ctx, const AABB* aabbs, size_t n, int mode, TREE** out) {              \
         return build_impl<T, TREE>(ctx, aabbs, n, mode, true, out);                                                       \
@@ -391,6 +429,14 @@ BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out)
         if (!tree || !dev_offsets || (nrays && !dev_rays)) { set_error("traverse_dev: null argument"); return BVHGPU_ERR_INVALID; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
         return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_sharded_dev_##SUF(TREE* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard) { \
+        if (!tree || !shard || (nrays && !dev_rays)) { set_error("traverse_sharded: null argument"); return BVHGPU_ERR_INVALID; } \
+        if (shard->world < 1 || shard->world > BVHGPU_MAX_PEERS || shard->rank < 0 || shard->rank >= shard->world) {       \
+            set_error("traverse_sharded: bad rank/world %d/%d", shard->rank, shard->world); return BVHGPU_ERR_INVALID; }     \
+        if (nrays == 0 || tree->n == 0) { set_error("traverse_sharded: every rank needs a non-empty shard and tree"); return BVHGPU_ERR_UNSUPPORTED; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, nullptr, nullptr, shard->cap, nullptr, shard); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
         if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \

@@ -108,8 +108,10 @@ template <class T> int refit(Tree<T>* tree);                     // recompute ch
 
 // ---- traverse.cu ----
 // d_rays: rays on the device, or nullptr with h_rays = rays in host memory (chunked, overlapped H2D).
+// shard != nullptr: multi-GPU step, results go to every rank's peer-mapped global CSR (d_offsets / d_hits unused).
 template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays,
-                                       size_t nrays, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
+                                       size_t nrays, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total,
+                                       const bvhgpu_shard* shard = nullptr);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
                                        typename Traits<T>::Ray* d_rays);
 

@@ -169,6 +169,76 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
     if (threadIdx.x == 0) *total = carry_s;
 }
 
+// Destinations of the emit pass.  Single GPU: one destination (the caller's buffers), bases 0.  Sharded: every
+// rank's peer-mapped global CSR; this rank's rays start at ray_base, its hits at *hit_base (known after the
+// totals exchange).
+struct EmitDst {
+    int world;
+    uint32_t* offsets[BVHGPU_MAX_PEERS];
+    uint32_t* hits[BVHGPU_MAX_PEERS];
+    unsigned long long ray_base;
+    const unsigned long long* hit_base;      // nullptr = 0
+    const unsigned long long* grand_total;   // nullptr = local total
+    unsigned long long nrays_global;
+    int self;                                // destination that receives the grand total (local copy)
+};
+
+// Totals exchange over peer memory: mailbox layout (u64 words): tot[parity][src][2] = {seq, total}, done[parity][src].
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+struct PeerBoxes { int rank, world; unsigned long long* box[BVHGPU_MAX_PEERS]; unsigned long long seq; };
+
+__global__ void xchg_totals_kernel(PeerBoxes pb, const unsigned long long* __restrict__ local_total,
+                                   unsigned long long* __restrict__ xinfo /* {hit_base, grand_total} */, uint32_t* err, unsigned long long timeout_ns) {
+    const int lane = threadIdx.x;
+    const unsigned long long par = pb.seq & 1ull;
+    const unsigned long long mine = *local_total;
+    if (lane < pb.world) {                                   // publish {total, seq} into peer `lane`'s mailbox, slot [par][rank]
+        unsigned long long* slot = pb.box[lane] + (par * BVHGPU_MAX_PEERS + pb.rank) * 2;
+        slot[1] = mine;
+        __threadfence_system();
+        st_release_sys(slot, pb.seq);
+    }
+    unsigned long long tot = 0;
+    if (lane < pb.world) {                                   // wait for peer `lane`'s total in my own mailbox
+        const unsigned long long* slot = pb.box[pb.rank] + (par * BVHGPU_MAX_PEERS + lane) * 2;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(slot) != pb.seq) {
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+            __nanosleep(200);
+        }
+        tot = slot[1];
+    }
+    unsigned long long base = 0, grand = 0;
+    for (int r = 0; r < pb.world; ++r) {
+        const unsigned long long v = __shfl_sync(0xffffffffu, tot, r);
+        if (r < pb.rank) base += v;
+        grand += v;
+    }
+    if (lane == 0) { xinfo[0] = base; xinfo[1] = grand; }
+}
+
+__global__ void xchg_done_kernel(PeerBoxes pb, uint32_t* err, unsigned long long timeout_ns) {
+    const int lane = threadIdx.x;
+    const unsigned long long par = pb.seq & 1ull;
+    __threadfence_system();                                   // my emit stores (previous kernel) are ordered before the flag
+    if (lane < pb.world) st_release_sys(pb.box[lane] + 4 * BVHGPU_MAX_PEERS + par * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
+    if (lane < pb.world) {
+        const unsigned long long* slot = pb.box[pb.rank] + 4 * BVHGPU_MAX_PEERS + par * BVHGPU_MAX_PEERS + lane;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(slot) != pb.seq) {
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+            __nanosleep(200);
+        }
+    }
+}
+
 // Pass 2: final offsets + hit lists.  Rays with <= K hits copy their slots, the rest walk again.
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
@@ -177,27 +247,40 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
                                                    const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
                                                    const unsigned long long* __restrict__ total,
-                                                   uint32_t* __restrict__ offsets, uint32_t* __restrict__ hits, unsigned long long cap) {
+                                                   EmitDst dst, unsigned long long cap) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) { const unsigned long long t = *total; offsets[nrays] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t; }
+    const unsigned long long hbase = dst.hit_base ? *dst.hit_base : 0ull;
+    if (r == 0) {
+        const unsigned long long t = dst.grand_total ? *dst.grand_total : *total;
+        dst.offsets[dst.self][dst.nrays_global] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
+    }
     if (r >= nrays) return;
-    const unsigned long long off = blocksum[r / SCAN_TILE] + local[r];
-    offsets[r] = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
+    const unsigned long long off = hbase + blocksum[r / SCAN_TILE] + local[r];
+    const uint32_t off32 = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
+    for (int d = 0; d < dst.world; ++d) dst.offsets[d][dst.ray_base + r] = off32;
     const uint32_t c = counts[r];
-    if (c == 0 || hits == nullptr) return;
+    if (c == 0 || dst.hits[0] == nullptr) return;
     if (c <= K) {
-        for (uint32_t k = 0; k < c; ++k) if (off + k < cap) hits[off + k] = slots[(size_t)k * nrays + r];
+        for (uint32_t k = 0; k < c; ++k) {
+            if (off + k < cap) {
+                const uint32_t h = slots[(size_t)k * nrays + r];
+                for (int d = 0; d < dst.world; ++d) dst.hits[d][off + k] = h;
+            }
+        }
     } else {
         T o[3], inv[3];
         load_ray<T>(rays, r, o, inv);
         unsigned long long w = off;
-        walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) { if (w < cap) hits[w] = shape; ++w; });
+        walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
+            if (w < cap) for (int d = 0; d < dst.world; ++d) dst.hits[d][w] = shape;
+            ++w;
+        });
     }
 }
 
 template <class T>
 int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays, size_t nrays,
-                    uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total) {
+                    uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total, const bvhgpu_shard* shard) {
     using Ray = typename Traits<T>::Ray;
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
@@ -227,8 +310,8 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     BVH_TRY(dalloc_t(ctx, &counts, R));
     BVH_TRY(dalloc_t(ctx, &local, R));
     if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
-    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 6));      // [nblk] total, [nblk+1] visits, [nblk+2..3] {hit_base, grand_total}, [nblk+4] error word
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 6 * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     auto launch_walk = [&](const Ray* rays, uint32_t first, uint32_t count) {
         const int grid = (count + 255) / 256;
@@ -263,8 +346,26 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    EmitDst dst{};
+    PeerBoxes pb{};
+    const unsigned long long xchg_timeout = 10ull * 1000ull * 1000ull * 1000ull;
+    if (shard) {
+        dst.world = shard->world; dst.self = shard->rank; dst.ray_base = shard->rays_before; dst.nrays_global = shard->nrays_global;
+        dst.hit_base = sums + nblk + 2; dst.grand_total = sums + nblk + 3;
+        pb.rank = shard->rank; pb.world = shard->world; pb.seq = shard->seq;
+        for (int d = 0; d < shard->world; ++d) {
+            dst.offsets[d] = (uint32_t*)shard->peer_offsets[d]; dst.hits[d] = (uint32_t*)shard->peer_hits[d];
+            pb.box[d] = (unsigned long long*)shard->peer_mailbox[d];
+        }
+        cap = shard->cap;
+        xchg_totals_kernel<<<1, 32, 0, st>>>(pb, sums + nblk, sums + nblk + 2, (uint32_t*)(sums + nblk + 4), xchg_timeout);
+        ctx->launches++;
+    } else {
+        dst.world = 1; dst.self = 0; dst.offsets[0] = d_offsets; dst.hits[0] = d_hits; dst.ray_base = 0; dst.nrays_global = R;
+    }
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap);
+    if (shard) { xchg_done_kernel<<<1, 32, 0, st>>>(pb, (uint32_t*)(sums + nblk + 4), xchg_timeout); ctx->launches++; }
     ctx->launches += 3;
     BVH_CUDA_TRY(cudaGetLastError());
     int rc = BVHGPU_OK;
@@ -308,8 +409,8 @@ int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t
     return BVHGPU_OK;
 }
 
-template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
-template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
+template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
 template int rays_new_device<float>(bvhgpu_ctx*, const float*, const float*, size_t, bvh_ray3f*);
 template int rays_new_device<double>(bvhgpu_ctx*, const double*, const double*, size_t, bvh_ray3d*);
 

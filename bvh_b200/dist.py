@@ -63,3 +63,83 @@ def allgather_csr(offsets: torch.Tensor, hits: torch.Tensor, total: int | None =
     g_off = torch.cat([g_off, all_meta[:, 1].sum().reshape(1)])
     g_hits = torch.cat([all_hits[r * max_h: r * max_h + h_each[r]] for r in range(world)])
     return g_off, g_hits
+
+
+class ShardedTraversal:
+    """The multi-GPU step with the exchange fused into the traversal (bvhgpu_traverse_sharded_dev_*): every rank
+    holds a peer-mapped copy of the global CSR; after its walk a rank publishes its hit total into all peers'
+    mailboxes over NVLink and its emit kernel stores its rebased offsets / hit lists straight into every rank's
+    buffers (P2P stores).  No NCCL call and no host synchronisation on the data path; torch.distributed is used
+    once, at construction, to swap the CUDA IPC handles."""
+
+    def __init__(self, bvh, nrays_local: int, cap: int, group=None):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import capi
+
+        self.bvh, self.capi, self.C, self.np = bvh, capi, C, np
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > capi.MAX_PEERS:
+            raise ValueError(f"at most {capi.MAX_PEERS} ranks")
+        sizes = [None] * self.world
+        dist.all_gather_object(sizes, int(nrays_local), group=group)
+        self.n_each = sizes
+        self.nrays_global = sum(sizes)
+        self.rays_before = sum(sizes[: self.rank])
+        self.cap = int(cap)
+        L, ctx = capi.lib(), bvh.ctx._h
+        self._own, handles = [], []
+        for nbytes in (4 * (self.nrays_global + 1), 4 * self.cap, capi.MAILBOX_BYTES):
+            ptr, h = C.c_void_p(), (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
+            capi.check(L.bvhgpu_peer_alloc(ctx, nbytes, C.byref(ptr), h))
+            self._own.append(ptr)
+            handles.append(bytes(h))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self._opened = []
+        self.shard = capi.Shard()
+        self.shard.rank, self.shard.world = self.rank, self.world
+        self.shard.rays_before, self.shard.nrays_global, self.shard.cap, self.shard.seq = self.rays_before, self.nrays_global, self.cap, 0
+        for r in range(self.world):
+            ptrs = []
+            for k in range(3):
+                if r == self.rank:
+                    ptrs.append(self._own[k].value)
+                else:
+                    p = C.c_void_p()
+                    hb = (C.c_ubyte * capi.IPC_HANDLE_BYTES).from_buffer_copy(everyone[r][k])
+                    capi.check(L.bvhgpu_peer_open(ctx, hb, C.byref(p)))
+                    self._opened.append(p)
+                    ptrs.append(p.value)
+            self.shard.peer_offsets[r], self.shard.peer_hits[r], self.shard.peer_mailbox[r] = ptrs
+        dist.barrier(group=group)
+        self._fn = getattr(L, f"bvhgpu_traverse_sharded_dev_{bvh._d['suffix']}")
+
+    def step(self, rays_ptr: int, nrays: int, mode: int = 0):
+        """Enqueue one sharded traversal (asynchronous); when the stream reaches the end of it this rank's copy of
+        the global CSR is complete (all peers have signalled that their stores landed)."""
+        self.shard.seq += 1
+        self.capi.check(self._fn(self.bvh._h, mode, self.C.c_void_p(rays_ptr), nrays, self.C.byref(self.shard)))
+
+    def fetch(self):
+        """Global CSR as numpy arrays (offsets u32[n_global+1], hits u32[total]); synchronises."""
+        np, C, L = self.np, self.C, self.capi.lib()
+        off = np.empty(self.nrays_global + 1, dtype=np.uint32)
+        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, off.ctypes.data_as(C.c_void_p), self._own[0], off.nbytes))
+        total = int(off[-1])
+        hits = np.empty(min(total, self.cap), dtype=np.uint32)
+        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, hits.ctypes.data_as(C.c_void_p), self._own[1], hits.nbytes))
+        return off, hits
+
+    def close(self):
+        L, ctx = self.capi.lib(), self.bvh.ctx._h
+        self.bvh.ctx.synchronize()
+        dist.barrier()
+        for p in self._opened:
+            L.bvhgpu_peer_close(ctx, p)
+        dist.barrier()
+        for p in self._own:
+            L.bvhgpu_peer_free(ctx, p)
+        self._opened, self._own = [], []

@@ -157,6 +157,36 @@ int bvhgpu_traverse_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_ray
                               void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
 int bvhgpu_traverse_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_rays, size_t nrays,
                               void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+/* ---- multi-GPU ray sharding with the exchange fused into the traversal (no NCCL on the data path) -------------
+ * Every rank owns a contiguous shard of the ray batch and a replica of the tree.  The global CSR lives in
+ * peer-mapped buffers (one copy per rank, allocated with bvhgpu_peer_alloc and opened on the other ranks through
+ * CUDA IPC): after its local walk a rank publishes its hit total to all peers' mailboxes over NVLink, waits for
+ * theirs, and its emit kernel then stores its rebased offsets and hit lists DIRECTLY into every rank's global
+ * buffers (P2P stores) -- the all-gather of hit lists north_star asks for, overlapped tile by tile with the emit.
+ * `seq` must increase by one per call on all ranks.  Mailbox size: BVHGPU_MAILBOX_BYTES. */
+#define BVHGPU_MAX_PEERS 8
+#define BVHGPU_MAILBOX_BYTES 1024
+#define BVHGPU_IPC_HANDLE_BYTES 64
+typedef struct {
+    int rank, world;
+    void* peer_offsets[BVHGPU_MAX_PEERS];   /* u32[nrays_global + 1] on every rank (index = rank)          */
+    void* peer_hits[BVHGPU_MAX_PEERS];      /* u32[cap] on every rank                                      */
+    void* peer_mailbox[BVHGPU_MAX_PEERS];   /* BVHGPU_MAILBOX_BYTES on every rank, zero-initialised         */
+    uint64_t seq;                           /* 1, 2, 3, ... identical on all ranks for the same step        */
+    size_t rays_before;                     /* global index of this rank's first ray                        */
+    size_t nrays_global;
+    size_t cap;                             /* capacity of the global hit buffers                           */
+} bvhgpu_shard;
+int bvhgpu_traverse_sharded_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard);
+int bvhgpu_traverse_sharded_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard);
+/* Peer-mappable device memory (plain cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle). */
+int bvhgpu_peer_alloc(bvhgpu_ctx* ctx, size_t bytes, void** dev_ptr, void* handle64);
+int bvhgpu_peer_open(bvhgpu_ctx* ctx, const void* handle64, void** dev_ptr);
+int bvhgpu_peer_close(bvhgpu_ctx* ctx, void* dev_ptr);
+int bvhgpu_peer_free(bvhgpu_ctx* ctx, void* dev_ptr);
+/* Synchronous device -> host copy on the context's stream (lets a binding read peer-allocated buffers). */
+int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+
 /* Counters of the last traversal on this tree: [0] node records visited, [1] hits. */
 int bvhgpu_traverse_stats_f32x3(bvhgpu_tree3f* tree, uint64_t* out2);
 int bvhgpu_traverse_stats_f64x3(bvhgpu_tree3d* tree, uint64_t* out2);
