@@ -149,7 +149,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from bvh_b200 import api, capi, scenes
-    from bvh_b200.dist import allgather_csr
+    from bvh_b200.dist import ShardedTraversal
     from bvh_b200.dtypes import RAY3F
 
     ctx = api.Context(local)
@@ -175,10 +175,13 @@ def run_b200(args):
     ctx.synchronize()
     ctx.set_option("profile", 1)
 
+    sharded = ShardedTraversal(bvh, N_RAYS, 2 * N_RAYS * world) if world > 1 else None
+
     def step():
-        bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap)
-        if world > 1:      # the path's one exchange step: all-gather of the hit lists (NCCL over NVLink)
-            allgather_csr(d_off, d_hits)
+        if sharded is None:
+            bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap)
+        else:              # walk + the path's one exchange step (hit lists stored into every rank's global CSR over NVLink P2P)
+            sharded.step(d_rays.data_ptr(), N_RAYS)
 
     def barrier():
         if world > 1:
@@ -217,8 +220,10 @@ def run_b200(args):
     if world > 1:
         if rank == 0:
             line = _base_line(args, value, step_ms, launches, clocks)
-            line["config"]["parallelism"] = f"ray batch sharded over {world} GPUs (1M rays each), tree replicated, NCCL all-gather of CSR hit lists inside the step"
+            line["config"]["parallelism"] = (f"ray batch sharded over {world} GPUs (1M rays each), tree replicated; all-gather of the CSR hit lists fused into the "
+                                             "traversal: totals via peer mailboxes, emit kernel stores into every rank's global CSR over NVLink P2P (CUDA IPC), inside the step")
             print(json.dumps(line), flush=True)
+        sharded.close()
         dist.destroy_process_group()
         return
 
