@@ -189,7 +189,8 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
@@ -197,6 +198,11 @@ def run_b200(args):
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     walk_ms = []
+    if rank == 0:                          # nvidia-smi needs a moment for its first sample: keep the GPU loaded until it has one
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 5.0:
+            bvh.traverse_dev(d_rays.data_ptr(), N_RAYS, d_off.data_ptr(), d_hits.data_ptr(), cap)   # local work only (no peer handshake)
+            torch.cuda.synchronize(dev)
     barrier()
     sampler.mark_begin()
     for k in range(args.steps):
