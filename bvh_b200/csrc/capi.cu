@@ -206,25 +206,6 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
-    // Zero-copy path: when rays, offsets and hits all live in pinned (device-mapped) host memory, the walk kernel
-    // reads the rays and the emit kernel writes the CSR straight through PCIe -- no staging copies, the transfers
-    // overlap the traversal inside the kernels themselves.
-    auto mapped_host = [](const void* p) {
-        cudaPointerAttributes a{};
-        if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-        return a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
-    };
-    if (nrays && tree->n && hits && cap && mapped_host(rays) && mapped_host(offsets) && mapped_host(hits)) {
-        size_t t0 = 0;
-        int rc0 = traverse_device<T>(tree, mode, rays, nullptr, nrays, offsets, hits, cap, &t0);
-        if (total) *total = t0;
-        if (rc0 == BVHGPU_OK) {
-            BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            return BVHGPU_OK;
-        }
-        if (rc0 != BVHGPU_ERR_CAPACITY) return rc0;
-        // hit list larger than the caller's buffer: fall through to the staged path, which retains the result on the device
-    }
     size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 4 * nrays), 1024);
     size_t tot = 0;
     int rc = BVHGPU_OK;

@@ -105,37 +105,13 @@ __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T
                                                          uint32_t first, uint32_t count,
                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
                                                          unsigned long long* __restrict__ visit_total) {
-    // rays [first, first+count) of a batch of nrays (the pageable-host path feeds the batch in chunks).
-    // The block's 256 rays are one contiguous 9 KB (f32) range: fetch it with coalesced 16-byte loads into shared
-    // memory and pick the lane's origin / inv_direction from there.  Besides turning 6 strided scalar loads per
-    // lane into 2.25 vector loads, this is what makes reading rays straight out of pinned HOST memory (zero-copy
-    // H2D inside the kernel, full 128-byte PCIe reads) efficient.
-    constexpr int WORDS = (int)(sizeof(typename Traits<T>::Ray) / 4);            // 9 (f32) / 18 (f64)
-    __shared__ uint4 sray4[256 * WORDS / 4];
-    const uint32_t r0 = first + blockIdx.x * blockDim.x;
-    const uint32_t nblock = min(256u, first + count - r0);
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(rays + r0);
-        const uint32_t nwords = nblock * WORDS;
-        uint32_t* sw = reinterpret_cast<uint32_t*>(sray4);
-        if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            const uint4* src4 = reinterpret_cast<const uint4*>(src);
-            for (uint32_t i = threadIdx.x; i < nwords / 4; i += 256) sray4[i] = __ldg(src4 + i);
-            for (uint32_t i = (nwords / 4) * 4 + threadIdx.x; i < nwords; i += 256) sw[i] = __ldg(src + i);
-        } else {
-            for (uint32_t i = threadIdx.x; i < nwords; i += 256) sw[i] = __ldg(src + i);
-        }
-    }
-    __syncthreads();
-    const uint32_t r = r0 + threadIdx.x;
+    // rays [first, first+count) of a batch of nrays (the host-pointer entry point feeds the batch in chunks
+    // so that the H2D copy of chunk c+1 overlaps the walk of chunk c)
+    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t visits = 0;
     if (r < first + count) {
         T o[3], inv[3];
-        {
-            const T* p = reinterpret_cast<const T*>(sray4) + (size_t)threadIdx.x * 9;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { o[k] = p[k]; inv[k] = p[6 + k]; }
-        }
+        load_ray<T>(rays, r, o, inv);
         uint32_t cnt = 0;
         visits = walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
             if (cnt < K) slots[(size_t)cnt * nrays + r] = shape;
