@@ -206,28 +206,32 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
+    if (nrays == 0 || tree->n == 0) {                            // nothing to pipeline
+        size_t tot0 = 0;
+        BVH_TRY(ensure_result_buffers(tree, nrays, 1024));
+        BVH_TRY(traverse_device<T>(tree, mode, nullptr, rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot0));
+        BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (total) *total = 0;
+        return BVHGPU_OK;
+    }
     size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 4 * nrays), 1024);
     size_t tot = 0;
     int rc = BVHGPU_OK;
     for (int attempt = 0; attempt < 2; ++attempt) {
         rc = ensure_result_buffers(tree, nrays, want);
         if (rc != BVHGPU_OK) break;
-        rc = traverse_device<T>(tree, mode, nullptr, rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
-        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }   // grow once and redo
+        rc = traverse_host_pipelined<T>(tree, mode, rays, nrays, offsets, hits, cap, &tot);
+        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && tot > tree->hits_cap && attempt == 0) { want = tot; continue; }   // grow once and redo
         break;
     }
     if (total) *total = tot;
     if (rc != BVHGPU_OK) return rc;
-    BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    int ret = BVHGPU_OK;
-    if (hits && tot <= cap) {
-        if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(hits, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream));
-    } else if (tot > cap) {
+    if (tot > cap) {
         set_error("traverse: %zu hits do not fit the caller's capacity %zu (use bvhgpu_traverse_fetch_*)", tot, cap);
-        ret = BVHGPU_ERR_CAPACITY;
+        return BVHGPU_ERR_CAPACITY;
     }
-    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    return ret;
+    return BVHGPU_OK;
 }
 
 template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t cap) {
@@ -293,6 +297,8 @@ BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
     BVH_CUDA_TRY(cudaMallocHost((void**)&ctx->h_pinned, 256 * sizeof(uint32_t)));
     for (int i = 0; i < 2; ++i) { BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_walk[i])); BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_build[i])); }
     BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
@@ -310,6 +316,8 @@ BVH_EXPORT void bvhgpu_destroy(bvhgpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) if (ctx->ev_emit[i]) cudaEventDestroy(ctx->ev_emit[i]);
     if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->ev_total) cudaEventDestroy(ctx->ev_total);
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);

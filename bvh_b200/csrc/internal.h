@@ -48,9 +48,9 @@ struct bvhgpu_ctx {
     cudaEvent_t ev_build[2] = {nullptr, nullptr};
     bool have_walk = false, have_build = false;
     // host-pointer traversal: H2D chunks on a second stream, overlapped with the walks
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_order = nullptr, ev_total = nullptr;
-    cudaEvent_t ev_chunk[16] = {};
+    cudaEvent_t ev_chunk[16] = {}, ev_emit[16] = {};
 };
 #define BVH_MAX_CHUNKS 16u
 
@@ -112,6 +112,9 @@ template <class T> int refit(Tree<T>* tree);                     // recompute ch
 template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays,
                                        size_t nrays, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total,
                                        const bvhgpu_shard* shard = nullptr);
+// Host rays in, host CSR out; H2D / walk+scan+emit / D2H pipelined over chunks.  Needs tree->d_offsets / d_hits sized by the caller.
+template <class T> int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::Ray* h_rays, size_t nrays,
+                                               uint32_t* h_offsets, uint32_t* h_hits, size_t h_cap, size_t* total);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
                                        typename Traits<T>::Ray* d_rays);
 

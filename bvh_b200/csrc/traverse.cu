@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
                                                            unsigned long long* __restrict__ total) {
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
+    if (threadIdx.x == 0) carry_s = *total;          // running total of the chunks scanned before this one (0 for the first)
     __syncthreads();
     for (uint32_t b0 = 0; b0 < nblocks; b0 += 1024) {
         const uint32_t b = b0 + threadIdx.x;
@@ -247,14 +247,14 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
                                                    const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
                                                    const unsigned long long* __restrict__ total,
-                                                   EmitDst dst, unsigned long long cap) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count) {
+    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long hbase = dst.hit_base ? *dst.hit_base : 0ull;
-    if (r == 0) {
+    if (r == first) {                         // (chunked host path: the last chunk's write is the final total)
         const unsigned long long t = dst.grand_total ? *dst.grand_total : *total;
         dst.offsets[dst.self][dst.nrays_global] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
     }
-    if (r >= nrays) return;
+    if (r >= first + count) return;
     const unsigned long long off = hbase + blocksum[r / SCAN_TILE] + local[r];
     const uint32_t off32 = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
     for (int d = 0; d < dst.world; ++d) dst.offsets[d][dst.ray_base + r] = off32;
@@ -363,8 +363,8 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     } else {
         dst.world = 1; dst.self = 0; dst.offsets[0] = d_offsets; dst.hits[0] = d_hits; dst.ray_base = 0; dst.nrays_global = R;
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap);
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap, 0u, R);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap, 0u, R);
     if (shard) { xchg_done_kernel<<<1, 32, 0, st>>>(pb, (uint32_t*)(sums + nblk + 4), xchg_timeout); ctx->launches++; }
     ctx->launches += 3;
     BVH_CUDA_TRY(cudaGetLastError());
@@ -380,6 +380,79 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums); if (staged) dfree(ctx, staged);
     return rc;
 }
+
+// Host-pointer entry point, fully pipelined: the batch is cut into chunks; chunk c's H2D copy (copy stream) overlaps
+// the walk / scan / emit of chunk c-1 (compute stream), and chunk c-1's offsets travel back (D2H stream) while chunk c
+// is walked.  The per-chunk scans chain through a running total on the device, so every chunk's offsets are final as
+// soon as its emit kernel has run.  Results are retained in tree->d_offsets / d_hits (bvhgpu_traverse_fetch_*).
+template <class T>
+int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::Ray* h_rays, size_t nrays,
+                            uint32_t* h_offsets, uint32_t* h_hits, size_t h_cap, size_t* total) {
+    using Ray = typename Traits<T>::Ray;
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t R = (uint32_t)nrays;
+    BVH_TRY(resolve_status(tree));
+    if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const uint32_t K = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(ctx->traverse_slots, 64));
+    const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
+    unsigned long long* sums = nullptr;
+    Ray* staged = nullptr;
+    BVH_TRY(dalloc_t(ctx, &counts, R));
+    BVH_TRY(dalloc_t(ctx, &local, R));
+    if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 6));
+    BVH_TRY(dalloc_t(ctx, &staged, R));
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 6 * sizeof(unsigned long long), st));
+    BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));
+    BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
+    BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_order, 0));
+    const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
+    EmitDst dst{};
+    dst.world = 1; dst.self = 0; dst.offsets[0] = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.ray_base = 0; dst.nrays_global = R;
+    // chunk size: >= ~200k rays (a walk launch has a ~0.1 ms floor), multiple of the scan tile
+    uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 200000));
+    uint32_t per = ((R + nchunks - 1) / nchunks + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    nchunks = (R + per - 1) / per;
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t lo = c * per, hi = std::min<uint32_t>(R, lo + per), cnt = hi - lo;
+        BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+        BVH_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+        const int grid = (cnt + 255) / 256;
+        const uint32_t b0 = lo / SCAN_TILE, nb = (cnt + SCAN_TILE - 1) / SCAN_TILE;
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, lo, cnt, counts, slots, K, sums + nblk + 1);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, lo, cnt, counts, slots, K, sums + nblk + 1);
+        scan_local_kernel<<<nb, SCAN_THREADS, 0, st>>>(counts + lo, cnt, local + lo, sums + b0);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums + b0, nb, sums + nblk);
+        if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+        else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+        ctx->launches += 4;
+        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
+        BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
+        const uint32_t ncopy = cnt + (c + 1 == nchunks ? 1u : 0u);      // the last chunk also carries offsets[R] = total
+        BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    BVH_CUDA_TRY(cudaGetLastError());
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
+    BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BVH_CUDA_TRY(cudaStreamSynchronize(st));
+    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums); dfree(ctx, staged);
+    const unsigned long long tot = h[0];
+    tree->last_total = (size_t)tot; tree->last_visits = h[1]; tree->last_nrays = nrays;
+    if (total) *total = (size_t)tot;
+    int rc = BVHGPU_OK;
+    if (tot > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", tot); rc = BVHGPU_ERR_CAPACITY; }
+    else if (tot > tree->hits_cap) { set_error("traverse: %llu hits exceed the retained buffer (%zu)", tot, tree->hits_cap); rc = BVHGPU_ERR_CAPACITY; }
+    else if (h_hits && tot <= h_cap) {
+        if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(h_hits, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->d2h_stream));
+    return rc;
+}
+template int traverse_host_pipelined<float>(Tree<float>*, int, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_host_pipelined<double>(Tree<double>*, int, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 
 // ---- Ray::new for a batch (src/ray/ray_impl.rs:70-80) -------------------------------------------------
 template <class T> __device__ __forceinline__ T sqrt_rn(T x);
