@@ -41,6 +41,8 @@ struct bvhgpu_ctx {
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     int64_t traverse_slots = 4;    // per-ray hit slots of the single-pass traversal (0 = two-pass)
+    int64_t traverse_persistent = 1;   // 1: persistent refill walk kernel, 0: one ray per thread
+    int walk_grid = 0;             // persistent grid size (computed once)
     int64_t build_tile = 0;        // reserved
     uint32_t* h_pinned = nullptr;  // small pinned read-back area (256 words)
     int64_t profile = 0;           // bracket dominant kernels with events

@@ -123,6 +123,86 @@ __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T
     if (lane_id() == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
 }
 
+// Pass 1, persistent form.  A fixed grid of warps pulls rays from a global ticket counter; a lane that finishes
+// its ray is refilled as soon as REFILL lanes of its warp are idle, so warps stay populated although rays take
+// 10..400 visits (the one-ray-per-thread kernel above averages 12 of 32 active lanes on random rays).
+// STREAM: the rays are still arriving from the host (chunked H2D on the copy stream); `ready` counts the rays
+// whose bytes are resident (bumped by a 4-byte DMA after every chunk), lanes wait for their ray to arrive, and
+// ray loads bypass the non-coherent path.  Copy and walk overlap without any per-chunk kernel tail.
+template <class T, bool FLAT, bool STREAM>
+__global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                              const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                              const typename Traits<T>::Ray* rays, uint32_t nrays,
+                                                              uint32_t* __restrict__ ticket, const uint32_t* ready,
+                                                              uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
+                                                              unsigned long long* __restrict__ visit_total) {
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    constexpr int REFILL = 8;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = lane_id(), lt = lanemask_lt();
+    uint32_t r = NONE, i = 0, cnt = 0, visits = 0;
+    T o[3] = {T(0), T(0), T(0)}, inv[3] = {T(0), T(0), T(0)};
+    bool exhausted = false;
+    for (;;) {
+        // ---- refill idle lanes -------------------------------------------------------------------------
+        const uint32_t need = __ballot_sync(FULL, r == NONE);
+        if (need && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(ticket, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= nrays) exhausted = true;
+            const uint32_t mine = base + __popc(need & lt);
+            const bool take = r == NONE && mine < nrays;
+            if (STREAM) {
+                const uint32_t want = __reduce_max_sync(FULL, take ? mine + 1 : 0u);
+                if (want) {
+                    uint32_t ns = 100;
+                    while (*(volatile const uint32_t*)ready < want) { __nanosleep(ns); if (ns < 2000) ns <<= 1; }
+                    __threadfence();
+                }
+            }
+            if (take) {
+                const T* p = reinterpret_cast<const T*>(rays + mine);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (STREAM) { o[k] = __ldcg(p + k); inv[k] = __ldcg(p + 6 + k); }
+                    else        { o[k] = __ldg(p + k);  inv[k] = __ldg(p + 6 + k); }
+                }
+                r = mine; i = 0; cnt = 0;
+            }
+        }
+        if (__ballot_sync(FULL, r != NONE) == 0) break;
+        // ---- walk until enough lanes have gone idle ----------------------------------------------------
+        for (;;) {
+            if (r != NONE) {
+                T mn[3], mx[3];
+                uint32_t skip, shape;
+                fetch(trec + i, mn, mx, skip, shape);
+                ++visits;
+                if (slab_hit(o, inv, mn, mx)) {
+                    if (shape != BVH_INVALID) {
+                        bool report = true;
+                        if (FLAT) {
+                            T smn[3], smx[3];
+                            load_aabb(aabb + shape, smn, smx);
+                            report = slab_hit(o, inv, smn, smx);
+                        }
+                        if (report) { if (cnt < K) slots[(size_t)cnt * nrays + r] = shape; ++cnt; }
+                    }
+                    i = i + 1;
+                } else {
+                    i = skip;
+                }
+                if (i >= n_rec) { counts[r] = cnt; r = NONE; }
+            }
+            const int idle = __popc(__ballot_sync(FULL, r == NONE));
+            if (idle == 32 || (idle >= REFILL && !exhausted)) break;
+        }
+    }
+    visits = __reduce_add_sync(FULL, visits);
+    if (lane == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
+}
+
 // Exclusive scan of counts, phase A: per-block local exclusive offsets + block totals.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ counts, uint32_t n,
                                                                   uint32_t* __restrict__ local, unsigned long long* __restrict__ blocksum) {
@@ -278,6 +358,40 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
     }
 }
 
+// Launch pass 1 over rays [first, first+count): persistent refill kernel (default) or one ray per thread.
+// sums layout (u64 words): [nblk] total, [nblk+1] visits, [nblk+2..3] exchange info, [nblk+4] error, [nblk+5] ticket, [nblk+6] ready.
+template <class T>
+static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray* rays, uint32_t R, uint32_t first, uint32_t count,
+                        uint32_t* counts, uint32_t* slots, uint32_t K, unsigned long long* sums, uint32_t nblk, bool stream_mode) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->traverse_persistent && !stream_mode) {
+        const int grid = (count + 255) / 256;
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+        ctx->launches++;
+        return BVHGPU_OK;
+    }
+    if (first != 0 || count != R) { set_error("internal: persistent walk covers whole batches only"); return BVHGPU_ERR_INTERNAL; }
+    if (ctx->walk_grid == 0) {
+        int occ = 1;
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persistent_kernel<float, false, false>, 256, 0));
+        ctx->walk_grid = ctx->sm_count * (occ < 1 ? 1 : occ);
+    }
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->walk_grid, ((uint64_t)R + 255) / 256);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(sums + nblk + 5);
+    const uint32_t* ready = reinterpret_cast<const uint32_t*>(sums + nblk + 6);
+    if (stream_mode) {
+        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+    } else {
+        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+    }
+    ctx->launches++;
+    return BVHGPU_OK;
+}
+
 template <class T>
 int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays, size_t nrays,
                     uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total, const bvhgpu_shard* shard) {
@@ -310,8 +424,8 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     BVH_TRY(dalloc_t(ctx, &counts, R));
     BVH_TRY(dalloc_t(ctx, &local, R));
     if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 6));      // [nblk] total, [nblk+1] visits, [nblk+2..3] {hit_base, grand_total}, [nblk+4] error word
-    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 6 * sizeof(unsigned long long), st));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 8));      // see launch_pass1 for the layout of the tail words
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 8 * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     auto launch_walk = [&](const Ray* rays, uint32_t first, uint32_t count) {
         const int grid = (count + 255) / 256;
@@ -335,7 +449,7 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         d_rays = staged;
     } else {
         if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
-        launch_walk(d_rays, 0, R);
+        BVH_TRY(launch_pass1<T>(tree, flat, d_rays, R, 0, R, counts, slots, K, sums, nblk, false));
         if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
     }
     const int grid = (R + 255) / 256;
@@ -402,37 +516,47 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
     BVH_TRY(dalloc_t(ctx, &counts, R));
     BVH_TRY(dalloc_t(ctx, &local, R));
     if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 6));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 8));
     BVH_TRY(dalloc_t(ctx, &staged, R));
-    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 6 * sizeof(unsigned long long), st));
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 8 * sizeof(unsigned long long), st));
     BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));
     BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
     BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_order, 0));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     EmitDst dst{};
     dst.world = 1; dst.self = 0; dst.offsets[0] = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.ray_base = 0; dst.nrays_global = R;
-    // chunk size: >= ~200k rays (a walk launch has a ~0.1 ms floor), multiple of the scan tile
-    uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 200000));
-    uint32_t per = ((R + nchunks - 1) / nchunks + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
-    nchunks = (R + per - 1) / per;
-    for (uint32_t c = 0; c < nchunks; ++c) {
-        const uint32_t lo = c * per, hi = std::min<uint32_t>(R, lo + per), cnt = hi - lo;
-        BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * cnt, cudaMemcpyHostToDevice, ctx->copy_stream));
-        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
-        BVH_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
-        const int grid = (cnt + 255) / 256;
-        const uint32_t b0 = lo / SCAN_TILE, nb = (cnt + SCAN_TILE - 1) / SCAN_TILE;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, lo, cnt, counts, slots, K, sums + nblk + 1);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, lo, cnt, counts, slots, K, sums + nblk + 1);
-        scan_local_kernel<<<nb, SCAN_THREADS, 0, st>>>(counts + lo, cnt, local + lo, sums + b0);
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums + b0, nb, sums + nblk);
-        if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
-        else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
-        ctx->launches += 4;
-        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
-        BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
-        const uint32_t ncopy = cnt + (c + 1 == nchunks ? 1u : 0u);      // the last chunk also carries offsets[R] = total
-        BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    // ONE persistent walk kernel consumes the rays as they arrive: the batch is copied in small chunks on the copy
+    // stream, each followed by a 4-byte DMA that bumps the device-side `ready` counter the kernel's lanes wait on.
+    BVH_TRY(launch_pass1<T>(tree, flat, staged, R, 0, R, counts, slots, K, sums, nblk, true));
+    {
+        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 32768));
+        uint32_t* h_ready = ctx->h_pinned + 64;                  // pinned: one value per chunk, alive until the final sync
+        uint32_t* d_ready = reinterpret_cast<uint32_t*>(sums + nblk + 6);
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
+            BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));
+            h_ready[c] = hi;
+            BVH_CUDA_TRY(cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+    }
+    {
+        const int grid = (R + 255) / 256;
+        scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+        // emit + D2H of the offsets in 4 slices so that the copy back overlaps the rest of the emit
+        const uint32_t nsl = R >= 400000 ? 4 : 1;
+        for (uint32_t c = 0; c < nsl; ++c) {
+            const uint32_t lo = (uint32_t)((uint64_t)R * c / nsl), hi = (uint32_t)((uint64_t)R * (c + 1) / nsl), cnt = hi - lo;
+            const int g = (cnt + 255) / 256;
+            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+            BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
+            BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
+            const uint32_t ncopy = cnt + (c + 1 == nsl ? 1u : 0u);
+            BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+        (void)grid;
+        ctx->launches += 2 + nsl;
     }
     BVH_CUDA_TRY(cudaGetLastError());
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
