@@ -299,6 +299,7 @@ BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
     BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     BVH_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
+    for (int i = 0; i < 5; ++i) BVH_CUDA_TRY(cudaEventCreate(&ctx->ev_e2e[i]));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
@@ -356,6 +357,16 @@ BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out)
     cudaEvent_t* ev = nullptr;
     if (!strcmp(name, "walk_ms") && ctx->have_walk) ev = ctx->ev_walk;
     else if (!strcmp(name, "build_ms") && ctx->have_build) ev = ctx->ev_build;
+    if (!ev && ctx->have_e2e && !strncmp(name, "e2e_", 4)) {      // e2e_walk_ms / e2e_h2d_ms / e2e_emit_ms / e2e_d2h_ms: since call start
+        int k = !strcmp(name, "e2e_walk_ms") ? 1 : !strcmp(name, "e2e_h2d_ms") ? 2 : !strcmp(name, "e2e_emit_ms") ? 3 : !strcmp(name, "e2e_d2h_ms") ? 4 : 0;
+        if (k) {
+            BVH_CUDA_TRY(cudaEventSynchronize(ctx->ev_e2e[k]));
+            float ms = 0.f;
+            BVH_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_e2e[0], ctx->ev_e2e[k]));
+            *out = (double)ms;
+            return BVHGPU_OK;
+        }
+    }
     if (!ev) { set_error("get_metric: '%s' not recorded (set option profile=1 and run the call first)", name); return BVHGPU_ERR_INVALID; }
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_CUDA_TRY(cudaEventSynchronize(ev[1]));

@@ -53,6 +53,8 @@ struct bvhgpu_ctx {
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_order = nullptr, ev_total = nullptr;
     cudaEvent_t ev_chunk[16] = {}, ev_emit[16] = {};
+    cudaEvent_t ev_e2e[5] = {};    // profile: start, walk end, last H2D done, last emit, last D2H
+    bool have_e2e = false;
 };
 #define BVH_MAX_CHUNKS 16u
 

@@ -527,7 +527,9 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
     dst.world = 1; dst.self = 0; dst.offsets[0] = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.ray_base = 0; dst.nrays_global = R;
     // ONE persistent walk kernel consumes the rays as they arrive: the batch is copied in small chunks on the copy
     // stream, each followed by a 4-byte DMA that bumps the device-side `ready` counter the kernel's lanes wait on.
+    if (ctx->profile) cudaEventRecord(ctx->ev_e2e[0], st);
     BVH_TRY(launch_pass1<T>(tree, flat, staged, R, 0, R, counts, slots, K, sums, nblk, true));
+    if (ctx->profile) cudaEventRecord(ctx->ev_e2e[1], st);
     {
         const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 32768));
         uint32_t* h_ready = ctx->h_pinned + 64;                  // pinned: one value per chunk, alive until the final sync
@@ -538,6 +540,7 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
             h_ready[c] = hi;
             BVH_CUDA_TRY(cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
         }
+        if (ctx->profile) cudaEventRecord(ctx->ev_e2e[2], ctx->copy_stream);
     }
     {
         const int grid = (R + 255) / 256;
@@ -556,6 +559,7 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
             BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
         (void)grid;
+        if (ctx->profile) { cudaEventRecord(ctx->ev_e2e[3], st); cudaEventRecord(ctx->ev_e2e[4], ctx->d2h_stream); ctx->have_e2e = true; }
         ctx->launches += 2 + nsl;
     }
     BVH_CUDA_TRY(cudaGetLastError());
