@@ -40,8 +40,8 @@ struct bvhgpu_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
-    int64_t traverse_slots = 4;    // per-ray hit slots of the single-pass traversal (0 = two-pass)
-    int64_t traverse_persistent = 1;   // 1: persistent refill walk kernel, 0: one ray per thread
+    int64_t traverse_slots = -1;   // per-ray hit slots of the single-pass traversal (0 = two-pass, -1 = auto by batch size)
+    int64_t traverse_persistent = 2;   // 0: one ray per thread, 1: persistent refill kernel, 2: coherence probe decides on the device
     int walk_grid = 0;             // persistent grid size (computed once)
     int64_t build_tile = 0;        // reserved
     uint32_t* h_pinned = nullptr;  // small pinned read-back area (256 words)

@@ -15,6 +15,16 @@
 
 namespace bvhb200 {
 
+// Per-ray hit slots of the single-pass scheme: "traverse_slots" option, or (-1, default) as many as a 1 GB
+// scratch budget allows, between 4 and 64 -- rays with more hits than slots are walked a second time by the emit pass.
+static inline uint32_t pick_slots(const bvhgpu_ctx* ctx, uint32_t nrays) {
+    if (ctx->traverse_slots >= 0) return (uint32_t)std::min<int64_t>(ctx->traverse_slots, 64);
+    uint64_t k = (1ull << 28) / std::max<uint32_t>(nrays, 1u);
+    uint32_t p = 4;
+    while (p * 2 <= k && p < 64) p *= 2;
+    return p;
+}
+
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;     // 2048 counts per block
@@ -97,6 +107,36 @@ template <class T> __device__ __forceinline__ void load_ray(const typename Trait
     for (int k = 0; k < 3; ++k) { o[k] = __ldg(p + k); inv[k] = __ldg(p + 6 + k); }
 }
 
+// Coherence probe: neighbouring rays of a coherent batch (camera rays) point the same way, and then the static
+// one-ray-per-thread mapping wins (adjacent lanes walk the same nodes: one L1 wavefront serves many lanes); on
+// incoherent batches the persistent refill kernel wins.  The probe samples 1024 neighbour pairs and leaves its
+// verdict in *flag; BOTH pass-1 kernels are launched and the one the verdict rules out returns immediately, so
+// the choice costs no host synchronisation.
+template <class T>
+__global__ void __launch_bounds__(256) coherence_probe_kernel(const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays, uint32_t* flag) {
+    __shared__ float acc[8];
+    float sum = 0.f;
+    const uint32_t samples = 1024, stride = nrays > 2 * samples ? nrays / samples : 1;
+    uint32_t n = 0;
+    for (uint32_t k = threadIdx.x; k < samples; k += 256) {
+        const uint32_t i = k * stride;
+        if (i + 1 >= nrays) break;
+        const T* a = reinterpret_cast<const T*>(rays + i) + 3;
+        const T* b = reinterpret_cast<const T*>(rays + i + 1) + 3;
+        sum += (float)(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+        ++n;
+    }
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); n += __shfl_xor_sync(0xffffffffu, n, o); }
+    __shared__ uint32_t cnt[8];
+    if (lane_id() == 0) { acc[threadIdx.x >> 5] = sum; cnt[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f; uint32_t c = 0;
+        for (int w = 0; w < 8; ++w) { s += acc[w]; c += cnt[w]; }
+        *flag = (c > 0 && s / (float)c > 0.9f) ? 1u : 0u;          // 1 = coherent
+    }
+}
+
 // Pass 1: count all hits of every ray, keep the first K in slot-major scratch.
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
@@ -104,9 +144,8 @@ __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T
                                                          const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
                                                          uint32_t first, uint32_t count,
                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
-                                                         unsigned long long* __restrict__ visit_total) {
-    // rays [first, first+count) of a batch of nrays (the host-pointer entry point feeds the batch in chunks
-    // so that the H2D copy of chunk c+1 overlaps the walk of chunk c)
+                                                         unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
+    if (gate && *gate != run_if) return;             // the coherence probe chose the other pass-1 kernel
     const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t visits = 0;
     if (r < first + count) {
@@ -135,7 +174,8 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
                                                               const typename Traits<T>::Ray* rays, uint32_t nrays,
                                                               uint32_t* __restrict__ ticket, const uint32_t* ready,
                                                               uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
-                                                              unsigned long long* __restrict__ visit_total) {
+                                                              unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
+    if (gate && *gate != run_if) return;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
     constexpr int REFILL = 8;
     const uint32_t FULL = 0xffffffffu;
@@ -365,12 +405,20 @@ static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray*
                         uint32_t* counts, uint32_t* slots, uint32_t K, unsigned long long* sums, uint32_t nblk, bool stream_mode) {
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
-    if (!ctx->traverse_persistent && !stream_mode) {
-        const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+    // traverse_persistent: 0 = one ray per thread, 1 = persistent refill, 2 (default) = probe decides on the device
+    const int64_t pmode = stream_mode ? 1 : ctx->traverse_persistent;
+    uint32_t* gate = nullptr;
+    if (pmode >= 2) {
+        gate = reinterpret_cast<uint32_t*>(sums + nblk + 7);
+        coherence_probe_kernel<T><<<1, 256, 0, st>>>(rays, R, gate);
         ctx->launches++;
-        return BVHGPU_OK;
+    }
+    if (pmode == 0 || pmode >= 2) {
+        const int grid = (count + 255) / 256;
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
+        ctx->launches++;
+        if (pmode == 0) return BVHGPU_OK;
     }
     if (first != 0 || count != R) { set_error("internal: persistent walk covers whole batches only"); return BVHGPU_ERR_INTERNAL; }
     if (ctx->walk_grid == 0) {
@@ -382,11 +430,11 @@ static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray*
     uint32_t* ticket = reinterpret_cast<uint32_t*>(sums + nblk + 5);
     const uint32_t* ready = reinterpret_cast<const uint32_t*>(sums + nblk + 6);
     if (stream_mode) {
-        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
-        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, nullptr, 0u);
+        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, nullptr, 0u);
     } else {
-        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
-        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1);
+        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, gate, 0u);
+        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, gate, 0u);
     }
     ctx->launches++;
     return BVHGPU_OK;
@@ -416,7 +464,7 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     BVH_TRY(resolve_status(tree));                               // never walk a tree whose build failed
     if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
     const uint32_t R = (uint32_t)nrays;
-    const uint32_t K = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(ctx->traverse_slots, 64));
+    const uint32_t K = pick_slots(ctx, R);
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;       // [nblk] block offsets, [nblk] total, [nblk+1] visits
@@ -429,8 +477,8 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     auto launch_walk = [&](const Ray* rays, uint32_t first, uint32_t count) {
         const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1);
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
         ctx->launches++;
     };
     if (h_rays) {
@@ -508,7 +556,7 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
     const uint32_t R = (uint32_t)nrays;
     BVH_TRY(resolve_status(tree));
     if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
-    const uint32_t K = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(ctx->traverse_slots, 64));
+    const uint32_t K = pick_slots(ctx, R);
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;

@@ -78,15 +78,17 @@ def _check_traverse(api, bvh, want_nodes, shapes, rays, prec="f32"):
     flat = O.flatten(want_nodes, prec)
     r_rec = O.traverse(want_nodes, shapes, rays, O.MODE_RECURSIVE, prec)
     r_flat = O.traverse(flat, shapes, rays, O.MODE_FLAT, prec)
-    for slots in (4, 0, 1):                       # single-pass, two-pass, forced overflow re-walk
+    for slots, pers in ((4, 2), (0, 1), (1, 0), (-1, 1)):   # single-pass / two-pass / forced overflow re-walk x pass-1 kernel choice
         bvh.ctx.set_option("traverse_slots", slots)
+        bvh.ctx.set_option("traverse_persistent", pers)
         off, hits = bvh.traverse_batch(rays, mode=capi.TRAVERSE_BVH)
         assert np.array_equal(off.astype(np.uint64), r_rec.offsets), slots
         assert np.array_equal(hits, r_rec.hits), slots
         off, hits = bvh.traverse_batch(rays, mode=capi.TRAVERSE_FLAT)
         assert np.array_equal(off.astype(np.uint64), r_flat.offsets), slots
         assert np.array_equal(hits, r_flat.hits), slots
-    bvh.ctx.set_option("traverse_slots", 4)
+    bvh.ctx.set_option("traverse_slots", -1)
+    bvh.ctx.set_option("traverse_persistent", 2)
     visits, total = bvh.traverse_stats()
     assert total == len(r_flat.hits)
 
