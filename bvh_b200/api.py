@@ -236,6 +236,24 @@ class Bvh:
             capi.check(st)
         return offsets, hits[: total.value]
 
+    def query_batch(self, kind: int, queries, mode: int = capi.TRAVERSE_BVH):
+        """Bvh::traverse with Aabb / Point / Ball queries (IntersectsAabb implementors other than Ray).
+        queries: (n, 6) {min,max} for capi.QUERY_AABB, (n, 3) for QUERY_POINT, (n, 4) {center, radius} for QUERY_BALL."""
+        stride = {capi.QUERY_AABB: 6, capi.QUERY_POINT: 3, capi.QUERY_BALL: 4}[kind]
+        q = np.ascontiguousarray(queries, dtype=self._d["scalar"]).reshape(-1, stride)
+        n = len(q)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        cap = max(16 * n, 1024)
+        hits = np.zeros(cap, dtype=np.uint32)
+        total = C.c_size_t(0)
+        st = getattr(capi.lib(), f"bvhgpu_query_{self._d['suffix']}")(self._h, mode, kind, _ptr(q), n, _ptr(offsets), _ptr(hits), cap, C.byref(total))
+        if st == capi.ERR_CAPACITY and total.value <= U32_MAX:
+            hits = np.zeros(total.value, dtype=np.uint32)
+            capi.check(getattr(capi.lib(), f"bvhgpu_traverse_fetch_{self._d['suffix']}")(self._h, _ptr(hits), total.value))
+        else:
+            capi.check(st)
+        return offsets, hits[: total.value]
+
     def traverse_dev(self, rays_ptr: int, nrays: int, offsets_ptr: int, hits_ptr: int, cap: int, mode: int = capi.TRAVERSE_BVH,
                      want_total: bool = False):
         total = C.c_size_t(0)

@@ -13,6 +13,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "bvh_b200.h")
 OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_CAPACITY, ERR_TIMEOUT, ERR_UNSUPPORTED, ERR_INTERNAL = range(8)
 BUILD_EXACT_SAH, BUILD_LBVH = 0, 1
 TRAVERSE_BVH, TRAVERSE_FLAT = 0, 1
+QUERY_AABB, QUERY_POINT, QUERY_BALL = 1, 2, 3
 
 
 MAX_PEERS, MAILBOX_BYTES, IPC_HANDLE_BYTES = 8, 1024, 64
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_traverse_fetch_{s}").argtypes = [vp, vp, sz]
         getattr(L, f"bvhgpu_traverse_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_stats_{s}").argtypes = [vp, u64p]
+        getattr(L, f"bvhgpu_query_{s}").argtypes = [vp, i32, i32, vp, sz, vp, vp, sz, szp]
+        getattr(L, f"bvhgpu_query_dev_{s}").argtypes = [vp, i32, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_sharded_dev_{s}").argtypes = [vp, i32, vp, sz, C.POINTER(Shard)]
         getattr(L, f"bvhgpu_rays_new_dev_{s}").argtypes = [vp, vp, vp, sz, vp]
         getattr(L, f"bvhgpu_sah_cost_{s}").argtypes = [vp, C.POINTER(C.c_double)]

@@ -234,6 +234,39 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     return BVHGPU_OK;
 }
 
+template <class T>
+static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, size_t n, uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total) {
+    if (!tree || (n && !queries) || !offsets) { set_error("query: null argument"); return BVHGPU_ERR_INVALID; }
+    if (kind < BVHGPU_QUERY_AABB || kind > BVHGPU_QUERY_BALL) { set_error("query: bad kind %d", kind); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    const size_t stride = kind == BVHGPU_QUERY_AABB ? 6 : (kind == BVHGPU_QUERY_POINT ? 3 : 4);
+    T* d_q = nullptr;
+    if (n) {
+        BVH_TRY(dalloc_t(ctx, &d_q, n * stride));
+        BVH_CUDA_TRY(cudaMemcpyAsync(d_q, queries, sizeof(T) * n * stride, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 16 * n), 1024), tot = 0;
+    int rc = BVHGPU_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_result_buffers(tree, n, want);
+        if (rc != BVHGPU_OK) break;
+        rc = query_device<T>(tree, mode, kind, d_q, n, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
+        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }
+        break;
+    }
+    dfree(ctx, d_q);
+    if (total) *total = tot;
+    if (rc != BVHGPU_OK) return rc;
+    BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int ret = BVHGPU_OK;
+    if (hits && tot <= cap) { if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(hits, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream)); }
+    else if (tot > cap) { set_error("query: %zu hits do not fit the caller's capacity %zu (use bvhgpu_traverse_fetch_*)", tot, cap); ret = BVHGPU_ERR_CAPACITY; }
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ret;
+}
+
 template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t cap) {
     if (!tree || !hits) { set_error("traverse_fetch: null argument"); return BVHGPU_ERR_INVALID; }
     if (cap < tree->last_total) { set_error("traverse_fetch: capacity %zu < %zu hits", cap, tree->last_total); return BVHGPU_ERR_CAPACITY; }
@@ -457,6 +490,16 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
         if (nrays == 0 || tree->n == 0) { set_error("traverse_sharded: every rank needs a non-empty shard and tree"); return BVHGPU_ERR_UNSUPPORTED; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
         return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, nullptr, nullptr, shard->cap, nullptr, shard); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_query_##SUF(TREE* tree, int mode, int kind, const T* queries, size_t n, uint32_t* offsets, uint32_t* hits, \
+                                      size_t cap, size_t* total) {                                                       \
+        return query_host_impl<T>(tree, mode, kind, queries, n, offsets, hits, cap, total);                              \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_query_dev_##SUF(TREE* tree, int mode, int kind, const void* dev_queries, size_t n, void* dev_offsets, \
+                                          void* dev_hits, size_t cap, size_t* total) {                                    \
+        if (!tree || !dev_offsets || (n && !dev_queries)) { set_error("query_dev: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return query_device<T>(tree, mode, kind, (const T*)dev_queries, n, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
         if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \

@@ -630,6 +630,147 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
 template int traverse_host_pipelined<float>(Tree<float>*, int, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 template int traverse_host_pipelined<double>(Tree<double>*, int, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 
+// ---- the other IntersectsAabb implementors: Aabb, Point, Ball (src/aabb/intersection.rs:35-45, src/ball.rs:85-106) ----
+// Same stackless walk, another predicate.  Query records: Aabb {min,max} (6 T), Point (3 T), Ball {center, radius} (4 T).
+template <class T, int KIND> struct Query;
+template <class T> struct Query<T, BVHGPU_QUERY_AABB> {
+    T mn[3], mx[3];
+    __device__ __forceinline__ void load(const T* p) { for (int k = 0; k < 3; ++k) { mn[k] = __ldg(p + k); mx[k] = __ldg(p + 3 + k); } }
+    static constexpr int STRIDE = 6;
+    __device__ __forceinline__ bool hit(const T bmn[3], const T bmx[3]) const {            // aabb_impl.rs:240-248
+        bool h = true;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (mx[i] < bmn[i] || bmx[i] < mn[i]) h = false;
+        return h;
+    }
+};
+template <class T> struct Query<T, BVHGPU_QUERY_POINT> {
+    T p[3];
+    __device__ __forceinline__ void load(const T* q) { for (int k = 0; k < 3; ++k) p[k] = __ldg(q + k); }
+    static constexpr int STRIDE = 3;
+    __device__ __forceinline__ bool hit(const T bmn[3], const T bmx[3]) const {            // Aabb::contains, aabb_impl.rs:175-177
+        bool h = true;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (!(p[i] >= bmn[i]) || !(p[i] <= bmx[i])) h = false;
+        return h;
+    }
+};
+template <class T> struct Query<T, BVHGPU_QUERY_BALL> {
+    T c[3], r2;
+    __device__ __forceinline__ void load(const T* q) { for (int k = 0; k < 3; ++k) c[k] = __ldg(q + k); const T r = __ldg(q + 3); r2 = mul_rn(r, r); }
+    static constexpr int STRIDE = 4;
+    __device__ __forceinline__ bool hit(const T bmn[3], const T bmx[3]) const {            // Ball::intersects_aabb, ball.rs:85-99
+        T d2 = T(0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            T x = c[i];
+            if (x < bmn[i]) x = bmn[i];
+            if (x > bmx[i]) x = bmx[i];
+            const T d = sub_rn(x, c[i]);
+            d2 = add_rn(d2, mul_rn(d, d));
+        }
+        return d2 <= r2;
+    }
+};
+
+template <class T, int KIND, bool FLAT, class Emit>
+__device__ __forceinline__ void walk_query(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                           const typename Traits<T>::DAabb* __restrict__ aabb, const Query<T, KIND>& q, Emit emit) {
+    uint32_t i = 0;
+    while (i < n_rec) {
+        T mn[3], mx[3];
+        uint32_t skip, shape;
+        fetch(trec + i, mn, mx, skip, shape);
+        if (q.hit(mn, mx)) {
+            if (shape != BVH_INVALID) {
+                bool report = true;
+                if (FLAT) { T smn[3], smx[3]; load_aabb(aabb + shape, smn, smx); report = q.hit(smn, smx); }
+                if (report) emit(shape);
+            }
+            i = i + 1;
+        } else i = skip;
+    }
+}
+
+// count pass (FILL = false) and fill pass (FILL = true) of the classic two-pass scheme: query batches are small
+template <class T, int KIND, bool FLAT, bool FILL>
+__global__ void __launch_bounds__(256) query_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                    const typename Traits<T>::DAabb* __restrict__ aabb, const T* __restrict__ queries, uint32_t nq,
+                                                    uint32_t* __restrict__ counts, const uint32_t* __restrict__ local,
+                                                    const unsigned long long* __restrict__ blocksum, const unsigned long long* __restrict__ total,
+                                                    uint32_t* __restrict__ offsets, uint32_t* __restrict__ hits, unsigned long long cap) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (FILL && r == 0) { const unsigned long long t = *total; offsets[nq] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t; }
+    if (r >= nq) return;
+    Query<T, KIND> q;
+    q.load(queries + (size_t)r * Query<T, KIND>::STRIDE);
+    if (!FILL) {
+        uint32_t cnt = 0;
+        walk_query<T, KIND, FLAT>(trec, n_rec, aabb, q, [&](uint32_t) { ++cnt; });
+        counts[r] = cnt;
+    } else {
+        unsigned long long w = blocksum[r / SCAN_TILE] + local[r];
+        offsets[r] = w > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)w;
+        if (hits) walk_query<T, KIND, FLAT>(trec, n_rec, aabb, q, [&](uint32_t shape) { if (w < cap) hits[w] = shape; ++w; });
+    }
+}
+
+template <class T, int KIND>
+static int query_launch(Tree<T>* tree, bool flat, const T* d_queries, uint32_t nq, uint32_t* counts, uint32_t* local,
+                        unsigned long long* sums, uint32_t nblk, uint32_t* d_offsets, uint32_t* d_hits, size_t cap) {
+    cudaStream_t st = tree->ctx->stream;
+    const int grid = (nq + 255) / 256;
+    if (flat) query_kernel<T, KIND, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    else      query_kernel<T, KIND, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, nq, local, sums);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+    if (flat) query_kernel<T, KIND, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    else      query_kernel<T, KIND, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    tree->ctx->launches += 4;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+template <class T>
+int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t nq, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (nq > 0x7FFFFFFFull) { set_error("query: too many queries"); return BVHGPU_ERR_INVALID; }
+    if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("query: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
+    if (kind != BVHGPU_QUERY_AABB && kind != BVHGPU_QUERY_POINT && kind != BVHGPU_QUERY_BALL) { set_error("query: bad kind %d", kind); return BVHGPU_ERR_INVALID; }
+    if (nq == 0 || tree->n == 0) {
+        BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nq + 1), st));
+        if (total) *total = 0;
+        tree->last_total = 0;
+        return BVHGPU_OK;
+    }
+    BVH_TRY(resolve_status(tree));
+    if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const uint32_t R = (uint32_t)nq, nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *counts = nullptr, *local = nullptr;
+    unsigned long long* sums = nullptr;
+    BVH_TRY(dalloc_t(ctx, &counts, R));
+    BVH_TRY(dalloc_t(ctx, &local, R));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
+    const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
+    int rc = kind == BVHGPU_QUERY_AABB  ? query_launch<T, BVHGPU_QUERY_AABB>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
+           : kind == BVHGPU_QUERY_POINT ? query_launch<T, BVHGPU_QUERY_POINT>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
+                                        : query_launch<T, BVHGPU_QUERY_BALL>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap);
+    if (rc == BVHGPU_OK && total) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
+        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaStreamSynchronize(st));
+        *total = (size_t)h[0];
+        tree->last_total = (size_t)h[0];
+        if (h[0] > 0xFFFFFFFFull || (d_hits && h[0] > cap)) { set_error("query: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
+    }
+    dfree(ctx, counts); dfree(ctx, local); dfree(ctx, sums);
+    return rc;
+}
+template int query_device<float>(Tree<float>*, int, int, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int query_device<double>(Tree<double>*, int, int, const double*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+
 // ---- Ray::new for a batch (src/ray/ray_impl.rs:70-80) -------------------------------------------------
 template <class T> __device__ __forceinline__ T sqrt_rn(T x);
 template <> __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }

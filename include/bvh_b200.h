@@ -192,6 +192,20 @@ int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* dev_src, size
 int bvhgpu_traverse_stats_f32x3(bvhgpu_tree3f* tree, uint64_t* out2);
 int bvhgpu_traverse_stats_f64x3(bvhgpu_tree3d* tree, uint64_t* out2);
 
+/* ---- the other IntersectsAabb implementors as batched queries ------------------------------
+ * Bvh::traverse / FlatBvh::traverse with an Aabb (src/aabb/aabb_impl.rs:240-248, src/aabb/intersection.rs:35-39),
+ * a Point (Aabb::contains, src/aabb/aabb_impl.rs:175-177, intersection.rs:41-45) or a Ball (src/ball.rs:85-106) as the
+ * query.  `queries` holds n records of 6 T {min,max}, 3 T {point} or 4 T {center, radius}.  Output: CSR as for rays. */
+typedef enum { BVHGPU_QUERY_AABB = 1, BVHGPU_QUERY_POINT = 2, BVHGPU_QUERY_BALL = 3 } bvhgpu_query_kind;
+int bvhgpu_query_f32x3(bvhgpu_tree3f* tree, int mode, int kind, const float* queries, size_t n,
+                       uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_query_f64x3(bvhgpu_tree3d* tree, int mode, int kind, const double* queries, size_t n,
+                       uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_query_dev_f32x3(bvhgpu_tree3f* tree, int mode, int kind, const void* dev_queries, size_t n,
+                           void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+int bvhgpu_query_dev_f64x3(bvhgpu_tree3d* tree, int mode, int kind, const void* dev_queries, size_t n,
+                           void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+
 /* Ray::new for a batch (src/ray/ray_impl.rs:70-80): normalise, inv = 1/direction. Device pointers. */
 int bvhgpu_rays_new_dev_f32x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);
 int bvhgpu_rays_new_dev_f64x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);

@@ -149,6 +149,33 @@ template <class T> inline bool ray_intersects_aabb(const Ray3<T>& ray, const Aab
     return tmax >= fast_max(tmin, T(0));
 }
 
+// Other IntersectsAabb implementors (src/aabb/intersection.rs:35-45, src/ball.rs:85-106).
+// Query records: kind 1 = Aabb {min,max} (6 T), kind 2 = Point (3 T), kind 3 = Ball {center, radius} (4 T).
+template <class T> inline bool aabb_intersects_aabb(const Aabb3<T>& q, const Aabb3<T>& b) {          // aabb_impl.rs:240-248
+    for (int i = 0; i < 3; ++i) if (q.max[i] < b.min[i] || b.max[i] < q.min[i]) return false;
+    return true;
+}
+template <class T> inline bool aabb_contains_point(const Aabb3<T>& b, const T p[3]) {                  // aabb_impl.rs:175-177 ([3p] nalgebra: all components)
+    for (int i = 0; i < 3; ++i) if (!(p[i] >= b.min[i])) return false;
+    for (int i = 0; i < 3; ++i) if (!(p[i] <= b.max[i])) return false;
+    return true;
+}
+template <class T> inline bool ball_intersects_aabb(const T c[3], T radius, const Aabb3<T>& b) {      // ball.rs:85-99
+    T d2 = T(0);
+    for (int i = 0; i < 3; ++i) {
+        T x = c[i];                                    // f32::clamp: if x < min {min} ; if x > max {max}
+        if (x < b.min[i]) x = b.min[i];
+        if (x > b.max[i]) x = b.max[i];
+        const T d = x - c[i];
+        d2 = d2 + d * d;                               // powi(2)
+    }
+    return d2 <= radius * radius;
+}
+template <class T> inline bool query_intersects(int kind, const T* q, const Aabb3<T>& b) {
+    if (kind == 1) return aabb_intersects_aabb(*reinterpret_cast<const Aabb3<T>*>(q), b);
+    if (kind == 2) return aabb_contains_point(b, q);
+    return ball_intersects_aabb(q, q[3], b);
+}
 // ----------------------------------------------------------------------------
 // L2a build.
 // ----------------------------------------------------------------------------
@@ -441,6 +468,35 @@ inline void traverse_recursive(const Node<T>* nodes, uint32_t n_nodes, const Aab
         const bool hr = ray_intersects_aabb(ray, nd.r_aabb);
         if (hr) push(nd.child_r);       // popped after the whole left subtree
         if (hl) push(nd.child_l);
+    }
+}
+
+// Bvh::traverse / FlatBvh::traverse for the non-ray queries (kind 1..3, see query_intersects).
+template <class T>
+inline void traverse_query(int kind, const T* q, const Node<T>* nodes, uint32_t n_nodes, const FlatNode<T>* flat, uint32_t n_flat,
+                           const Aabb3<T>* shapes, bool use_flat, std::vector<uint32_t>& out) {
+    if (use_flat) {                                             // src/flat_bvh.rs:396-431
+        uint32_t index = 0;
+        while (index < n_flat) {
+            const FlatNode<T>& node = flat[index];
+            if (node.entry_index == U32_MAX) {
+                if (query_intersects(kind, q, shapes[node.shape_index])) out.push_back(node.shape_index);
+                index = node.exit_index;
+            } else index = query_intersects(kind, q, node.aabb) ? node.entry_index : node.exit_index;
+        }
+        return;
+    }
+    if (n_nodes == 0) return;
+    if (nodes[0].is_leaf()) { if (query_intersects(kind, q, shapes[nodes[0].shape])) out.push_back(nodes[0].shape); return; }
+    std::vector<uint32_t> stack{0};
+    while (!stack.empty()) {
+        const uint32_t i = stack.back();
+        stack.pop_back();
+        const Node<T>& nd = nodes[i];
+        if (nd.is_leaf()) { out.push_back(nd.shape); continue; }
+        const bool hl = query_intersects(kind, q, nd.l_aabb), hr = query_intersects(kind, q, nd.r_aabb);
+        if (hr) stack.push_back(nd.child_r);
+        if (hl) stack.push_back(nd.child_l);
     }
 }
 

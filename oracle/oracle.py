@@ -68,6 +68,8 @@ def lib():
         _lib.orc_traverse_batch_f32.restype = C.c_uint64
         _lib.orc_traverse_batch_f64.restype = C.c_uint64
         _lib.orc_splitmix64.restype = C.c_uint64
+        _lib.orc_query_batch_f32.restype = C.c_uint64
+        _lib.orc_query_batch_f64.restype = C.c_uint64
         _lib.orc_last_build_ns.restype = C.c_uint64
         _lib.orc_hardware_threads.restype = C.c_uint32
         _lib.orc_sizeof.restype = C.c_uint32
@@ -160,6 +162,29 @@ def traverse(tree: np.ndarray, shapes: np.ndarray, rays: np.ndarray, mode: int =
             break
         cap = int(total)
     return TraverseResult(offsets, hits[:total].copy(), int(stats[0]), int(stats[1]), int(stats[2]), bool(ovf.value), int(stats[4]) * 1e-9)
+
+
+QUERY_AABB, QUERY_POINT, QUERY_BALL = 1, 2, 3
+_QSTRIDE = {1: 6, 2: 3, 3: 4}
+
+
+def query(kind: int, queries, nodes, shapes, flat=None, prec="f32"):
+    """Bvh::traverse (flat=None) / FlatBvh::traverse for Aabb / Point / Ball queries (src/aabb/intersection.rs:35-45,
+    src/ball.rs:85-106).  queries: (n, 6) aabb min+max | (n, 3) points | (n, 4) centre+radius.  Returns (offsets u64, hits u32)."""
+    d = _DT[prec]
+    q = np.ascontiguousarray(queries, dtype=d["f"]).reshape(-1, _QSTRIDE[kind])
+    nodes = np.ascontiguousarray(nodes, dtype=d["node"])
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    fl = np.ascontiguousarray(flat, dtype=d["flat"]) if flat is not None else np.zeros(0, dtype=d["flat"])
+    offsets = np.zeros(len(q) + 1, dtype=np.uint64)
+    cap = max(64 * len(q), 1024)
+    while True:
+        hits = np.empty(cap, dtype=np.uint32)
+        total = getattr(lib(), f"orc_query_batch_{prec}")(C.c_int(kind), C.c_int(1 if flat is not None else 0), _p(nodes), C.c_uint32(len(nodes)),
+                                                         _p(fl), C.c_uint32(len(fl)), _p(shapes), _p(q), C.c_uint64(len(q)), _p(offsets), _p(hits), C.c_uint64(cap))
+        if total <= cap:
+            return offsets, hits[:total].copy()
+        cap = int(total)
 
 
 def is_consistent(nodes, shapes, prec="f32") -> bool:

@@ -108,6 +108,21 @@ static uint64_t g_last_build_ns = 0;
                                               int* iter_overflow) {                                          \
         return traverse_batch<T>(mode, tree, n_tree, shapes, rays, nrays, offsets, hits, cap, stats5, threads, iter_overflow); \
     }                                                                                                        \
+    ORC_API uint64_t orc_query_batch_##SUF(int kind, int use_flat, const Node<T>* nodes, uint32_t n_nodes, const FlatNode<T>* flat, \
+                                           uint32_t n_flat, const Aabb3<T>* shapes, const T* queries, uint64_t nq, uint64_t* offsets, \
+                                           uint32_t* hits, uint64_t cap) {                                    \
+        const int stride = kind == 1 ? 6 : (kind == 2 ? 3 : 4);                                              \
+        std::vector<uint32_t> out;                                                                           \
+        uint64_t total = 0;                                                                                  \
+        for (uint64_t i = 0; i < nq; ++i) {                                                                  \
+            out.clear();                                                                                     \
+            traverse_query<T>(kind, queries + i * stride, nodes, n_nodes, flat, n_flat, shapes, use_flat != 0, out); \
+            offsets[i] = total;                                                                              \
+            for (uint32_t h : out) { if (total < cap) hits[total] = h; ++total; }                            \
+        }                                                                                                    \
+        offsets[nq] = total;                                                                                 \
+        return total;                                                                                        \
+    }                                                                                                        \
     ORC_API int orc_is_consistent_##SUF(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes) {    \
         return is_consistent(nodes, n_nodes, shapes) ? 1 : 0;                                                \
     }                                                                                                        \

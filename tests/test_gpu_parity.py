@@ -413,3 +413,44 @@ def test_lbvh_sah_cost_ratio_config2(api):
     assert np.array_equal(a[0], b[0])                    # same hit counts per ray
     for x, y in zip(O.per_ray_lists(a[0], a[1])[:5000], O.per_ray_lists(b[0], b[1])[:5000]):
         assert sorted(x.tolist()) == sorted(y.tolist())
+
+
+# ---- Aabb / Point / Ball queries (the other IntersectsAabb implementors) ------------------------------
+def test_query_kats_from_the_reference(api):
+    """testbase.rs:227-266: point (0,0,0) -> {0}; point (0,1000,0) -> {}; aabb [5.1,-1,-1]..[9.9,1,1] -> {5..10};
+    sphere c=(5,-1,-1) r=1.4 -> {4,5,6}; through Bvh and FlatBvh semantics."""
+    from bvh_b200 import capi
+
+    boxes = O.aligned_boxes()
+    bvh = api.Bvh.build(boxes)
+    cases = [(capi.QUERY_POINT, [[0, 0, 0]], {0}), (capi.QUERY_POINT, [[0, 1000, 0]], set()),
+             (capi.QUERY_AABB, [[5.1, -1, -1, 9.9, 1, 1]], set(range(5, 11))), (capi.QUERY_BALL, [[5, -1, -1, 1.4]], {4, 5, 6})]
+    for kind, q, want in cases:
+        for mode in (capi.TRAVERSE_BVH, capi.TRAVERSE_FLAT):
+            _, hits = bvh.query_batch(kind, q, mode)
+            assert sorted(int(h) - 10 for h in hits) == sorted(want)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["boxes21", "cubes500", "random3000", "points500", "huge300"])
+def test_query_parity(api, name, prec):
+    from bvh_b200 import capi
+
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    flat = O.flatten(want.nodes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    rng = np.random.default_rng(12)
+    lo, hi = shapes["min"].min(axis=0).astype(float), shapes["max"].max(axis=0).astype(float)
+    ext = hi - lo + 1e-3
+    n = 3000
+    pts = rng.uniform(lo - 0.05 * ext, hi + 0.05 * ext, (n, 3))
+    pts[:200] = shapes["min"][rng.integers(0, len(shapes), 200)]          # exactly on box corners: >= / <= edge cases
+    amin = rng.uniform(lo, hi, (n, 3))
+    aab = np.concatenate([amin, amin + rng.uniform(0, 0.2, (n, 3)) * ext], axis=1)
+    balls = np.concatenate([rng.uniform(lo, hi, (n, 3)), (rng.uniform(0, 0.15, (n, 1)) * ext.max())], axis=1)
+    for kind, q in ((capi.QUERY_POINT, pts), (capi.QUERY_AABB, aab), (capi.QUERY_BALL, balls)):
+        for mode, fl in ((capi.TRAVERSE_BVH, None), (capi.TRAVERSE_FLAT, flat)):
+            off, hits = bvh.query_batch(kind, q, mode)
+            woff, whits = O.query(kind, q, want.nodes, shapes, fl, prec)
+            assert np.array_equal(off.astype(np.uint64), woff) and np.array_equal(hits, whits), (kind, mode)
