@@ -292,3 +292,23 @@ def test_closed_form_flatten(n_cubes):
         if is_leaf[i]:
             g = flat[nav + 1]
             assert g["entry_index"] == O.U32_MAX and g["exit_index"] == nav + 2 and g["shape_index"] == nodes[i]["shape"]
+
+
+# ---- the non-ray queries of traverse_some_built_bh (testbase.rs:227-266) ---------------------------------------------
+@pytest.mark.parametrize("use_flat", [False, True])
+def test_aligned_boxes_point_aabb_sphere_queries(use_flat):
+    boxes = O.aligned_boxes()
+    res = O.build(boxes)
+    flat = O.flatten(res.nodes) if use_flat else None
+    cases = [(O.QUERY_POINT, [[0, 0, 0]], {0}), (O.QUERY_POINT, [[0, 1000, 0]], set()),
+             (O.QUERY_AABB, [[5.1, -1, -1, 9.9, 1, 1]], set(range(5, 11))), (O.QUERY_BALL, [[5, -1, -1, 1.4]], {4, 5, 6})]
+    for kind, q, want in cases:
+        _, hits = O.query(kind, q, res.nodes, boxes, flat)
+        assert sorted(int(h) - 10 for h in hits) == sorted(want)
+
+
+def test_ball_doctest():                                # src/ball.rs:74-84
+    box = O.make_aabbs([[1.25, 1.25, 1.25]], [[3.0, 3.0, 3.0]])
+    res = O.build(box)
+    _, hits = O.query(O.QUERY_BALL, [[1.0, 1.0, 1.0, 1.0]], res.nodes, box)
+    assert hits.tolist() == [0]
