@@ -127,7 +127,7 @@ __device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T
                                           bool degenerate, uint32_t half, bool store_bkt, uint32_t& last_id, int& last_b) {
     const uint32_t lane = lane_id();
     const T K = sub_rn(T(6), T(0.01));                 // T::from(NUM_BUCKETS) - T::from(0.01), bvh_node.rs:214-215
-    constexpr int U = 4;                               // chunks in flight: index loads, then AABB gathers, then the math
+    constexpr int U = sizeof(T) == 8 ? 2 : 4;          // chunks in flight: index loads, then AABB gathers, then the math
     for (uint32_t base = p0; base < p1; base += 32 * U) {
         uint32_t id[U];
         T mn[U][3], mx[U][3];
@@ -547,7 +547,7 @@ __device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws
 
 // ---- the persistent kernel -------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) build_kernel(BuildParams<T> P) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParams<T> P) {
     __shared__ WarpScratch<T> wsall[WARPS_PER_CTA];
     WarpScratch<T>* ws = &wsall[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
