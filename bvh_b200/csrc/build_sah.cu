@@ -360,9 +360,7 @@ template <class T> __device__ __forceinline__ void create_big(const BuildParams<
     if (lane == 6) __stcg(&B->tiles, tiles);
     if (lane == 7) __stcg(&B->bin_done, 0u);
     if (lane == 8) __stcg(&B->scat_done, 0u);
-    __threadfence();
-    __syncwarp();
-    __threadfence();
+    __syncwarp();            // push_tiles fences (every lane) before it publishes: the stores above are covered
     push_tiles(P, KIND_BIN, t.start / TILE, tiles, t);
 }
 
@@ -512,9 +510,7 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, co
             }
         }
     }
-    __threadfence();
-    __syncwarp();
-    __threadfence();
+    __syncwarp();            // ordered by the fence inside push_tiles
     push_tiles(P, KIND_SCATTER, sid, tiles, t);
 }
 
@@ -588,7 +584,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParam
         else process_scatter_tile(P, ws, s.t, s.a, s.b, leaves);
         if (P.trace && lane == 0 && ticket < P.trace_cap) {
             const unsigned long long base = *(volatile unsigned long long*)&P.ctl->t_start;
-            P.trace[ticket] = make_uint4((s.kind << 28) | (s.kind == KIND_SEG ? s.t.count : s.b), s.kind == KIND_SEG ? s.t.node : s.a,
+            P.trace[ticket] = make_uint4((s.kind << 28) | (s.kind == KIND_SEG ? s.t.count : s.b), s.kind == KIND_SEG ? s.t.node : s.t.count,
                                          (uint32_t)(tr0 - base), (uint32_t)(global_timer_ns() - base));
         }
         if (leaves) {

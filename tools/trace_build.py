@@ -20,16 +20,17 @@ for k, name in enumerate(["SEG", "BIN", "SCATTER"]):
     if m.any():
         d = t1[m] - t0[m]
         print(f"{name:8s} n={m.sum():7d} dur mean {d.mean():7.2f} med {np.median(d):7.2f} max {d.max():7.2f} us | first start {t0[m].min():7.1f} last end {t1[m].max():7.1f}")
-# big-segment phases: group BIN tasks by sid
-print("big segments (sid, tiles, BIN start..end, SCATTER start..end):")
-bins = {}
-for k, s, a, b_ in zip(kind, t[:, 1], t0, t1):
+# big segments, keyed by their shape count (one generation each): BIN / SCATTER phase windows
+segs = {}
+for k, c, a, b_ in zip(kind, t[:, 1], t0, t1):
     if k in (1, 2):
-        e = bins.setdefault((int(s), int(k)), [a, b_, 0]); e[0] = min(e[0], a); e[1] = max(e[1], b_); e[2] += 1
-rows = sorted(set(s for s, _ in bins), key=lambda s: bins.get((s, 1), [1e9])[0])
-for s in rows[:40]:
-    bi, sc = bins.get((s, 1)), bins.get((s, 2))
-    print(f"  sid {s:6d} tiles {bi[2] if bi else 0:5d}  BIN {bi[0]:7.1f}..{bi[1]:7.1f}" + (f"  SCAT {sc[0]:7.1f}..{sc[1]:7.1f}" if sc else "  (degenerate)"))
+        e = segs.setdefault((int(c), int(k)), [a, b_, 0, 0.0]); e[0] = min(e[0], a); e[1] = max(e[1], b_); e[2] += 1; e[3] = max(e[3], b_ - a)
+print("count   tiles  BIN first-start .. last-end (longest tile) | SCATTER first-start .. last-end (longest)")
+for c in sorted(set(c for c, _ in segs), reverse=True)[:28]:
+    bi, sc = segs.get((c, 1)), segs.get((c, 2))
+    line = f"{c:7d} {bi[2]:5d}  BIN {bi[0]:7.1f} .. {bi[1]:7.1f} ({bi[3]:5.1f})"
+    if sc: line += f" | SCAT {sc[0]:7.1f} .. {sc[1]:7.1f} ({sc[3]:5.1f})"
+    print(line)
 m = kind == 0
 print("SEG tasks by size: ", end="")
 for lo, hi in [(2, 8), (8, 32), (32, 64), (64, 128), (128, 257)]:
@@ -37,6 +38,3 @@ for lo, hi in [(2, 8), (8, 32), (32, 64), (64, 128), (128, 257)]:
     if mm.any():
         print(f"[{lo},{hi}) n={mm.sum()} dur {np.mean(t1[mm]-t0[mm]):.1f}us  ", end="")
 print()
-edges = np.arange(0, t1.max() + 50, 50)
-act = [(int(((t0 < e + 50) & (t1 > e)).sum())) for e in edges]
-print("active tasks per 50us window:", act)
