@@ -454,3 +454,59 @@ def test_query_parity(api, name, prec):
             off, hits = bvh.query_batch(kind, q, mode)
             woff, whits = O.query(kind, q, want.nodes, shapes, fl, prec)
             assert np.array_equal(off.astype(np.uint64), woff) and np.array_equal(hits, whits), (kind, mode)
+
+
+# ---- randomized sweep (in the spirit of the reference's fuzz target, fuzz/fuzz_targets/fuzz.rs) ----------------------
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scene_sweep(api, seed):
+    """Random size (1..6000), random distribution family, random precision: build + flatten + traverse + point query parity."""
+    from bvh_b200 import capi
+
+    rng = np.random.default_rng(1000 + seed)
+    prec = "f32" if seed % 3 else "f64"
+    n = int(rng.choice([1, 2, 3, 5, 31, 32, 33, 64, 255, 256, 257, 511, 513, int(rng.integers(600, 6000))]))
+    fam = seed % 4
+    if fam == 0:        # uniform boxes
+        mn = rng.uniform(-100, 100, (n, 3)); size = rng.uniform(0, 5, (n, 3))
+    elif fam == 1:      # integer grid with many exact ties (Grid mode of the fuzzer: coordinates in thirds)
+        mn = rng.integers(-12, 12, (n, 3)).astype(float) / 3.0; size = rng.integers(0, 3, (n, 3)).astype(float) / 3.0
+    elif fam == 2:      # clustered, wildly different scales
+        c = rng.uniform(-1e4, 1e4, (max(n // 50, 1), 3)); mn = c[rng.integers(0, len(c), n)] + rng.normal(0, 1, (n, 3)) * 10.0 ** rng.uniform(-3, 2, (n, 1)); size = 10.0 ** rng.uniform(-4, 1, (n, 3))
+    else:               # flat sheet: one axis degenerate
+        mn = rng.uniform(-50, 50, (n, 3)); mn[:, int(rng.integers(0, 3))] = 7.0; size = rng.uniform(0, 2, (n, 3)); size[:, 1] = 0.0
+    shapes = O.make_aabbs(mn, mn + size, prec)
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    assert _nodes_equal(bvh.nodes, want.nodes), (seed, n, fam, prec)
+    assert np.array_equal(bvh.node_index, want.node_index)
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes, prec))
+    rays = rays_for(shapes, 1500, prec, seed=seed, axis_aligned=150)
+    r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, prec)
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits), (seed, n, fam, prec)
+    pts = rng.uniform(mn.min(axis=0), (mn + size).max(axis=0), (500, 3))
+    o2, h2 = bvh.query_batch(capi.QUERY_POINT, pts)
+    wo, wh = O.query(O.QUERY_POINT, pts, want.nodes, shapes, None, prec)
+    assert np.array_equal(o2.astype(np.uint64), wo) and np.array_equal(h2, wh)
+    bvh.free()
+
+
+def test_capacity_error_and_fetch(api):
+    """Caller buffer too small: BVHGPU_ERR_CAPACITY with the needed size, and bvhgpu_traverse_fetch_* returns the retained result."""
+    import ctypes as C
+
+    from bvh_b200 import capi
+    from tests.scenes import sponza
+
+    shapes = sponza()
+    bvh = api.Bvh.build(shapes)
+    o, d = np.tile([[-15.0, 2.0, 0.0]], (64, 1)), np.tile([[1.0, 0.05, 0.02]], (64, 1))
+    rays = api.Ray.new(o, d)
+    off = np.zeros(65, dtype=np.uint32); small = np.zeros(8, dtype=np.uint32); tot = C.c_size_t(0)
+    L = capi.lib()
+    st = L.bvhgpu_traverse_f32x3(bvh._h, 0, rays.ctypes.data_as(C.c_void_p), 64, off.ctypes.data_as(C.c_void_p), small.ctypes.data_as(C.c_void_p), 8, C.byref(tot))
+    assert st == capi.ERR_CAPACITY and tot.value > 8 and off[-1] == tot.value
+    full = np.zeros(tot.value, dtype=np.uint32)
+    capi.check(L.bvhgpu_traverse_fetch_f32x3(bvh._h, full.ctypes.data_as(C.c_void_p), tot.value))
+    off2, hits2 = bvh.traverse_batch(rays)
+    assert np.array_equal(off2, off) and np.array_equal(hits2, full)
