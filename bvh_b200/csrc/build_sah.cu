@@ -61,8 +61,10 @@ template <class T> struct __align__(16) WarpScratch {
 struct BuildCtl {
     uint32_t head, tail, leaves_done, error;
     unsigned long long t_start;
-    uint32_t pad[2];
+    uint32_t small_count;            // ranges of <= SMALL shapes deferred to small_subtrees_kernel
+    uint32_t pad;
 };
+constexpr uint32_t SMALL = 16;       // ranges this small are finished by ONE THREAD each in a second kernel
 
 template <class T> struct BuildParams {
     using Tr = Traits<T>;
@@ -82,6 +84,7 @@ template <class T> struct BuildParams {
     BuildStatus* status;
     uint32_t n;
     unsigned long long timeout_ns;
+    BTask<T>* small;                // deferred small ranges (capacity n/2 + 1)
     uint4* trace;                   // optional task log (BVHGPU_TRACE=file): {kind<<28|count, node/sid, t0_ns, t1_ns}
     uint32_t trace_cap;
 };
@@ -308,6 +311,17 @@ __device__ __forceinline__ int finish_node(const BuildParams<T>& P, WarpScratch<
         if (ccount == 1) {
             if (lane_id() == 0) write_leaf(P, cnode, t.node, __ldcg(P.idx[nbuf] + cstart), cstart);
             leaves += 1;
+        } else if (ccount <= SMALL) {
+            // The bottom of the tree holds most of the nodes, and a whole warp per 2..16-shape node wastes it: hand the
+            // range to small_subtrees_kernel, where one thread replays the reference recursion for it.
+            if (lane_id() == 0) {
+                BTask<T> c;
+                c.start = cstart; c.count = ccount; c.node = cnode; c.parent_buf = t.node | (nbuf << 31);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { c.ab[k] = ws->child[side * 12 + k]; c.cb[k] = ws->child[side * 12 + 6 + k]; }
+                store_struct_cg(P.small + atomicAdd(&P.ctl->small_count, 1u), c);
+            }
+            leaves += ccount;                 // accounted for here; the second kernel writes them
         } else {
             BTask<T>& c = out[nc++];
             c.start = cstart; c.count = ccount; c.node = cnode; c.parent_buf = t.node | (nbuf << 31);
@@ -595,6 +609,135 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParam
     }
 }
 
+// ---- small_subtrees_kernel: one THREAD per deferred range of <= SMALL shapes ---------------------------------------
+// A literal, sequential replay of BvhNode::prep_build / build_buckets (bvh_node.rs:81-279) on thread-private data:
+// the shapes of the range live in local arrays, the recursion is an explicit stack.  32 ranges per warp run
+// concurrently, which is ~25x cheaper in issue slots than a warp per node for the 2..16-shape nodes that make up
+// most of a tree.
+template <class T>
+__global__ void __launch_bounds__(128) small_subtrees_kernel(BuildParams<T> P) {
+    using Tr = Traits<T>;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= P.ctl->small_count) return;
+    BTask<T> t;
+    load_struct_cg(t, P.small + tid);
+    const uint32_t buf = t.parent_buf >> 31;
+    uint32_t id[SMALL];
+    T mn[SMALL][3], mx[SMALL][3], ct[SMALL][3];
+    for (uint32_t i = 0; i < t.count; ++i) {
+        id[i] = __ldcg(P.idx[buf] + t.start + i);
+        load_aabb(P.aabb + id[i], mn[i], mx[i]);
+        for (int k = 0; k < 3; ++k) ct[i][k] = center1(mn[i][k], mx[i][k]);
+    }
+    struct Frame { uint32_t s, c, node, parent; T ab[6], cb[6]; };
+    Frame stack[SMALL];
+    int sp = 0;
+    {
+        Frame& f = stack[sp++];
+        f.s = 0; f.c = t.count; f.node = t.node; f.parent = t.parent_buf & 0x7FFFFFFFu;
+        for (int k = 0; k < 6; ++k) { f.ab[k] = t.ab[k]; f.cb[k] = t.cb[k]; }
+    }
+    const T INF = Tr::inf();
+    const T K6 = sub_rn(T(6), T(0.01));
+    while (sp > 0) {
+        const Frame f = stack[--sp];
+        // split axis (aabb_impl.rs:594-596) and extent (bvh_node.rs:107-108)
+        int axis = 0;
+        T ext = sub_rn(f.cb[3], f.cb[0]);
+        { const T sy = sub_rn(f.cb[4], f.cb[1]), sz = sub_rn(f.cb[5], f.cb[2]);
+          if (sy > ext) { axis = 1; ext = sy; }
+          if (sz > ext) { axis = 2; ext = sz; } }
+        const T cbmin = f.cb[axis];
+        T L[12], R[12];                                   // chosen children: aabb min3 max3, centroid min3 max3
+        for (int k = 0; k < 12; ++k) { const bool isMin = (k % 6) < 3; L[k] = R[k] = isMin ? INF : -INF; }
+        uint32_t nl;
+        if (ext < Tr::eps()) {                            // bvh_node.rs:114-124: halve by position
+            nl = f.c / 2;
+            for (uint32_t i = 0; i < f.c; ++i) {
+                T* D = i < nl ? L : R;
+                const uint32_t j = f.s + i;
+                for (int k = 0; k < 3; ++k) {
+                    D[k] = mn[j][k] < D[k] ? mn[j][k] : D[k];         D[3 + k] = mx[j][k] > D[3 + k] ? mx[j][k] : D[3 + k];
+                    D[6 + k] = ct[j][k] < D[6 + k] ? ct[j][k] : D[6 + k]; D[9 + k] = ct[j][k] > D[9 + k] ? ct[j][k] : D[9 + k];
+                }
+            }
+        } else {                                          // build_buckets, bvh_node.rs:183-279
+            T bk[6][12];
+            uint32_t bn[6];
+            uint8_t bid[SMALL];
+            for (int b = 0; b < 6; ++b) { bn[b] = 0; for (int k = 0; k < 12; ++k) bk[b][k] = ((k % 6) < 3) ? INF : -INF; }
+            for (uint32_t i = 0; i < f.c; ++i) {
+                const uint32_t j = f.s + i;
+                int b = (int)mul_rn(div_rn(sub_rn(ct[j][axis], cbmin), ext), K6);
+                b = b < 0 ? 0 : (b > 5 ? 5 : b);
+                bid[i] = (uint8_t)b;
+                bn[b]++;
+                for (int k = 0; k < 3; ++k) {
+                    bk[b][k] = mn[j][k] < bk[b][k] ? mn[j][k] : bk[b][k];         bk[b][3 + k] = mx[j][k] > bk[b][3 + k] ? mx[j][k] : bk[b][3 + k];
+                    bk[b][6 + k] = ct[j][k] < bk[b][6 + k] ? ct[j][k] : bk[b][6 + k]; bk[b][9 + k] = ct[j][k] > bk[b][9 + k] ? ct[j][k] : bk[b][9 + k];
+                }
+            }
+            const T sap = surface_area(f.ab, f.ab + 3);
+            int best = 0;
+            bool found = false;
+            T min_cost = INF;
+            for (int s = 0; s < 5; ++s) {                 // bvh_node.rs:231-247
+                T l[12], r[12];
+                uint32_t cl = 0, cr = 0;
+                for (int k = 0; k < 12; ++k) { const bool isMin = (k % 6) < 3; l[k] = r[k] = isMin ? INF : -INF; }
+                for (int b = 0; b < 6; ++b) {
+                    T* D = b <= s ? l : r;
+                    if (b <= s) cl += bn[b]; else cr += bn[b];
+                    for (int k = 0; k < 12; ++k) { const bool isMin = (k % 6) < 3; D[k] = isMin ? (bk[b][k] < D[k] ? bk[b][k] : D[k]) : (bk[b][k] > D[k] ? bk[b][k] : D[k]); }
+                }
+                const T cost = div_rn(add_rn(mul_rn((T)cl, surface_area(l, l + 3)), mul_rn((T)cr, surface_area(r, r + 3))), sap);
+                if (cost < min_cost) {
+                    best = s; min_cost = cost; found = true;
+                    for (int k = 0; k < 12; ++k) { L[k] = l[k]; R[k] = r[k]; }
+                }
+            }
+            (void)found;                                   // not found: L / R stay Aabb::empty(), best = 0 (bvh_node.rs:225-230)
+            // stable 6-way partition of the range (bvh_node.rs:250-272)
+            uint32_t tid2[SMALL];
+            T tmn[SMALL][3], tmx[SMALL][3], tct[SMALL][3];
+            uint32_t w = 0;
+            nl = 0;
+            for (int b = 0; b < 6; ++b) {
+                if (b <= best) nl += bn[b];
+                for (uint32_t i = 0; i < f.c; ++i) {
+                    if (bid[i] != b) continue;
+                    const uint32_t j = f.s + i;
+                    tid2[w] = id[j];
+                    for (int k = 0; k < 3; ++k) { tmn[w][k] = mn[j][k]; tmx[w][k] = mx[j][k]; tct[w][k] = ct[j][k]; }
+                    ++w;
+                }
+            }
+            for (uint32_t i = 0; i < f.c; ++i) {
+                const uint32_t j = f.s + i;
+                id[j] = tid2[i];
+                for (int k = 0; k < 3; ++k) { mn[j][k] = tmn[i][k]; mx[j][k] = tmx[i][k]; ct[j][k] = tct[i][k]; }
+            }
+        }
+        const uint32_t cl = f.node + 1, cr = f.node + 2 * nl;
+        {
+            typename Tr::Node nd;
+            nd.parent = f.parent; nd.child_l = cl; nd.child_r = cr; nd.shape = f.c;
+            for (int k = 0; k < 3; ++k) { nd.l_aabb.min[k] = L[k]; nd.l_aabb.max[k] = L[3 + k]; nd.r_aabb.min[k] = R[k]; nd.r_aabb.max[k] = R[3 + k]; }
+            store_struct_cg(P.nodes + f.node, nd);
+            P.node_start[f.node] = t.start + f.s;
+        }
+        // children: right first onto the stack so that the left is processed next (order is irrelevant for the result)
+        for (int side = 1; side >= 0; --side) {
+            const uint32_t cs = side ? f.s + nl : f.s, cc = side ? f.c - nl : nl, cn = side ? cr : cl;
+            if (cc == 1) { write_leaf(P, cn, f.node, id[cs], t.start + cs); continue; }
+            Frame& g = stack[sp++];
+            g.s = cs; g.c = cc; g.node = cn; g.parent = f.node;
+            const T* S = side ? R : L;
+            for (int k = 0; k < 6; ++k) { g.ab[k] = S[k]; g.cb[k] = S[6 + k]; }
+        }
+    }
+}
+
 // ---- prep: ABI layout -> device layout, NaN check, scene bounds (joint_aabb_of_shapes, utils.rs:97-109) ---
 template <class T>
 __global__ void __launch_bounds__(256) prep_kernel(const typename Traits<T>::Aabb* __restrict__ in, uint32_t n,
@@ -651,6 +794,7 @@ __global__ void init_keys_kernel(typename Traits<T>::Key* rootkeys, BuildCtl* ct
     if (threadIdx.x < 12) rootkeys[threadIdx.x] = key_is_min<T>(threadIdx.x) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
     if (threadIdx.x == 0) {
         ctl->head = ctl->tail = ctl->leaves_done = ctl->error = 0;
+        ctl->small_count = 0;
         ctl->t_start = 0;
         status->error = status->nan_found = status->tickets = status->leaves_done = 0;
     }
@@ -753,6 +897,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 8));
     BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
     BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
+    BVH_TRY(dalloc_t(ctx, &P.small, (size_t)n / 2 + 1));
     P.idx[0] = idx0;
     P.idx[1] = idx1;
     const char* trace_path = getenv("BVHGPU_TRACE");
@@ -784,6 +929,9 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
         build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
         ctx->launches++;
+        const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
+        small_subtrees_kernel<T><<<sgrid, 128, 0, st>>>(P);
+        ctx->launches++;
         if (ctx->profile) { cudaEventRecord(ctx->ev_build[1], st); ctx->have_build = true; }
     }
     finish_status_kernel<T><<<1, 32, 0, st>>>(P.ctl, P.status, n);
@@ -797,7 +945,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         dfree(ctx, P.trace);
     }
     dfree(ctx, idx0); dfree(ctx, idx1); dfree(ctx, P.bkt); dfree(ctx, P.q); dfree(ctx, P.qseq);
-    dfree(ctx, P.big); dfree(ctx, P.tilecnt); dfree(ctx, P.ctl); dfree(ctx, P.rootkeys);
+    dfree(ctx, P.big); dfree(ctx, P.tilecnt); dfree(ctx, P.ctl); dfree(ctx, P.rootkeys); dfree(ctx, P.small);
     tree->status_pending = true;
     return BVHGPU_OK;
 }
