@@ -85,6 +85,7 @@ template <class T> struct BuildParams {
     uint32_t n;
     unsigned long long timeout_ns;
     BTask<T>* small;                // deferred small ranges (capacity n/2 + 1)
+    uint32_t small_max;             // ranges up to this many shapes are deferred (0 = none): pays off in the throughput regime only
     uint4* trace;                   // optional task log (BVHGPU_TRACE=file): {kind<<28|count, node/sid, t0_ns, t1_ns}
     uint32_t trace_cap;
 };
@@ -311,7 +312,7 @@ __device__ __forceinline__ int finish_node(const BuildParams<T>& P, WarpScratch<
         if (ccount == 1) {
             if (lane_id() == 0) write_leaf(P, cnode, t.node, __ldcg(P.idx[nbuf] + cstart), cstart);
             leaves += 1;
-        } else if (ccount <= SMALL) {
+        } else if (ccount <= P.small_max) {
             // The bottom of the tree holds most of the nodes, and a whole warp per 2..16-shape node wastes it: hand the
             // range to small_subtrees_kernel, where one thread replays the reference recursion for it.
             if (lane_id() == 0) {
@@ -897,7 +898,11 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 8));
     BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
     BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
-    BVH_TRY(dalloc_t(ctx, &P.small, (size_t)n / 2 + 1));
+    // Deferring the bottom of the tree to the thread-per-range kernel adds that kernel's own latency (~0.1-0.4 ms tail) but
+    // removes most warp-per-node work: measured slower below ~0.5 M shapes (120 k: 0.62 -> 0.67 ms), faster above
+    // (1.2 M f32: 3.33 -> 2.32 ms, 10 M f64: 48 -> 28 ms).
+    P.small_max = n >= 400000u ? SMALL : 0u;
+    BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
     P.idx[0] = idx0;
     P.idx[1] = idx1;
     const char* trace_path = getenv("BVHGPU_TRACE");
@@ -929,9 +934,11 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
         build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
         ctx->launches++;
-        const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
-        small_subtrees_kernel<T><<<sgrid, 128, 0, st>>>(P);
-        ctx->launches++;
+        if (P.small_max) {
+            const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
+            small_subtrees_kernel<T><<<sgrid, 128, 0, st>>>(P);
+            ctx->launches++;
+        }
         if (ctx->profile) { cudaEventRecord(ctx->ev_build[1], st); ctx->have_build = true; }
     }
     finish_status_kernel<T><<<1, 32, 0, st>>>(P.ctl, P.status, n);

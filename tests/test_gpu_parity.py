@@ -254,7 +254,8 @@ def test_config2_full_size(api):
 
 
 def test_large_build_properties(api):
-    """1.2M shapes (beyond what the reference benches): GPU == oracle, plus the size-independent invariants."""
+    """1.2M shapes (beyond what the reference benches; this size also runs the thread-per-range kernel for the bottom of
+    the tree): GPU == oracle, plus the size-independent invariants."""
     shapes = O.create_n_cubes(100_000)
     bvh = api.Bvh.build(shapes)
     nodes, idx = bvh.nodes, bvh.node_index
