@@ -901,7 +901,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     // Deferring the bottom of the tree to the thread-per-range kernel adds that kernel's own latency (~0.1-0.4 ms tail) but
     // removes most warp-per-node work: measured slower below ~0.5 M shapes (120 k: 0.62 -> 0.67 ms), faster above
     // (1.2 M f32: 3.33 -> 2.32 ms, 10 M f64: 48 -> 28 ms).
-    P.small_max = n >= 400000u ? SMALL : 0u;
+    P.small_max = (ctx->build_small < 0 ? n >= 400000u : ctx->build_small != 0) ? SMALL : 0u;
     BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
     P.idx[0] = idx0;
     P.idx[1] = idx1;

@@ -97,6 +97,7 @@ int bvhgpu_synchronize(bvhgpu_ctx* ctx);
 uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
 /* Tunables: "traverse_slots" (per-ray hit slots of the single-pass path, 0 = two-pass count/fill, -1 = auto),
  * "traverse_persistent" (0 = one ray per thread, 1 = persistent refill kernel, 2 = decided per batch by a coherence probe),
+ * "build_small" (exact builder: finish ranges of <= 16 shapes with one thread each in a second kernel; -1 auto by size, 0 never, 1 always),
  * "profile" (1: bracket the dominant kernels with CUDA events, read back with bvhgpu_get_metric). */
 int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value);
 /* Measurements of the last profiled call on this context: "walk_ms" (traversal walk kernel),

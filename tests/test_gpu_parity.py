@@ -492,6 +492,24 @@ def test_random_scene_sweep(api, seed):
     bvh.free()
 
 
+@pytest.mark.parametrize("name,prec", [("cubes1000", "f32"), ("random5000", "f32"), ("points3000", "f32"), ("huge2000", "f32"), ("skew3000", "f32"),
+                                       ("random33", "f32"), ("cubes200", "f64"), ("random3000", "f64"), ("huge300", "f64")])
+def test_thread_per_range_kernel_forced(api, name, prec):
+    """The bottom-of-tree kernel (one thread per range of <= 16 shapes) is normally used from 400 k shapes up; force it on
+    small scenes, including the degenerate and the "no split wins" branches."""
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    ctx = api.Context.default()
+    ctx.set_option("build_small", 1)
+    try:
+        bvh = api.Bvh.build(shapes, prec=prec)
+        assert _nodes_equal(bvh.nodes, want.nodes), name
+        assert np.array_equal(bvh.node_index, want.node_index)
+        assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes, prec))
+    finally:
+        ctx.set_option("build_small", -1)
+
+
 def test_capacity_error_and_fetch(api):
     """Caller buffer too small: BVHGPU_ERR_CAPACITY with the needed size, and bvhgpu_traverse_fetch_* returns the retained result."""
     import ctypes as C
