@@ -11,7 +11,7 @@ SO_PATH = os.path.join(_HERE, "libbvh_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "bvh_b200.h")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_CAPACITY, ERR_TIMEOUT, ERR_UNSUPPORTED, ERR_INTERNAL = range(8)
-BUILD_EXACT_SAH, BUILD_LBVH = 0, 1
+BUILD_EXACT_SAH, BUILD_LBVH, BUILD_LBVH_TREELET = 0, 1, 2
 TRAVERSE_BVH, TRAVERSE_FLAT = 0, 1
 QUERY_AABB, QUERY_POINT, QUERY_BALL = 1, 2, 3
 

@@ -21,50 +21,12 @@
 // follow the reference rule child_l = i+1, child_r = i + 2*n_l (bvh_node.rs:138-142), so the
 // output array IS the reference's preorder `Bvh.nodes`.
 #include "internal.h"
+#include "build_types.cuh"
 #include <vector>
 #include <cstdlib>
+#include <cstring>
 
 namespace bvhb200 {
-
-constexpr int TILE = 256;              // shapes per tile task of a multi-warp segment
-constexpr int WARPS_PER_CTA = 8;
-constexpr int LOCAL_STACK = 24;        // per-warp DFS stack (entries)
-constexpr uint32_t LOCAL_MAX = 6;      // right children up to this size stay on the warp's own stack; larger ones go to
-                                       // the global queue: idle warps are plentiful, the critical path is what matters
-constexpr uint32_t KIND_SEG = 0, KIND_BIN = 1, KIND_SCATTER = 2;
-
-template <class T> struct __align__(16) BTask {
-    uint32_t start, count, node, parent_buf;   // parent_buf: bit31 = which index buffer holds the range
-    T ab[6];                                   // aabb_bounds      (min xyz, max xyz)
-    T cb[6];                                   // centroid_bounds
-};
-template <class T> struct __align__(16) QSlot {
-    BTask<T> t;
-    uint32_t kind, a, b, pad;                  // tile tasks: a = big-segment id, b = tile index
-};
-template <class T> struct __align__(16) BigSeg {
-    using Key = typename Traits<T>::Key;
-    BTask<T> t;
-    Key keys[72];                              // [bucket][12]: aabb min3, aabb max3, centroid min3, centroid max3
-    uint32_t cnt[6]; uint32_t tiles; uint32_t bin_done;
-    uint32_t scat_done; uint32_t nl; uint32_t pad0[2];
-    uint32_t base[6]; uint32_t pad1[2];
-    T child[24];                               // lab, lcb, rab, rcb of the chosen split
-};
-template <class T> struct __align__(16) WarpScratch {
-    using Key = typename Traits<T>::Key;
-    Key keys[72];
-    uint32_t cnt[8];
-    T child[24];
-    BTask<T> stack[LOCAL_STACK];
-};
-struct BuildCtl {
-    uint32_t head, tail, leaves_done, error;
-    unsigned long long t_start;
-    uint32_t small_count;            // ranges of <= SMALL shapes deferred to small_subtrees_kernel
-    uint32_t pad;
-};
-constexpr uint32_t SMALL = 16;       // ranges this small are finished by ONE THREAD each in a second kernel
 
 template <class T> struct BuildParams {
     using Tr = Traits<T>;
@@ -956,6 +918,68 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     tree->status_pending = true;
     return BVHGPU_OK;
 }
+
+// ---- treelet session: lbvh.cu pre-fills the task queue with SEG tasks (one per treelet of <= TILE shapes) and this runs
+// the same persistent kernel over them: binned-SAH re-optimisation of the bottom of an LBVH tree, staged in shared memory.
+template <class T>
+int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletSession<T>* S) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = tree->n;
+    BuildParams<T>* P = new BuildParams<T>();
+    memset(P, 0, sizeof(*P));
+    P->aabb = tree->d_aabb; P->nodes = tree->d_nodes; P->node_index = tree->d_node_index; P->node_start = tree->d_node_start;
+    P->n = n; P->status = tree->d_status; P->timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    const uint32_t qcap = next_pow2(std::max<uint64_t>(n, 1024) * 2);
+    P->qmask = qcap - 1;
+    P->idx[0] = sorted_ids;
+    BVH_TRY(dalloc_t(ctx, &P->idx[1], n));
+    BVH_TRY(dalloc_t(ctx, &P->bkt, n));
+    BVH_TRY(dalloc_t(ctx, &P->q, qcap));
+    BVH_TRY(dalloc_t(ctx, &P->qseq, qcap));
+    BVH_TRY(dalloc_t(ctx, &P->big, 2));
+    BVH_TRY(dalloc_t(ctx, &P->tilecnt, 32));
+    BVH_TRY(dalloc_t(ctx, &P->ctl, 1));
+    P->small_max = (ctx->build_small < 0 ? n >= 400000u : ctx->build_small != 0) ? SMALL : 0u;
+    BVH_TRY(dalloc_t(ctx, &P->small, P->small_max ? (size_t)n / 2 + 1 : 1));
+    BVH_CUDA_TRY(cudaMemsetAsync(P->qseq, 0, sizeof(uint32_t) * qcap, st));
+    BVH_CUDA_TRY(cudaMemsetAsync(P->ctl, 0, sizeof(BuildCtl), st));
+    S->params = P; S->q = P->q; S->qseq = P->qseq; S->qmask = P->qmask; S->ctl = P->ctl;
+    return BVHGPU_OK;
+}
+template <class T> __global__ void treelet_start_kernel(BuildCtl* ctl) { if (threadIdx.x == 0) ctl->t_start = global_timer_ns(); }
+
+template <class T>
+int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
+    cudaStream_t st = ctx->stream;
+    BuildParams<T>* P = static_cast<BuildParams<T>*>(S->params);
+    const uint32_t n = tree->n;
+    treelet_start_kernel<T><<<1, 32, 0, st>>>(P->ctl);
+    int occ = 1;
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+    if (occ < 1) occ = 1;
+    uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (want < 1) want = 1;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
+    build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(*P);
+    ctx->launches += 2;
+    if (P->small_max) {
+        const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
+        small_subtrees_kernel<T><<<sgrid, 128, 0, st>>>(*P);
+        ctx->launches++;
+    }
+    finish_status_kernel<T><<<1, 32, 0, st>>>(P->ctl, P->status, n);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    dfree(ctx, P->idx[1]); dfree(ctx, P->bkt); dfree(ctx, P->q); dfree(ctx, P->qseq); dfree(ctx, P->big); dfree(ctx, P->tilecnt);
+    dfree(ctx, P->ctl); dfree(ctx, P->small);
+    delete P;
+    S->params = nullptr;
+    return BVHGPU_OK;
+}
+template int treelet_begin<float>(bvhgpu_ctx*, Tree<float>*, uint32_t*, TreeletSession<float>*);
+template int treelet_begin<double>(bvhgpu_ctx*, Tree<double>*, uint32_t*, TreeletSession<double>*);
+template int treelet_finish<float>(bvhgpu_ctx*, Tree<float>*, TreeletSession<float>*);
+template int treelet_finish<double>(bvhgpu_ctx*, Tree<double>*, TreeletSession<double>*);
 
 template int build_exact_sah<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, Tree<float>*);
 template int build_exact_sah<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, Tree<double>*);

@@ -1,0 +1,49 @@
+// bvh_b200/csrc/build_types.cuh -- task / queue records of the persistent SAH build kernel, shared with lbvh.cu
+// (the LBVH + treelet mode pre-fills the queue with one SEG task per treelet).
+#pragma once
+#include "common.cuh"
+
+namespace bvhb200 {
+
+constexpr int TILE = 256;              // shapes per tile task of a multi-warp segment
+constexpr int WARPS_PER_CTA = 8;
+constexpr int LOCAL_STACK = 24;        // per-warp DFS stack (entries)
+constexpr uint32_t LOCAL_MAX = 6;      // right children up to this size stay on the warp's own stack; larger ones go to
+                                       // the global queue: idle warps are plentiful, the critical path is what matters
+constexpr uint32_t KIND_SEG = 0, KIND_BIN = 1, KIND_SCATTER = 2;
+
+template <class T> struct __align__(16) BTask {
+    uint32_t start, count, node, parent_buf;   // parent_buf: bit31 = which index buffer holds the range
+    T ab[6];                                   // aabb_bounds      (min xyz, max xyz)
+    T cb[6];                                   // centroid_bounds
+};
+template <class T> struct __align__(16) QSlot {
+    BTask<T> t;
+    uint32_t kind, a, b, pad;                  // tile tasks: a = big-segment id, b = tile index
+};
+template <class T> struct __align__(16) BigSeg {
+    using Key = typename Traits<T>::Key;
+    BTask<T> t;
+    Key keys[72];                              // [bucket][12]: aabb min3, aabb max3, centroid min3, centroid max3
+    uint32_t cnt[6]; uint32_t tiles; uint32_t bin_done;
+    uint32_t scat_done; uint32_t nl; uint32_t pad0[2];
+    uint32_t base[6]; uint32_t pad1[2];
+    T child[24];                               // lab, lcb, rab, rcb of the chosen split
+};
+template <class T> struct __align__(16) WarpScratch {
+    using Key = typename Traits<T>::Key;
+    Key keys[72];
+    uint32_t cnt[8];
+    T child[24];
+    BTask<T> stack[LOCAL_STACK];
+};
+struct BuildCtl {
+    uint32_t head, tail, leaves_done, error;
+    unsigned long long t_start;
+    uint32_t small_count;            // ranges of <= SMALL shapes deferred to small_subtrees_kernel
+    uint32_t pad;
+};
+constexpr uint32_t SMALL = 16;       // ranges this small are finished by ONE THREAD each in a second kernel
+
+
+}  // namespace bvhb200

@@ -60,7 +60,7 @@ static int build_impl(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* aabbs, si
     if (!ctx || !out || (n && !aabbs)) { set_error("build: null argument"); return BVHGPU_ERR_INVALID; }
     *out = nullptr;
     if (n > (1ull << 30)) { set_error("build: n = %zu exceeds 2^30 shapes (u32 node indices)", n); return BVHGPU_ERR_INVALID; }
-    if (mode != BVHGPU_BUILD_EXACT_SAH && mode != BVHGPU_BUILD_LBVH) { set_error("build: unknown mode %d", mode); return BVHGPU_ERR_INVALID; }
+    if (mode != BVHGPU_BUILD_EXACT_SAH && mode != BVHGPU_BUILD_LBVH && mode != BVHGPU_BUILD_LBVH_TREELET) { set_error("build: unknown mode %d", mode); return BVHGPU_ERR_INVALID; }
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     TreeT* tree = new (std::nothrow) TreeT();
     if (!tree) { set_error("build: out of host memory"); return BVHGPU_ERR_INTERNAL; }
@@ -76,7 +76,7 @@ static int build_impl(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* aabbs, si
         }
         d_in = staged;
     }
-    if (rc == BVHGPU_OK) rc = mode == BVHGPU_BUILD_LBVH ? build_lbvh<T>(ctx, d_in, (uint32_t)n, tree) : build_exact_sah<T>(ctx, d_in, (uint32_t)n, tree);
+    if (rc == BVHGPU_OK) rc = mode == BVHGPU_BUILD_EXACT_SAH ? build_exact_sah<T>(ctx, d_in, (uint32_t)n, tree) : build_lbvh<T>(ctx, d_in, (uint32_t)n, tree, mode == BVHGPU_BUILD_LBVH_TREELET);
     if (staged) dfree(ctx, staged);
     if (rc == BVHGPU_OK && host_input) rc = resolve_status(tree);     // host entry point reports errors eagerly
     if (rc != BVHGPU_OK) { tree_release(tree); delete tree; return rc; }

@@ -101,8 +101,15 @@ template <class T> int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>
 template <class T> int convert_aabbs(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n,
                                      typename Traits<T>::DAabb* out, uint32_t* d_nan_flag);
 
+// ---- treelet session (build_sah.cu), used by lbvh.cu for BVHGPU_BUILD_LBVH_TREELET ----
+struct BuildCtl;
+template <class T> struct QSlot;
+template <class T> struct TreeletSession { void* params = nullptr; QSlot<T>* q = nullptr; uint32_t* qseq = nullptr; uint32_t qmask = 0; BuildCtl* ctl = nullptr; };
+template <class T> int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletSession<T>* S);
+template <class T> int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S);
+
 // ---- lbvh.cu ----
-template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree);
+template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree, bool treelets);
 
 // ---- flatten.cu ----
 template <class T> int build_traversal_records(Tree<T>* tree);   // d_tnodes

@@ -9,12 +9,15 @@
 //                        by position so duplicate codes still give a strict binary tree (Karras 2012)
 //   4. path_kernel x7    pointer jumping: L(v) = number of left edges on the root path, needed for ...
 //   5. box_kernel        bottom-up subtree AABBs with arrival counters
+//   5b. (BVHGPU_BUILD_LBVH_TREELET) every subtree of <= 256 shapes is handed to the persistent SAH build kernel as a SEG
+//       task: binned-SAH re-optimisation of the treelets, staged in shared memory, same preorder index range
 //   6. emit_kernel       ... the reference's indexing rule  index(v) = 2*first(v) + L(v)  which is exactly
 //                        child_l = i+1, child_r = i + 2*n_l (bvh_node.rs:138-142): the output is a valid
 //                        preorder `Bvh.nodes`, so flatten / traversal / refit run on it unchanged.
 // Hit sets are identical to the reference tree's for rays without an exactly-zero direction component
 // (every valid BVH yields the same set); topology, node indices and SAH cost differ.
 #include "internal.h"
+#include "build_types.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace bvhb200 {
@@ -110,20 +113,24 @@ __global__ void __launch_bounds__(256) path_kernel(const uint32_t* __restrict__ 
     if (not_done && uu != 0u) *not_done = (uint32_t)BVHGPU_ERR_INTERNAL;   // root path longer than 2^rounds edges
 }
 
-// Bottom-up subtree AABBs: one thread per leaf climbs; the second arrival at a node merges and carries on.
+// Bottom-up subtree bounds: one thread per leaf climbs; the second arrival at a node merges and carries on.
+// boxes[v][0..5] = AABB of the subtree, boxes[v][6..11] = bounds of its shapes' centroids (needed as centroid_bounds by
+// the SAH re-optimisation of the treelets).
 template <class T>
 __global__ void __launch_bounds__(256) box_up_kernel(const typename Traits<T>::DAabb* __restrict__ aabb, const uint32_t* __restrict__ vals, uint32_t n,
                                                      const uint32_t* __restrict__ parent, const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
                                                      T* __restrict__ boxes, uint32_t* arrivals) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    T mn[3], mx[3];
-    load_aabb(aabb + vals[p], mn, mx);
+    T b[12];
+    load_aabb(aabb + vals[p], b, b + 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) b[6 + k] = b[9 + k] = center1(b[k], b[3 + k]);
     uint32_t v = n - 1 + p;
     {
-        T* b = boxes + 6ull * v;
+        T* d = boxes + 12ull * v;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { __stcg(b + k, mn[k]); __stcg(b + 3 + k, mx[k]); }
+        for (int k = 0; k < 12; ++k) __stcg(d + k, b[k]);
     }
     while (v != 0) {
         const uint32_t par = parent[v];
@@ -131,27 +138,31 @@ __global__ void __launch_bounds__(256) box_up_kernel(const typename Traits<T>::D
         if (atomicAdd(arrivals + par, 1u) == 0u) return;       // sibling subtree not finished yet
         __threadfence();
         const uint32_t sib = left[par] == v ? right[par] : left[par];
-        const T* sb = boxes + 6ull * sib;
+        const T* sb = boxes + 12ull * sib;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const T smn = __ldcg(sb + k), smx = __ldcg(sb + 3 + k);
-            mn[k] = smn < mn[k] ? smn : mn[k];
-            mx[k] = smx > mx[k] ? smx : mx[k];
+        for (int k = 0; k < 12; ++k) {
+            const T o = __ldcg(sb + k);
+            const bool isMin = (k % 6) < 3;
+            b[k] = isMin ? (o < b[k] ? o : b[k]) : (o > b[k] ? o : b[k]);
         }
         v = par;
-        T* b = boxes + 6ull * v;
+        T* d = boxes + 12ull * v;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { __stcg(b + k, mn[k]); __stcg(b + 3 + k, mx[k]); }
+        for (int k = 0; k < 12; ++k) __stcg(d + k, b[k]);
     }
 }
 
+// Emits the reference-layout nodes.  treelets: subtrees of <= TILE shapes are NOT emitted; their root becomes a SEG task of
+// the persistent SAH build kernel (queue slot written here, consumed by the next launch), which rebuilds that range with the
+// reference's 6-bucket SAH in shared memory and writes its nodes / leaves into the same preorder index range.
 template <class T>
 __global__ void __launch_bounds__(256) lbvh_emit_kernel(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ left,
                                                         const uint32_t* __restrict__ right, const uint32_t* __restrict__ first,
                                                         const uint32_t* __restrict__ count, const uint32_t* __restrict__ parent,
                                                         const uint32_t* __restrict__ L, const T* __restrict__ boxes,
                                                         typename Traits<T>::Node* __restrict__ nodes, uint32_t* __restrict__ node_index,
-                                                        uint32_t* __restrict__ node_start) {
+                                                        uint32_t* __restrict__ node_start,
+                                                        bool treelets, QSlot<T>* q, uint32_t* qseq, uint32_t qmask, BuildCtl* ctl) {
     using Tr = Traits<T>;
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * n - 1) return;
@@ -160,6 +171,21 @@ __global__ void __launch_bounds__(256) lbvh_emit_kernel(uint32_t n, const uint32
     const uint32_t idx = 2 * f + L[v];
     const uint32_t par = parent[v];
     const uint32_t pidx = v == 0 ? 0u : 2 * first[par] + L[par];
+    const uint32_t cnt = leaf ? 1u : count[v];
+    if (treelets) {
+        if (v != 0 && count[par] <= (uint32_t)TILE) return;           // strictly inside a treelet: the SAH kernel writes it
+        if (!leaf && cnt <= (uint32_t)TILE) {                          // treelet root -> SEG task
+            const uint32_t tk = atomicAdd(&ctl->tail, 1u);
+            QSlot<T>& s = q[tk & qmask];
+            s.t.start = f; s.t.count = cnt; s.t.node = idx; s.t.parent_buf = pidx;          // range lives in index buffer 0
+            const T* b = boxes + 12ull * v;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { s.t.ab[k] = b[k]; s.t.cb[k] = b[6 + k]; }
+            s.kind = KIND_SEG; s.a = s.b = s.pad = 0;
+            qseq[tk & qmask] = tk + 1u;
+            return;
+        }
+    }
     typename Tr::Node nd;
     nd.parent = pidx;
     if (leaf) {
@@ -168,12 +194,13 @@ __global__ void __launch_bounds__(256) lbvh_emit_kernel(uint32_t n, const uint32
 #pragma unroll
         for (int k = 0; k < 3; ++k) { nd.l_aabb.min[k] = nd.r_aabb.min[k] = Tr::inf(); nd.l_aabb.max[k] = nd.r_aabb.max[k] = -Tr::inf(); }
         node_index[shape] = idx;
+        if (treelets) atomicAdd(&ctl->leaves_done, 1u);
     } else {
         const uint32_t cl = left[v], cr = right[v];
         const uint32_t nl = cl >= n - 1 ? 1u : count[cl];
-        nd.child_l = idx + 1; nd.child_r = idx + 2 * nl; nd.shape = count[v];
-        const T* bl = boxes + 6ull * cl;
-        const T* br = boxes + 6ull * cr;
+        nd.child_l = idx + 1; nd.child_r = idx + 2 * nl; nd.shape = cnt;
+        const T* bl = boxes + 12ull * cl;
+        const T* br = boxes + 12ull * cr;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { nd.l_aabb.min[k] = bl[k]; nd.l_aabb.max[k] = bl[3 + k]; nd.r_aabb.min[k] = br[k]; nd.r_aabb.max[k] = br[3 + k]; }
     }
@@ -195,7 +222,7 @@ template <class T> int prep_only(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb
                                  typename Traits<T>::Key* rootkeys, BuildStatus* status);
 
 template <class T>
-int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree) {
+int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree, bool treelets) {
     using Tr = Traits<T>;
     cudaStream_t st = ctx->stream;
     tree->ctx = ctx; tree->n = n; tree->n_nodes = n ? 2 * n - 1 : 0;
@@ -227,7 +254,7 @@ int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32
     BVH_TRY(dalloc_t(ctx, &left, n)); BVH_TRY(dalloc_t(ctx, &right, n)); BVH_TRY(dalloc_t(ctx, &first, n)); BVH_TRY(dalloc_t(ctx, &count, n));
     BVH_TRY(dalloc_t(ctx, &parent, total)); BVH_TRY(dalloc_t(ctx, &isleft, total));
     BVH_TRY(dalloc_t(ctx, &upA, total)); BVH_TRY(dalloc_t(ctx, &upB, total)); BVH_TRY(dalloc_t(ctx, &valA, total)); BVH_TRY(dalloc_t(ctx, &valB, total));
-    BVH_TRY(dalloc_t(ctx, &arrivals, n)); BVH_TRY(dalloc_t(ctx, &boxes, 6ull * total));
+    BVH_TRY(dalloc_t(ctx, &arrivals, n)); BVH_TRY(dalloc_t(ctx, &boxes, 12ull * total));
     const unsigned gn = (n + 255) / 256, gt = (total + 255) / 256;
     morton_kernel<T><<<gn, 256, 0, st>>>(tree->d_aabb, n, rootkeys, keys, vals);
     size_t tmp_bytes = 0;
@@ -244,16 +271,20 @@ int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32
     }
     BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * n, st));
     box_up_kernel<T><<<gn, 256, 0, st>>>(tree->d_aabb, vals2, n, parent, left, right, boxes, arrivals);
-    lbvh_emit_kernel<T><<<gt, 256, 0, st>>>(n, vals2, left, right, first, count, parent, vi, boxes, tree->d_nodes, tree->d_node_index, tree->d_node_start);
+    TreeletSession<T> S;
+    if (treelets) BVH_TRY(treelet_begin<T>(ctx, tree, vals2, &S));
+    lbvh_emit_kernel<T><<<gt, 256, 0, st>>>(n, vals2, left, right, first, count, parent, vi, boxes, tree->d_nodes, tree->d_node_index, tree->d_node_start,
+                                            treelets, S.q, S.qseq, S.qmask, S.ctl);
     ctx->launches += 14;
     BVH_CUDA_TRY(cudaGetLastError());
+    if (treelets) BVH_TRY(treelet_finish<T>(ctx, tree, &S));
     dfree(ctx, keys); dfree(ctx, keys2); dfree(ctx, vals); dfree(ctx, vals2); dfree(ctx, left); dfree(ctx, right); dfree(ctx, first); dfree(ctx, count);
     dfree(ctx, parent); dfree(ctx, isleft); dfree(ctx, upA); dfree(ctx, upB); dfree(ctx, valA); dfree(ctx, valB); dfree(ctx, arrivals); dfree(ctx, boxes);
     dfree(ctx, tmp); dfree(ctx, rootkeys);
     return BVHGPU_OK;
 }
 
-template int build_lbvh<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, Tree<float>*);
-template int build_lbvh<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, Tree<double>*);
+template int build_lbvh<float>(bvhgpu_ctx*, const bvh_aabb3f*, uint32_t, Tree<float>*, bool);
+template int build_lbvh<double>(bvhgpu_ctx*, const bvh_aabb3d*, uint32_t, Tree<double>*, bool);
 
 }  // namespace bvhb200

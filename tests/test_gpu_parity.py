@@ -368,12 +368,16 @@ def test_config5_ten_million_f64(api):
 
 
 # ---- BVHGPU_BUILD_LBVH: different topology, same layout rule, same hit sets ------------------------------------------
-@pytest.mark.parametrize("name", ["cubes1", "random2", "random3", "random33", "random1000", "cubes1000", "points3000", "line700", "skew3000", "huge300"])
-def test_lbvh_mode_is_a_valid_reference_layout_bvh(api, name):
+@pytest.mark.parametrize("mode", [1, 2], ids=["lbvh", "lbvh_treelet"])
+@pytest.mark.parametrize("name", ["cubes1", "random2", "random3", "random33", "random257", "random1000", "cubes1000", "points3000", "line700", "skew3000", "huge300"])
+def test_lbvh_mode_is_a_valid_reference_layout_bvh(api, name, mode):
     from bvh_b200 import capi
 
     shapes = scene(name)
-    bvh = api.Bvh.build(shapes, mode=capi.BUILD_LBVH)
+    bvh = api.Bvh.build(shapes, mode=mode)
+    if mode == capi.BUILD_LBVH_TREELET and len(shapes) <= 256:
+        # a scene that fits one treelet is rebuilt entirely by the SAH kernel: identical to the exact builder
+        assert _nodes_equal(bvh.nodes, O.build(shapes).nodes)
     nodes, idx = bvh.nodes, bvh.node_index
     n = len(shapes)
     assert len(nodes) == 2 * n - 1
@@ -405,9 +409,12 @@ def test_lbvh_sah_cost_ratio_config2(api):
     shapes = O.create_n_cubes(10_000)
     exact = api.Bvh.build(shapes)
     lbvh = api.Bvh.build(shapes, mode=capi.BUILD_LBVH)
-    ce, cl = exact.sah_cost(), lbvh.sah_cost()
-    print(f"SAH cost (pseudo-area) exact {ce[0]:.4f} lbvh {cl[0]:.4f} ratio {cl[0] / ce[0]:.3f}; geometric ratio {cl[1] / ce[1]:.3f}")
+    tre = api.Bvh.build(shapes, mode=capi.BUILD_LBVH_TREELET)
+    ce, cl, ct = exact.sah_cost(), lbvh.sah_cost(), tre.sah_cost()
+    print(f"SAH cost (pseudo-area) exact {ce[0]:.4f} lbvh {cl[0]:.4f} ratio {cl[0] / ce[0]:.3f}; geometric ratio {cl[1] / ce[1]:.3f}; "
+          f"lbvh+treelet ratio {ct[0] / ce[0]:.3f} (geometric {ct[1] / ce[1]:.3f})")
     assert cl[0] / ce[0] < 3.0
+    assert ct[0] / ce[0] <= 1.10                           # stated tolerance
     rays, _ = O.create_rays(200_000)
     a = exact.traverse_batch(rays)
     b = lbvh.traverse_batch(rays)

@@ -57,7 +57,7 @@ def trav_time(bvh, rays, prec="f32"):
 # configs[0]/[1]: cube scenes, f32
 for n_cubes in (100, 1000, 10000, 100000):
     a = scenes.create_n_cubes_aabbs(n_cubes)
-    for mode, name in ((capi.BUILD_EXACT_SAH, "exact_sah"), (capi.BUILD_LBVH, "lbvh")):
+    for mode, name in ((capi.BUILD_EXACT_SAH, "exact_sah"), (capi.BUILD_LBVH, "lbvh"), (capi.BUILD_LBVH_TREELET, "lbvh_treelet")):
         ms = build_time(a, "f32", mode)
         out[f"build_{name}_{12*n_cubes}_f32"] = {"ms": ms, "Mprims_per_s": len(a) / ms / 1e3}
 a = scenes.create_n_cubes_aabbs(10000)
@@ -76,6 +76,11 @@ tris = z["vertices"][z["triangles"].astype(np.int64)]
 sp = np.zeros(len(tris), dtype=BY_PREC["f32"]["aabb"]); sp["min"] = tris.min(axis=1); sp["max"] = tris.max(axis=1)
 out["build_exact_sah_sponza_66450_f32"] = {"ms": (m := build_time(sp, "f32", capi.BUILD_EXACT_SAH)), "Mprims_per_s": len(sp) / m / 1e3}
 sbvh = api.Bvh.build(sp, ctx=ctx)
+for mode, name in ((capi.BUILD_LBVH, "lbvh"), (capi.BUILD_LBVH_TREELET, "lbvh_treelet")):
+    m = build_time(sp, "f32", mode)
+    tb = api.Bvh.build(sp, ctx=ctx, mode=mode)
+    out[f"build_{name}_sponza_66450_f32"] = {"ms": m, "Mprims_per_s": len(sp) / m / 1e3, "sah_cost_ratio_vs_exact": tb.sah_cost()[0] / sbvh.sah_cost()[0],
+                                            "sah_geometric_ratio_vs_exact": tb.sah_cost()[1] / sbvh.sah_cost()[1]}
 o, d = scenes.pinhole_rays(2048, 2048)
 ms, tot, v = trav_time(sbvh, api.Ray.new(o, d, ctx=ctx))
 out["traverse_sponza_4M_coherent"] = {"ms": ms, "Mrays_per_s": 4.194304e3 / ms, "hits": tot, "visits_per_ray": v / 4194304}
@@ -89,6 +94,8 @@ ms = build_time(a64, "f64", capi.BUILD_EXACT_SAH)
 out["build_exact_sah_10M_f64"] = {"ms": ms, "Mprims_per_s": len(a64) / ms / 1e3}
 ms = build_time(a64, "f64", capi.BUILD_LBVH)
 out["build_lbvh_10M_f64"] = {"ms": ms, "Mprims_per_s": len(a64) / ms / 1e3}
+ms = build_time(a64, "f64", capi.BUILD_LBVH_TREELET)
+out["build_lbvh_treelet_10M_f64"] = {"ms": ms, "Mprims_per_s": len(a64) / ms / 1e3}
 b64 = api.Bvh.build(a64, prec="f64", ctx=ctx)
 t0 = time.perf_counter(); b64.refit(a64); out["refit_10M_f64_host_call_ms"] = (time.perf_counter() - t0) * 1e3
 print(json.dumps(out, indent=1))
