@@ -236,6 +236,24 @@ class Bvh:
             capi.check(st)
         return offsets, hits[: total.value]
 
+    def traverse_ordered(self, rays: np.ndarray, ascending: bool = True):
+        """Batched nearest_traverse_iterator / farthest_traverse_iterator: CSR + distances, perfectly sorted per ray."""
+        rays = np.ascontiguousarray(rays, dtype=self._d["ray"])
+        n = len(rays)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        cap = max(8 * n, 1024)
+        fn = getattr(capi.lib(), f"bvhgpu_traverse_ordered_{self._d['suffix']}")
+        while True:
+            hits = np.zeros(cap, dtype=np.uint32)
+            dists = np.zeros(cap, dtype=self._d["scalar"])
+            total = C.c_size_t(0)
+            st = fn(self._h, _ptr(rays), n, 1 if ascending else 0, _ptr(offsets), _ptr(hits), _ptr(dists), cap, C.byref(total))
+            if st == capi.ERR_CAPACITY and total.value <= U32_MAX and total.value > cap:
+                cap = total.value
+                continue
+            capi.check(st)
+            return offsets, hits[: total.value], dists[: total.value]
+
     def query_batch(self, kind: int, queries, mode: int = capi.TRAVERSE_BVH):
         """Bvh::traverse with Aabb / Point / Ball queries (IntersectsAabb implementors other than Ray).
         queries: (n, 6) {min,max} for capi.QUERY_AABB, (n, 3) for QUERY_POINT, (n, 4) {center, radius} for QUERY_BALL."""

@@ -267,6 +267,35 @@ static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, 
     return ret;
 }
 
+template <class T>
+static int ordered_host_impl(Tree<T>* tree, const typename Traits<T>::Ray* rays, size_t nrays, int ascending,
+                             uint32_t* offsets, uint32_t* hits, T* dists, size_t cap, size_t* total) {
+    if (!tree || (nrays && !rays) || !offsets || (cap && (!hits || !dists))) { set_error("traverse_ordered: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    typename Traits<T>::Ray* d_rays = nullptr;
+    uint32_t *d_off = nullptr, *d_hits = nullptr;
+    T* d_dists = nullptr;
+    BVH_TRY(dalloc_t(ctx, &d_rays, nrays));
+    BVH_TRY(dalloc_t(ctx, &d_off, nrays + 1));
+    BVH_TRY(dalloc_t(ctx, &d_hits, cap));
+    BVH_TRY(dalloc_t(ctx, &d_dists, cap));
+    if (nrays) BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(*rays) * nrays, cudaMemcpyHostToDevice, ctx->stream));
+    size_t tot = 0;
+    int rc = traverse_ordered_device<T>(tree, d_rays, nrays, ascending, d_off, d_hits, d_dists, cap, &tot);
+    if (total) *total = tot;
+    if (rc == BVHGPU_OK || rc == BVHGPU_ERR_CAPACITY) {
+        cudaMemcpyAsync(offsets, d_off, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream);
+        const size_t m = std::min(tot, cap);
+        if (m) { cudaMemcpyAsync(hits, d_hits, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream); cudaMemcpyAsync(dists, d_dists, sizeof(T) * m, cudaMemcpyDeviceToHost, ctx->stream); }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("traverse_ordered: %s", cudaGetErrorString(e)); rc = BVHGPU_ERR_CUDA; }
+    }
+    dfree(ctx, d_rays); dfree(ctx, d_off); dfree(ctx, d_hits); dfree(ctx, d_dists);
+    return rc;
+}
+
 template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t cap) {
     if (!tree || !hits) { set_error("traverse_fetch: null argument"); return BVHGPU_ERR_INVALID; }
     if (cap < tree->last_total) { set_error("traverse_fetch: capacity %zu < %zu hits", cap, tree->last_total); return BVHGPU_ERR_CAPACITY; }
@@ -501,6 +530,10 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
         if (!tree || !dev_offsets || (n && !dev_queries)) { set_error("query_dev: null argument"); return BVHGPU_ERR_INVALID; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
         return query_device<T>(tree, mode, kind, (const T*)dev_queries, n, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_ordered_##SUF(TREE* tree, const RAY* rays, size_t nrays, int ascending, uint32_t* offsets,      \
+                                                 uint32_t* hits, T* dists, size_t cap, size_t* total) {                  \
+        return ordered_host_impl<T>(tree, rays, nrays, ascending, offsets, hits, dists, cap, total);                      \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
         if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \

@@ -126,6 +126,9 @@ template <class T> int traverse_device(Tree<T>* tree, int mode, const typename T
 // Host rays in, host CSR out; H2D / walk+scan+emit / D2H pipelined over chunks.  Needs tree->d_offsets / d_hits sized by the caller.
 template <class T> int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::Ray* h_rays, size_t nrays,
                                                uint32_t* h_offsets, uint32_t* h_hits, size_t h_cap, size_t* total);
+// hits sorted by entry (ascending) / exit (descending) distance, with the distances; device pointers
+template <class T> int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays, size_t nrays, int ascending,
+                                               uint32_t* d_offsets, uint32_t* d_hits, T* d_dists, size_t cap, size_t* total);
 // Aabb / Point / Ball queries (device pointers); two-pass count / fill.
 template <class T> int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t nq, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,

@@ -771,6 +771,102 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
 template int query_device<float>(Tree<float>*, int, int, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 template int query_device<double>(Tree<double>*, int, int, const double*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 
+// ---- ordered traversal: hits of every ray sorted by AABB entry distance (nearest first) or by exit
+// distance (farthest first), with the distance.  The reference's DistanceTraverseIterator (src/bvh/distance_traverse.rs) is
+// a best-effort heap walk ("not necessarily perfectly sorted", ties in heap order); this returns the same SET, perfectly
+// sorted, ties in the reference's DFS order.  Distances follow Ray::intersection_slice_for_aabb (src/ray/ray_impl.rs:118-145).
+template <class T>
+__device__ __forceinline__ bool slab_slice(const T o[3], const T inv[3], const T mn[3], const T mx[3], T& tmin_out, T& tmax_out) {
+    const T l0 = mul_rn(sub_rn(mn[0], o[0]), inv[0]), r0 = mul_rn(sub_rn(mx[0], o[0]), inv[0]);
+    const T l1 = mul_rn(sub_rn(mn[1], o[1]), inv[1]), r1 = mul_rn(sub_rn(mx[1], o[1]), inv[1]);
+    const T l2 = mul_rn(sub_rn(mn[2], o[2]), inv[2]), r2 = mul_rn(sub_rn(mx[2], o[2]), inv[2]);
+    const bool nan = (l0 != l0) | (r0 != r0) | (l1 != l1) | (r1 != r1) | (l2 != l2) | (r2 != r2);
+    const T tmin = tmax2(tmax2(tmin2(l0, r0), tmin2(l1, r1)), tmin2(l2, r2));
+    const T tmax = tmin2(tmin2(tmax2(l0, r0), tmax2(l1, r1)), tmax2(l2, r2));
+    tmin_out = tmin > T(0) ? tmin : T(0);                       // fast_max(inf.max(), 0)
+    tmax_out = tmax;
+    return !nan && !(tmin_out > tmax);                          // None iff tmin > tmax or NaN
+}
+
+template <class T, bool FILL>
+__global__ void __launch_bounds__(256) ordered_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                      const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays, int ascending,
+                                                      uint32_t* __restrict__ counts, const uint32_t* __restrict__ local,
+                                                      const unsigned long long* __restrict__ blocksum, const unsigned long long* __restrict__ total,
+                                                      uint32_t* __restrict__ offsets, uint32_t* __restrict__ hits, T* __restrict__ dists, unsigned long long cap) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (FILL && r == 0) { const unsigned long long t = *total; offsets[nrays] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t; }
+    if (r >= nrays) return;
+    T o[3], inv[3];
+    load_ray<T>(rays, r, o, inv);
+    unsigned long long base = 0, w = 0;
+    if (FILL) { base = blocksum[r / SCAN_TILE] + local[r]; offsets[r] = base > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)base; w = base; }
+    uint32_t cnt = 0, i = 0;
+    while (i < n_rec) {
+        T mn[3], mx[3], t0, t1;
+        uint32_t skip, shape;
+        fetch(trec + i, mn, mx, skip, shape);
+        if (slab_slice(o, inv, mn, mx, t0, t1)) {
+            if (shape != BVH_INVALID) {
+                if (FILL) { if (w < cap) { hits[w] = shape; dists[w] = ascending ? t0 : t1; } ++w; }
+                ++cnt;
+            }
+            i = i + 1;
+        } else i = skip;
+    }
+    if (!FILL) { counts[r] = cnt; return; }
+    // stable insertion sort of this ray's list (lists are short): ascending entry distance / descending exit distance
+    const unsigned long long end = w < cap ? w : cap;
+    for (unsigned long long a = base + 1; a < end; ++a) {
+        const T d = dists[a];
+        const uint32_t h = hits[a];
+        unsigned long long b = a;
+        while (b > base && (ascending ? dists[b - 1] > d : dists[b - 1] < d)) { dists[b] = dists[b - 1]; hits[b] = hits[b - 1]; --b; }
+        dists[b] = d; hits[b] = h;
+    }
+}
+
+template <class T>
+int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays, size_t nrays, int ascending,
+                            uint32_t* d_offsets, uint32_t* d_hits, T* d_dists, size_t cap, size_t* total) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (nrays > 0x7FFFFFFFull) { set_error("traverse_ordered: too many rays"); return BVHGPU_ERR_INVALID; }
+    if (nrays == 0 || tree->n == 0) {
+        BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nrays + 1), st));
+        if (total) *total = 0;
+        return BVHGPU_OK;
+    }
+    BVH_TRY(resolve_status(tree));
+    if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const uint32_t R = (uint32_t)nrays, nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *counts = nullptr, *local = nullptr;
+    unsigned long long* sums = nullptr;
+    BVH_TRY(dalloc_t(ctx, &counts, R));
+    BVH_TRY(dalloc_t(ctx, &local, R));
+    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
+    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
+    const int grid = (R + 255) / 256;
+    ordered_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, d_rays, R, ascending, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+    ordered_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, d_rays, R, ascending, counts, local, sums, sums + nblk, d_offsets, d_hits, d_dists, (unsigned long long)cap);
+    ctx->launches += 4;
+    BVH_CUDA_TRY(cudaGetLastError());
+    int rc = BVHGPU_OK;
+    if (total) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
+        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaStreamSynchronize(st));
+        *total = (size_t)h[0];
+        if (h[0] > 0xFFFFFFFFull || h[0] > cap) { set_error("traverse_ordered: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
+    }
+    dfree(ctx, counts); dfree(ctx, local); dfree(ctx, sums);
+    return rc;
+}
+template int traverse_ordered_device<float>(Tree<float>*, const bvh_ray3f*, size_t, int, uint32_t*, uint32_t*, float*, size_t, size_t*);
+template int traverse_ordered_device<double>(Tree<double>*, const bvh_ray3d*, size_t, int, uint32_t*, uint32_t*, double*, size_t, size_t*);
+
 // ---- Ray::new for a batch (src/ray/ray_impl.rs:70-80) -------------------------------------------------
 template <class T> __device__ __forceinline__ T sqrt_rn(T x);
 template <> __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }

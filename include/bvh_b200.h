@@ -208,6 +208,17 @@ int bvhgpu_query_dev_f32x3(bvhgpu_tree3f* tree, int mode, int kind, const void* 
 int bvhgpu_query_dev_f64x3(bvhgpu_tree3d* tree, int mode, int kind, const void* dev_queries, size_t n,
                            void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
 
+/* ---- distance-ordered traversal: batched counterpart of Bvh::nearest_traverse_iterator /
+ * farthest_traverse_iterator (src/bvh/distance_traverse.rs, src/bvh/bvh_impl.rs).  Per ray: the shapes whose AABB the ray
+ * hits (same set as bvhgpu_traverse_*, BVH semantics), sorted by AABB entry distance ascending (`ascending` != 0) or by
+ * exit distance descending, with that distance in `dists` (Ray::intersection_slice_for_aabb, src/ray/ray_impl.rs:118-145).
+ * The reference iterator is best-effort ("not necessarily perfectly sorted"); this result is perfectly sorted, ties in the
+ * reference's DFS order.  Host pointers; `cap` entries in hits and dists. */
+int bvhgpu_traverse_ordered_f32x3(bvhgpu_tree3f* tree, const bvh_ray3f* rays, size_t nrays, int ascending,
+                                  uint32_t* offsets, uint32_t* hits, float* dists, size_t cap, size_t* total);
+int bvhgpu_traverse_ordered_f64x3(bvhgpu_tree3d* tree, const bvh_ray3d* rays, size_t nrays, int ascending,
+                                  uint32_t* offsets, uint32_t* hits, double* dists, size_t cap, size_t* total);
+
 /* Ray::new for a batch (src/ray/ray_impl.rs:70-80): normalise, inv = 1/direction. Device pointers. */
 int bvhgpu_rays_new_dev_f32x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);
 int bvhgpu_rays_new_dev_f64x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);

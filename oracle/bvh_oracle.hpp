@@ -149,6 +149,21 @@ template <class T> inline bool ray_intersects_aabb(const Ray3<T>& ray, const Aab
     return tmax >= fast_max(tmin, T(0));
 }
 
+// Ray::intersection_slice_for_aabb (src/ray/ray_impl.rs:118-145)
+template <class T> inline bool ray_slice_for_aabb(const Ray3<T>& ray, const Aabb3<T>& b, T& tmin_out, T& tmax_out) {
+    T l[3], r[3];
+    for (int k = 0; k < 3; ++k) {
+        l[k] = (b.min[k] - ray.origin[k]) * ray.inv_direction[k];
+        r[k] = (b.max[k] - ray.origin[k]) * ray.inv_direction[k];
+    }
+    for (int k = 0; k < 3; ++k) if (std::isnan(l[k]) || std::isnan(r[k])) return false;
+    T tmin = smin(l[0], r[0]), tmax = smax(l[0], r[0]);
+    for (int k = 1; k < 3; ++k) { tmin = smax(tmin, smin(l[k], r[k])); tmax = smin(tmax, smax(l[k], r[k])); }
+    tmin_out = fast_max(tmin, T(0));
+    tmax_out = tmax;
+    return !(tmin_out > tmax) ;
+}
+
 // Other IntersectsAabb implementors (src/aabb/intersection.rs:35-45, src/ball.rs:85-106).
 // Query records: kind 1 = Aabb {min,max} (6 T), kind 2 = Point (3 T), kind 3 = Ball {center, radius} (4 T).
 template <class T> inline bool aabb_intersects_aabb(const Aabb3<T>& q, const Aabb3<T>& b) {          // aabb_impl.rs:240-248

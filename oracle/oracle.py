@@ -270,6 +270,16 @@ def ray_intersects_aabb(ray: np.ndarray, aabb: np.ndarray, prec="f32") -> bool:
     return bool(getattr(lib(), f"orc_ray_intersects_aabb_{prec}")(_p(ray), _p(aabb)))
 
 
+def ray_slice(ray, aabb, prec="f32"):
+    """Ray::intersection_slice_for_aabb (ray_impl.rs:118-145): (tmin, tmax) or None."""
+    d = _DT[prec]
+    ray = np.ascontiguousarray(ray, dtype=d["ray"]).reshape(1)
+    aabb = np.ascontiguousarray(aabb, dtype=d["aabb"]).reshape(1)
+    out = np.zeros(2, dtype=d["f"])
+    ok = getattr(lib(), f"orc_ray_slice_{prec}")(_p(ray), _p(aabb), _p(out))
+    return (out[0], out[1]) if ok else None
+
+
 def aligned_boxes(prec="f32") -> np.ndarray:
     out = np.zeros(21, dtype=_DT[prec]["aabb"])
     getattr(lib(), f"orc_aligned_boxes_{prec}")(_p(out))

@@ -123,6 +123,9 @@ static uint64_t g_last_build_ns = 0;
         offsets[nq] = total;                                                                                 \
         return total;                                                                                        \
     }                                                                                                        \
+    ORC_API int orc_ray_slice_##SUF(const Ray3<T>* ray, const Aabb3<T>* aabb, T* out2) {                      \
+        return ray_slice_for_aabb(*ray, *aabb, out2[0], out2[1]) ? 1 : 0;                                    \
+    }                                                                                                        \
     ORC_API int orc_is_consistent_##SUF(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes) {    \
         return is_consistent(nodes, n_nodes, shapes) ? 1 : 0;                                                \
     }                                                                                                        \

@@ -537,3 +537,32 @@ def test_capacity_error_and_fetch(api):
     capi.check(L.bvhgpu_traverse_fetch_f32x3(bvh._h, full.ctypes.data_as(C.c_void_p), tot.value))
     off2, hits2 = bvh.traverse_batch(rays)
     assert np.array_equal(off2, off) and np.array_equal(hits2, full)
+
+
+# ---- distance-ordered traversal ---------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["boxes21", "cubes300", "random3000"])
+def test_ordered_traversal(api, name, prec):
+    """Same hit set as Bvh::traverse, sorted by AABB entry distance (ascending) / exit distance (descending); the distances
+    are Ray::intersection_slice_for_aabb of the leaf's AABB, bit for bit; ties keep the reference's DFS order."""
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    rays = rays_for(shapes, 800, prec, seed=13, axis_aligned=100)
+    ref = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, prec)
+    lists = O.per_ray_lists(ref.offsets, ref.hits)
+    for ascending in (True, False):
+        off, hits, dists = bvh.traverse_ordered(rays, ascending)
+        assert np.array_equal(off.astype(np.uint64), ref.offsets)
+        for i, (ray, lst) in enumerate(zip(rays, lists)):
+            got_h, got_d = hits[off[i]:off[i + 1]], dists[off[i]:off[i + 1]]
+            sl = [O.ray_slice(ray, shapes[h], prec) for h in lst]
+            key = [s[0] if ascending else -s[1] for s in sl]
+            order = sorted(range(len(lst)), key=lambda j: key[j])          # stable: ties keep DFS order
+            assert got_h.tolist() == [int(lst[j]) for j in order], (name, i)
+            assert got_d.tolist() == [sl[j][0] if ascending else sl[j][1] for j in order]
+    # the reference's own monotonicity property (distance_traverse.rs:186-266)
+    off, hits, dists = bvh.traverse_ordered(rays, True)
+    for i in range(len(rays)):
+        d = dists[off[i]:off[i + 1]]
+        assert np.all(d[1:] >= d[:-1])

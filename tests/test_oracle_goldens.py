@@ -312,3 +312,19 @@ def test_ball_doctest():                                # src/ball.rs:74-84
     res = O.build(box)
     _, hits = O.query(O.QUERY_BALL, [[1.0, 1.0, 1.0, 1.0]], res.nodes, box)
     assert hits.tolist() == [0]
+
+
+def test_ray_slice_kats():                              # ray_impl.rs:256-299
+    box = O.make_aabbs([[-6.0, -8.0, -5.0]], [[-3.0, -4.0, 5.0]])
+    ray = O.ray_new([[2.0, 2.0, 2.0]], [[-5.0, -8.66666, -3.666666]])
+    tmin, tmax = O.ray_slice(ray, box)
+    assert abs(tmin - 10.6562) < 0.01 and abs(tmax - 12.3034) < 0.01
+    unit = O.unit_boxes([[-50.0, -50.0, -25.0]])
+    assert O.ray_slice(O.ray_new([[-50.0, -50.0, -50.0]], [[1.0, 0.0, 0.0]]), unit) is None          # parallel ray
+    assert O.ray_slice(O.ray_new([[0.0, 0.0, -0.5]], [[1.0, 0.0, 0.0]]), O.unit_boxes([[0.0, 0.0, 0.0]])) is None   # in-plane
+    # fuzz.rs:387-407: intersects_aabb <=> slice.is_some()
+    rng = np.random.default_rng(4)
+    for _ in range(500):
+        mn = rng.integers(-5, 5, 3).astype(np.float32); b = O.make_aabbs([mn], [mn + rng.integers(0, 4, 3)])
+        r = O.ray_new([rng.integers(-6, 6, 3) + 1.0 / 3.0], [rng.choice([-1.0, 0.0, 1.0, 0.3], 3) + np.array([0.0, 0.0, 1e-3])])
+        assert O.ray_intersects_aabb(r, b) == (O.ray_slice(r, b) is not None)
