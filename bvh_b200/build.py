@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libbvh_b200.so")
 SOURCES = ["capi.cu", "build_sah.cu", "flatten.cu", "traverse.cu", "lbvh.cu"]
-HEADERS = ["common.cuh", "internal.h", os.path.join("..", "..", "include", "bvh_b200.h")]
+HEADERS = ["common.cuh", "internal.h", "build_types.cuh", os.path.join("..", "..", "include", "bvh_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

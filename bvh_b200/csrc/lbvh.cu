@@ -9,7 +9,7 @@
 //                        by position so duplicate codes still give a strict binary tree (Karras 2012)
 //   4. path_kernel x7    pointer jumping: L(v) = number of left edges on the root path, needed for ...
 //   5. box_kernel        bottom-up subtree AABBs with arrival counters
-//   5b. (BVHGPU_BUILD_LBVH_TREELET) every subtree of <= 256 shapes is handed to the persistent SAH build kernel as a SEG
+//   5b. (BVHGPU_BUILD_LBVH_TREELET) every subtree of <= 512 shapes is handed to the persistent SAH build kernel as a SEG
 //       task: binned-SAH re-optimisation of the treelets, staged in shared memory, same preorder index range
 //   6. emit_kernel       ... the reference's indexing rule  index(v) = 2*first(v) + L(v)  which is exactly
 //                        child_l = i+1, child_r = i + 2*n_l (bvh_node.rs:138-142): the output is a valid

@@ -72,7 +72,7 @@ typedef enum {
 typedef enum {
     BVHGPU_BUILD_EXACT_SAH = 0, /* bit-identical to Bvh::build (6-bucket SAH, src/bvh/bvh_node.rs:81-279) */
     BVHGPU_BUILD_LBVH = 1,      /* Morton/Karras LBVH: same hit sets, different topology */
-    BVHGPU_BUILD_LBVH_TREELET = 2 /* LBVH top + every subtree of <= 256 shapes rebuilt with the reference's 6-bucket SAH (shared memory) */
+    BVHGPU_BUILD_LBVH_TREELET = 2 /* LBVH top + every subtree of <= 512 shapes rebuilt with the reference's 6-bucket SAH (shared memory) */
 } bvhgpu_build_mode;
 
 typedef enum {
