@@ -375,8 +375,9 @@ def test_lbvh_mode_is_a_valid_reference_layout_bvh(api, name, mode):
 
     shapes = scene(name)
     bvh = api.Bvh.build(shapes, mode=mode)
-    if mode == capi.BUILD_LBVH_TREELET and len(shapes) <= 512:
-        # a scene that fits one treelet is rebuilt entirely by the SAH kernel: identical to the exact builder
+    if mode == capi.BUILD_LBVH_TREELET and len(shapes) <= 512 and name.startswith("random"):
+        # a scene that fits one treelet is rebuilt entirely by the SAH kernel: identical to the exact builder (for shapes in
+        # general position; the degenerate "halve by position" branch sees the Morton order instead of the input order)
         assert _nodes_equal(bvh.nodes, O.build(shapes).nodes)
     nodes, idx = bvh.nodes, bvh.node_index
     n = len(shapes)
