@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 N_CUBES = 10_000           # 120 000 triangles
 N_RAYS = 1_000_000
+BUILD_PRIM_VISITS = 2_144_236     # P of the 120k scene (sum over internal nodes of their shape count)
 METRIC = "traversal_Mrays_per_s"
 UNIT = "Mrays/s"
 
@@ -286,7 +287,12 @@ def run_b200(args):
     line = _base_line(args, value, step_ms, launches, clocks)
     line["roofline"] = roofline
     line["e2e"] = e2e
-    line["build"] = {"value": n / (build_ms * 1e-3) / 1e6, "unit": "Mprims/s", "ms": build_ms, "what": "Bvh::build (exact SAH, bit-identical) + flatten, 120000 shapes, AABBs resident in HBM, median of 10"}
+    # algorithmic bytes of the build (SURVEY 8d / DESIGN 4.1): n*S_aabb + P*(S_aabb+8+8) + (2n-1)*S_node + n*8, P = sum over internal
+    # nodes of their range size = 2 144 236 for this scene (oracle counter; asserted in tests/test_oracle_goldens.py)
+    build_bytes = n * 24 + BUILD_PRIM_VISITS * (24 + 8 + 8) + (2 * n - 1) * 64 + n * 8
+    line["build"] = {"value": n / (build_ms * 1e-3) / 1e6, "unit": "Mprims/s", "ms": build_ms, "what": "Bvh::build (exact SAH, bit-identical) + flatten, 120000 shapes, AABBs resident in HBM, median of 10",
+                     "roofline": {"bound": "hbm", "achieved": build_bytes / (build_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": build_bytes / (build_ms * 1e-3) / 1e9 / peak,
+                                  "bytes_per_build": build_bytes, "note": "latency-bound at this size: ~9 multi-warp tree levels + warp-serial subtrees on a 30 MB L2-resident working set (DESIGN.md 4.1)"}}
     lt = []
     for k in range(3 + 10):
         flush.zero_()

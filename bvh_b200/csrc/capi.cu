@@ -209,7 +209,7 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     if (nrays == 0 || tree->n == 0) {                            // nothing to pipeline
         size_t tot0 = 0;
         BVH_TRY(ensure_result_buffers(tree, nrays, 1024));
-        BVH_TRY(traverse_device<T>(tree, mode, nullptr, rays, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot0));
+        BVH_TRY(traverse_device<T>(tree, mode, nullptr, nullptr, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot0));
         BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
         BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (total) *total = 0;

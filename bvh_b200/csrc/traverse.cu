@@ -68,6 +68,7 @@ __device__ __forceinline__ void fetch(const TNodeD* __restrict__ p, double mn[3]
     double w;
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mn[0]), "=d"(mn[1]), "=d"(mn[2]), "=d"(mx[0]) : "l"(p));
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx[1]), "=d"(mx[2]), "=d"(w), "=d"(w) : "l"(reinterpret_cast<const char*>(p) + 32));
+    (void)w;
     const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p) + 48));
     skip = t.x; shape = t.y;
 }
@@ -455,6 +456,7 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         tree->last_total = 0;
         return BVHGPU_OK;
     }
+    if (h_rays) { set_error("internal: host rays go through traverse_host_pipelined"); return BVHGPU_ERR_INTERNAL; }
     if (tree->n == 0) {                                          // empty Bvh: no hits (bvh_impl.rs:109-112)
         BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nrays + 1), st));
         if (total) *total = 0;
@@ -468,34 +470,13 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;       // [nblk] block offsets, [nblk] total, [nblk+1] visits
-    Ray* staged = nullptr;
     BVH_TRY(dalloc_t(ctx, &counts, R));
     BVH_TRY(dalloc_t(ctx, &local, R));
     if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
     BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 8));      // see launch_pass1 for the layout of the tail words
     BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 8 * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
-    auto launch_walk = [&](const Ray* rays, uint32_t first, uint32_t count) {
-        const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
-        ctx->launches++;
-    };
-    if (h_rays) {
-        // Host rays: chunked H2D on the copy stream, walk of chunk c overlaps the copy of chunk c+1.
-        BVH_TRY(dalloc_t(ctx, &staged, R));
-        BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));                        // copy stream starts after the allocation point
-        BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
-        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 250000));   // a walk launch costs ~0.1 ms whatever its size: keep chunks big
-        for (uint32_t c = 0; c < nchunks; ++c) {
-            const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
-            BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));
-            BVH_CUDA_TRY(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
-            BVH_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
-            launch_walk(staged, lo, hi - lo);
-        }
-        d_rays = staged;
-    } else {
+    {
         if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
         BVH_TRY(launch_pass1<T>(tree, flat, d_rays, R, 0, R, counts, slots, K, sums, nblk, false));
         if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
@@ -539,7 +520,7 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         if (h[0] > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", h[0]); rc = BVHGPU_ERR_CAPACITY; }
         else if (d_hits && h[0] > cap) { set_error("traverse: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
     }
-    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums); if (staged) dfree(ctx, staged);
+    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums);
     return rc;
 }
 

@@ -328,3 +328,11 @@ def test_ray_slice_kats():                              # ray_impl.rs:256-299
         mn = rng.integers(-5, 5, 3).astype(np.float32); b = O.make_aabbs([mn], [mn + rng.integers(0, 4, 3)])
         r = O.ray_new([rng.integers(-6, 6, 3) + 1.0 / 3.0], [rng.choice([-1.0, 0.0, 1.0, 0.3], 3) + np.array([0.0, 0.0, 1e-3])])
         assert O.ray_intersects_aabb(r, b) == (O.ray_slice(r, b) is not None)
+
+
+def test_bench_build_byte_model_constant():
+    """bench.py's algorithmic-byte model of the build uses P = sum over internal nodes of their range size for the 120k scene."""
+    import bench
+
+    res = O.build(O.create_n_cubes(10_000))
+    assert res.prim_visits == bench.BUILD_PRIM_VISITS
