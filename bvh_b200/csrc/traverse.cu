@@ -65,12 +65,11 @@ __device__ __forceinline__ void fetch(const TNodeF* __restrict__ p, float mn[3],
     shape = __float_as_uint(sh);
 }
 __device__ __forceinline__ void fetch(const TNodeD* __restrict__ p, double mn[3], double mx[3], uint32_t& skip, uint32_t& shape) {
-    double w;
+    double links, pad;                         // {skip, shape} travel as the bits of the 7th double of the 64-byte record
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mn[0]), "=d"(mn[1]), "=d"(mn[2]), "=d"(mx[0]) : "l"(p));
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx[1]), "=d"(mx[2]), "=d"(w), "=d"(w) : "l"(reinterpret_cast<const char*>(p) + 32));
-    (void)w;
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p) + 48));
-    skip = t.x; shape = t.y;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(mx[1]), "=d"(mx[2]), "=d"(links), "=d"(pad) : "l"(reinterpret_cast<const char*>(p) + 32));
+    const unsigned long long b = (unsigned long long)__double_as_longlong(links);
+    skip = (uint32_t)b; shape = (uint32_t)(b >> 32);
 }
 
 // The walk.  `emit(shape)` is called for every reported shape in reference order.
