@@ -107,10 +107,11 @@ template <class T> __device__ __forceinline__ void load_ray(const typename Trait
     for (int k = 0; k < 3; ++k) { o[k] = __ldg(p + k); inv[k] = __ldg(p + 6 + k); }
 }
 
-// Coherence probe: neighbouring rays of a coherent batch (camera rays) point the same way, and then consecutive rays
-// should stay in consecutive lanes (adjacent lanes walk the same nodes: one L1 wavefront serves many lanes); on
-// incoherent batches eager per-lane refill wins.  The probe samples 1024 neighbour pairs and leaves its verdict in
-// *flag, which the persistent kernel reads to pick its refill policy -- no host synchronisation.
+// Coherence probe: neighbouring rays of a coherent batch (camera rays) point the same way, and then the static
+// one-ray-per-thread mapping wins (adjacent lanes walk the same nodes: one L1 wavefront serves many lanes); on
+// incoherent batches the persistent refill kernel wins.  The probe samples 1024 neighbour pairs and leaves its
+// verdict in *flag; BOTH pass-1 kernels are launched and the one the verdict rules out returns immediately, so
+// the choice costs no host synchronisation.
 template <class T>
 __global__ void __launch_bounds__(256) coherence_probe_kernel(const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays, uint32_t* flag) {
     __shared__ float acc[8];
@@ -174,11 +175,9 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
                                                               uint32_t* __restrict__ ticket, const uint32_t* ready,
                                                               uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
                                                               unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
-    // gate (coherence probe verdict): 1 = coherent batch -> refill only whole warps with 32 consecutive rays (neighbouring
-    // camera rays stay in neighbouring lanes and share L1 wavefronts); 0 = incoherent -> refill as soon as 8 lanes are idle.
-    (void)run_if;
+    if (gate && *gate != run_if) return;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    const int REFILL = (gate && *gate) ? 32 : 8;
+    constexpr int REFILL = 8;
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = lane_id(), lt = lanemask_lt();
     uint32_t r = NONE, i = 0, cnt = 0, visits = 0;
@@ -414,12 +413,12 @@ static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray*
         coherence_probe_kernel<T><<<1, 256, 0, st>>>(rays, R, gate);
         ctx->launches++;
     }
-    if (pmode == 0) {
+    if (pmode == 0 || pmode >= 2) {
         const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, nullptr, 0u);
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
         ctx->launches++;
-        return BVHGPU_OK;
+        if (pmode == 0) return BVHGPU_OK;
     }
     if (first != 0 || count != R) { set_error("internal: persistent walk covers whole batches only"); return BVHGPU_ERR_INTERNAL; }
     if (ctx->walk_grid == 0) {
