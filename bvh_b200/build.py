@@ -25,7 +25,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-    "-Xcudafe", "--diag_suppress=177",
+    "-Xcudafe", "--diag_suppress=177", "-Xcudafe", "--diag_suppress=550",
 ]
 
 

@@ -10,8 +10,8 @@ bvh = api.Bvh.build(sp, ctx=ctx)
 def run(rays, label):
     dr = torch.from_numpy(rays.view(np.uint8).reshape(-1)).to(dev); n = len(rays)
     off = torch.empty(n + 1, dtype=torch.int32, device=dev); cap = 64 * n; hits = torch.empty(cap, dtype=torch.int32, device=dev)
-    for K in (0, 4, 8, 16, 32, 64):
-        for pers in (1, 0):
+    for K in (-1,):
+        for pers in (2, 1, 0):
             ctx.set_option("traverse_slots", K); ctx.set_option("traverse_persistent", pers)
             ts = []
             for k in range(8):
