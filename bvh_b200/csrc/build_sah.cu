@@ -50,6 +50,7 @@ template <class T> struct BuildParams {
     uint32_t small_max;             // ranges up to this many shapes are deferred (0 = none): pays off in the throughput regime only
     uint4* trace;                   // optional task log (BVHGPU_TRACE=file): {kind<<28|count, node/sid, t0_ns, t1_ns}
     uint32_t trace_cap;
+    uint32_t gang_budget;           // warps that gangs may hold at any time (0 = gang mode off)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -86,58 +87,99 @@ template <class T> __device__ __forceinline__ void split_axis(const BTask<T>& t,
     if (sz > ext) { axis = 2; ext = sz; cbmin = t.cb[2]; }
 }
 
-// Bucket assignment + Bucket::add_aabb (bvh_node.rs:204-222, utils.rs:78-83) for positions [p0,p1).
+// Bucket assignment + Bucket::add_aabb (bvh_node.rs:204-222, utils.rs:78-83) for positions [p0,p1); leaves the six
+// buckets of the range in ws->keys / ws->cnt.  No shared-memory atomics (an ATOMS costs the SM 64 cycles per warp and 13
+// of them per 32 shapes made the binning the longest phase of every level): the lanes of a chunk group combine their
+// own keys per bucket, one REDUX per (bucket, key) folds the warp, and lane k keeps key k of every bucket in registers.
 template <class T>
 __device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T>* ws, const uint32_t* __restrict__ src,
                                           uint32_t seg_start, uint32_t p0, uint32_t p1, int axis, T cbmin, T ext,
                                           bool degenerate, uint32_t half, bool store_bkt, uint32_t& last_id, int& last_b) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
     const uint32_t lane = lane_id();
     const T K = sub_rn(T(6), T(0.01));                 // T::from(NUM_BUCKETS) - T::from(0.01), bvh_node.rs:214-215
     constexpr int U = sizeof(T) == 8 ? 2 : 4;          // chunks in flight: index loads, then AABB gathers, then the math
+    const bool my_min = key_is_min<T>((int)lane);      // lanes 0..11 own key `lane` of each bucket
+    Key acc[6];
+    uint32_t cnt[6];
+#pragma unroll
+    for (int bb = 0; bb < 6; ++bb) { acc[bb] = my_min ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF; cnt[bb] = 0; }
     for (uint32_t base = p0; base < p1; base += 32 * U) {
         uint32_t id[U];
-        T mn[U][3], mx[U][3];
+        int bk[U];
+        Key kv[U][9];                                  // min3, max3, centre3 as keys
+        {
+            T mn[U][3], mx[U][3];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t pos = base + 32 * u + lane;
-            id[u] = pos < p1 ? __ldcg(src + pos) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t pos = base + 32 * u + lane;
-            if (pos < p1) load_aabb(P.aabb + id[u], mn[u], mx[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t pos = base + 32 * u + lane;
-            if (base + 32 * u >= p1) break;            // warp-uniform
-            int b = 0;
-            if (pos < p1) {
-                T c[3];
-#pragma unroll
-                for (int k = 0; k < 3; ++k) c[k] = center1(mn[u][k], mx[u][k]);
-                if (degenerate) {
-                    b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
-                } else {
-                    const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
-                    const T rel = div_rn(sub_rn(ca, cbmin), ext);
-                    b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
-                    b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
-                }
-                if (store_bkt) P.bkt[pos] = (uint8_t)b;
-                typename Traits<T>::Key* kb = ws->keys + b * 12;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    atomicMin(kb + k, f2key(mn[u][k]));
-                    atomicMax(kb + 3 + k, f2key(mx[u][k]));
-                    atomicMin(kb + 6 + k, f2key(c[k]));
-                    atomicMax(kb + 9 + k, f2key(c[k]));
-                }
-                atomicAdd(&ws->cnt[b], 1u);
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pos = base + 32 * u + lane;
+                id[u] = pos < p1 ? __ldcg(src + pos) : 0u;
             }
-            last_id = id[u];
-            last_b = b;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pos = base + 32 * u + lane;
+                if (pos < p1) load_aabb(P.aabb + id[u], mn[u], mx[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t pos = base + 32 * u + lane;
+                bk[u] = -1;
+                if (pos < p1) {
+                    T c[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c[k] = center1(mn[u][k], mx[u][k]);
+                    int b;
+                    if (degenerate) {
+                        b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
+                    } else {
+                        const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
+                        const T rel = div_rn(sub_rn(ca, cbmin), ext);
+                        b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
+                        b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
+                    }
+                    if (store_bkt) P.bkt[pos] = (uint8_t)b;
+                    bk[u] = b;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { kv[u][k] = f2key(mn[u][k]); kv[u][3 + k] = f2key(mx[u][k]); kv[u][6 + k] = f2key(c[k]); }
+                }
+                if (base + 32 * u < p1) { last_id = id[u]; last_b = bk[u] < 0 ? 0 : bk[u]; }
+            }
         }
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) {
+            bool in[U];
+            uint32_t c = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { in[u] = bk[u] == bb; c += __popc(__ballot_sync(0xffffffffu, in[u])); }
+            if (c == 0) continue;                      // warp-uniform
+            cnt[bb] += c;
+            Key mine = acc[bb];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const bool is_min = key_is_min<T>(k);
+                const int f = k < 6 ? k : (k < 9 ? k : k - 3);     // keys 6..8 (centroid min) and 9..11 (max) share the centre
+                Key v = is_min ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const Key x = kv[u][f];
+                    if (in[u]) v = is_min ? (x < v ? x : v) : (x > v ? x : v);
+                }
+                const Key r = is_min ? warp_min_key(v) : warp_max_key(v);
+                if ((int)lane == k) mine = is_min ? (r < mine ? r : mine) : (r > mine ? r : mine);
+            }
+            acc[bb] = mine;
+        }
+    }
+    if (lane < 12) {
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) ws->keys[bb * 12 + lane] = acc[bb];
+    }
+    if (lane < 6) {
+        uint32_t c = cnt[0];
+#pragma unroll
+        for (int bb = 1; bb < 6; ++bb) c = (int)lane == bb ? cnt[bb] : c;
+        ws->cnt[lane] = c;
     }
     __syncwarp();
 }
@@ -325,28 +367,227 @@ template <class T> __device__ __forceinline__ void push_tiles(const BuildParams<
     __syncwarp();
 }
 
-__device__ __forceinline__ uint32_t tile_slot(uint32_t p, bool first) { return 2u * (p / TILE) + (first ? 1u : 0u); }
+__device__ __forceinline__ uint32_t tile_slot(uint32_t p, bool first) { return 2u * (p / GT) + (first ? 1u : 0u); }
+// Multi-warp segment state: live segments are >= GANG_MIN > GT shapes long and disjoint, so start / GT is unique among
+// them -- except for a gang's parent and child, alive at the same time for a moment, whose starts may share a GT block
+// (left child: same start; right child: when the left one is tiny): hence the depth-parity bit.  Queue-mode segments
+// are finished before their children exist and use parity 0.
+__device__ __forceinline__ uint32_t state_index(uint32_t start, uint32_t par) { return 2u * (start / GT) + (par & 1u); }
 
-template <class T> __device__ __forceinline__ void create_big(const BuildParams<T>& P, const BTask<T>& t) {
+template <class T> __device__ __forceinline__ void init_state(BigSeg<T>* B) {
     using Tr = Traits<T>;
-    BigSeg<T>* B = P.big + t.start / TILE;
-    const uint32_t tiles = (t.count + TILE - 1) / TILE;
     const uint32_t lane = lane_id();
     for (int e = lane; e < 72; e += 32) __stcg(&B->keys[e], key_is_min<T>(e) ? Tr::KEY_POS_INF : Tr::KEY_NEG_INF);
     if (lane < 6) __stcg(&B->cnt[lane], 0u);
-    if (lane == 6) __stcg(&B->tiles, tiles);
+    if (lane == 6) atomicAdd(&B->epoch, 1u);      // tells a straggler still polling the slot's previous barrier that it is over
     if (lane == 7) __stcg(&B->bin_done, 0u);
     if (lane == 8) __stcg(&B->scat_done, 0u);
+}
+
+template <class T> __device__ __forceinline__ void create_big(const BuildParams<T>& P, const BTask<T>& t) {
+    const uint32_t sid = state_index(t.start, 0u);
+    const uint32_t tiles = (t.count + TILE - 1) / TILE;
+    init_state(P.big + sid);
     __syncwarp();            // push_tiles fences (every lane) before it publishes: the stores above are covered
-    push_tiles(P, KIND_BIN, t.start / TILE, tiles, t);
+    push_tiles(P, KIND_BIN, sid, tiles, t);
+}
+
+// A gang takes the segment if enough co-resident warps are left in the budget: one warp per GT shapes, all of them
+// spinning on the segment's two barriers, so the reservation is what keeps the queue live.
+template <class T> __device__ __forceinline__ bool try_create_gang(const BuildParams<T>& P, const BTask<T>& t) {
+    if (P.gang_budget == 0u || t.count < GANG_MIN) return false;
+    const uint32_t tiles = t.count / GT;
+    uint32_t ok = 0;
+    if (lane_id() == 0) {
+        const uint32_t used = atomicAdd(&P.ctl->gang_used, tiles);
+        ok = used + tiles <= P.gang_budget ? 1u : 0u;
+        if (!ok) atomicSub(&P.ctl->gang_used, tiles);
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) return false;
+    init_state(P.big + state_index(t.start, 0u));
+    __syncwarp();
+    push_tiles(P, KIND_GANG, 0u, tiles, t);
+    return true;
 }
 
 template <class T>
 __device__ __forceinline__ void dispatch_children(const BuildParams<T>& P, BTask<T> ch[2], int nc) {
     for (int i = 0; i < nc; ++i) {
-        if (ch[i].count > (uint32_t)TILE) create_big(P, ch[i]);
+        if (ch[i].count > (uint32_t)TILE) { if (!try_create_gang(P, ch[i])) create_big(P, ch[i]); }
         else push_seg(P, ch[i]);
     }
+}
+
+
+// ---- in-warp subtree: <= 32 shapes, one per lane, whole levels at a time ------------------------------------------------
+// Below ~32 shapes a warp per node is 3 us of dependent round trips for a handful of shapes, and that -- not the top of
+// the tree -- is most of the nodes.  Here the range is loaded ONCE and every level handles all of its nodes together,
+// in registers, with no bins at all: the shapes of a node are first partitioned by bucket (stable, ballots), so that
+// candidate split s is a PREFIX of the node's lanes; a segmented prefix scan and a segmented suffix scan of the 12 keys
+// then hold, at every bucket boundary, exactly the two Bucket::join_bucket chains the reference folds
+// (bvh_node.rs:231-235; min/max are associative and commutative, the result is the same bits).  Empty buckets make
+// consecutive candidates identical, and the reference's strict `<` keeps the first: one evaluation per boundary and
+// "lowest lane wins" is the same choice.  The index arrays are not written: they are scratch, leaves carry the shape.
+template <class T> __device__ __forceinline__ typename Traits<T>::Key shfl_key_up(typename Traits<T>::Key v, uint32_t d) { return __shfl_up_sync(0xffffffffu, v, d); }
+template <class T> __device__ __forceinline__ typename Traits<T>::Key shfl_key_down(typename Traits<T>::Key v, uint32_t d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+template <class T>
+__device__ void process_subtree(const BuildParams<T>& P, WarpScratch<T>* ws, const BTask<T>& t, uint32_t& leaves) {
+    using Tr = Traits<T>;
+    using Key = typename Tr::Key;
+    const uint32_t lane = lane_id();
+    const uint32_t lt = lanemask_lt();
+    const T K = sub_rn(T(6), T(0.01));
+    // the shape in this lane
+    uint32_t id = 0;
+    T mn[3] = {T(0), T(0), T(0)}, mx[3] = {T(0), T(0), T(0)};
+    // the node it belongs to (identical in all lanes of the node; scount == 0: lane is done)
+    uint32_t snode = t.node, sparent = t.parent_buf & 0x7FFFFFFFu, sstart = 0, scount = lane < t.count ? t.count : 0u;
+    T ab[6], cb[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { ab[k] = t.ab[k]; cb[k] = t.cb[k]; }
+    if (lane < t.count) {
+        id = __ldcg(P.idx[t.parent_buf >> 31] + t.start + lane);
+        load_aabb(P.aabb + id, mn, mx);
+    }
+    while (__any_sync(0xffffffffu, scount >= 2u)) {
+        const bool active = scount >= 2u;
+        // ---- bucket (bvh_node.rs:204-222) or position half (bvh_node.rs:114-124) ----
+        int axis = 0;
+        T ext = sub_rn(cb[3], cb[0]), cbmin = cb[0];
+        { const T sy = sub_rn(cb[4], cb[1]), sz = sub_rn(cb[5], cb[2]);
+          if (sy > ext) { axis = 1; ext = sy; cbmin = cb[1]; }
+          if (sz > ext) { axis = 2; ext = sz; cbmin = cb[2]; } }
+        const bool degenerate = ext < Tr::eps();
+        int b = 0;
+        if (active) {
+            if (degenerate) {
+                b = (lane - sstart) < scount / 2 ? 0 : 1;
+            } else {
+                const T ca = center1(axis == 0 ? mn[0] : (axis == 1 ? mn[1] : mn[2]), axis == 0 ? mx[0] : (axis == 1 ? mx[1] : mx[2]));
+                b = (int)mul_rn(div_rn(sub_rn(ca, cbmin), ext), K);
+                b = b < 0 ? 0 : (b > 5 ? 5 : b);
+            }
+        }
+        // ---- stable partition by bucket inside each node (bvh_node.rs:250-272) ----
+        const uint32_t segmask = !active ? 0u : ((scount >= 32u ? 0xffffffffu : ((1u << scount) - 1u)) << sstart);
+        uint32_t dest = lane;
+        {
+            uint32_t below = 0, rank = 0;
+#pragma unroll
+            for (int bb = 0; bb < 6; ++bb) {
+                const uint32_t m = __ballot_sync(0xffffffffu, active && b == bb) & segmask;
+                if (bb < b) below += __popc(m);
+                if (bb == b) rank = __popc(m & lt);
+            }
+            if (active) dest = sstart + below + rank;
+        }
+        __syncwarp();
+        {
+            Staged<T>& d = ws->stage[dest];
+            d.id = id; d.b = b;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { d.mn[k] = mn[k]; d.mx[k] = mx[k]; }
+        }
+        __syncwarp();
+        {
+            const Staged<T>& d = ws->stage[lane];
+            id = d.id; b = d.b;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { mn[k] = d.mn[k]; mx[k] = d.mx[k]; }
+        }
+        // ---- segmented scans: Pk = join of the node's lanes up to here, Sk = from here on ----
+        T Pk[12], Sk[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const T c = center1(mn[k], mx[k]);
+            Pk[k] = mn[k]; Pk[3 + k] = mx[k]; Pk[6 + k] = c; Pk[9 + k] = c;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Sk[k] = Pk[k];
+        const uint32_t send = sstart + scount;
+        const uint32_t longest = __reduce_max_sync(0xffffffffu, active ? scount : 0u);     // scan steps: log2 of the longest node
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            if (d >= longest) break;
+            const bool okp = active && lane >= sstart + d, oks = active && lane + d < send;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const T up = __shfl_up_sync(0xffffffffu, Pk[k], d), dn = __shfl_down_sync(0xffffffffu, Sk[k], d);
+                if (key_is_min<T>(k)) { if (okp) Pk[k] = min_t(up, Pk[k]); if (oks) Sk[k] = min_t(dn, Sk[k]); }
+                else                  { if (okp) Pk[k] = max_t(up, Pk[k]); if (oks) Sk[k] = max_t(dn, Sk[k]); }
+            }
+        }
+        // ---- candidate boundaries: between this lane and the next, where the bucket changes ----
+        const int b_next = __shfl_down_sync(0xffffffffu, b, 1);
+        const uint32_t o1 = lane - sstart + 1u;                     // left count of the boundary after this lane
+        const bool cand = active && o1 < scount && (degenerate ? o1 == scount / 2 : b_next != b);
+        T Rn[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Rn[k] = __shfl_down_sync(0xffffffffu, Sk[k], 1);
+        T cost = Tr::inf();
+        if (cand) {
+            cost = div_rn(add_rn(mul_rn((T)o1, surface_area(Pk, Pk + 3)), mul_rn((T)(scount - o1), surface_area(Rn, Rn + 3))),
+                          surface_area(ab, ab + 3));                // bvh_node.rs:236-238
+        }
+        // first-wins argmin of the node's candidates (bvh_node.rs:239-246) on order-preserving keys; a candidate only
+        // counts if cost < +inf (NaN never does)
+        const bool valid = cand && cost < Tr::inf();
+        const Key ck = valid ? f2key(cost) : ~Key(0);
+        {
+            Key m = ck;
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) {
+                if (d >= longest) break;
+                const Key up = shfl_key_up<T>(m, d);
+                if (active && lane >= sstart + d) m = up < m ? up : m;
+            }
+            const uint32_t lastl = active ? send - 1u : lane;
+            m = __shfl_sync(0xffffffffu, m, lastl);
+            const uint32_t win = __ballot_sync(0xffffffffu, valid && ck == m) & segmask;
+            const uint32_t cm = __ballot_sync(0xffffffffu, cand) & segmask;
+            bool found = win != 0u;
+            uint32_t q = found ? (uint32_t)__ffs(win) - 1u : (cm ? (uint32_t)__ffs(cm) - 1u : sstart);
+            if (degenerate) found = true;                            // the half split is unconditional; q is its only candidate
+            if (!active) q = lane;
+            // ---- children (bvh_node.rs:126-151): lane q holds the left join, lane q + 1 the right one ----
+            const uint32_t nl = q - sstart + 1u;
+            if (active && lane == q) {
+                typename Tr::Node nd;
+                nd.parent = sparent; nd.child_l = snode + 1u; nd.child_r = snode + 2u * nl; nd.shape = scount;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    nd.l_aabb.min[k] = found ? Pk[k] : Tr::inf();  nd.l_aabb.max[k] = found ? Pk[3 + k] : -Tr::inf();
+                    nd.r_aabb.min[k] = found ? Rn[k] : Tr::inf();  nd.r_aabb.max[k] = found ? Rn[3 + k] : -Tr::inf();
+                }
+                store_struct_cg(P.nodes + snode, nd);
+                P.node_start[snode] = t.start + sstart;
+            }
+            const bool right = lane > q;
+            const uint32_t srcl = !active ? lane : (right ? q + 1u : q);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const T pub = lane == q ? Pk[k] : Sk[k];
+                const T got = __shfl_sync(0xffffffffu, pub, srcl);
+                const T v = found ? got : (key_is_min<T>(k) ? Tr::inf() : -Tr::inf());
+                if (k < 6) ab[k] = v; else cb[k - 6] = v;
+            }
+            if (active) {
+                sparent = snode;
+                snode = right ? snode + 2u * nl : snode + 1u;
+                const uint32_t ccount = right ? scount - nl : nl;
+                sstart = right ? q + 1u : sstart;
+                scount = ccount;
+                if (ccount == 1u) {                                  // bvh_node.rs:95-104
+                    write_leaf(P, snode, sparent, id, t.start + lane);
+                    scount = 0;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    leaves += t.count;
 }
 
 // ---- SEG: one warp owns the whole range; depth-first continuation ------------------------------------
@@ -355,6 +596,14 @@ __device__ void process_seg(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T
     using Tr = Traits<T>;
     int sp = 0;
     for (;;) {
+        if (t.count <= SUBW) {
+            process_subtree(P, ws, t, leaves);
+            if (sp == 0) return;
+            --sp;
+            t = ws->stack[sp];
+            __syncwarp();
+            continue;
+        }
         int axis; T ext, cbmin;
         split_axis(t, axis, ext, cbmin);
         const bool degenerate = ext < Tr::eps();            // bvh_node.rs:114
@@ -518,6 +767,148 @@ __device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws
     finish_big(P, ws, t, nl, true, leaves);
 }
 
+
+// ---- GANG: the top of the tree, level by level, by a set of co-resident warps -----------------------------------------
+// Queue hops (publish -> poll -> pop, ~3 us each, two per level plus the last-tile epilogues) dominate the latency of
+// the first levels, where there is one segment and nothing else to do.  A gang is `count / GT` warps that stay with
+// the segment: each bins its own GT shapes, ALL of them evaluate the split after barrier 1 (redundantly -- no
+// broadcast), each computes the stable-partition prefix of its own tile from the per-tile counts and scatters it, and
+// after barrier 2 the warps re-map themselves onto the children: warp k takes tile k of the left child while
+// k < tiles(left), else tile k - tiles(left) of the right child, else it leaves.  floor() tiling makes
+// tiles(left) + tiles(right) <= tiles, so a gang only ever shrinks and never waits for a warp that is not running.
+template <class T>
+__device__ __forceinline__ bool gang_barrier(const BuildParams<T>& P, uint32_t* ctr, uint32_t tiles, const uint32_t* epoch, uint32_t e0) {
+    __threadfence();
+    __syncwarp();
+    uint32_t ok = 1;
+    if (lane_id() == 0) {
+        atomicAdd(ctr, 1u);
+        uint32_t spins = 0, ns = 32;
+        // The state slot is recycled two levels down (same start, same node parity) by warps that may be that far ahead
+        // of this one once the barrier has opened: a changed epoch means exactly that.
+        while (ld_relaxed(ctr) < tiles && ld_relaxed(epoch) == e0) {
+            if ((++spins & 63u) == 0u) {
+                if (ld_relaxed(&P.ctl->error) != 0u) { ok = 0; break; }
+                if ((spins & 4095u) == 0u &&
+                    global_timer_ns() - *(volatile unsigned long long*)&P.ctl->t_start > P.timeout_ns) {
+                    atomicExch(&P.ctl->error, (uint32_t)BVHGPU_ERR_TIMEOUT);
+                    ok = 0;
+                    break;
+                }
+            }
+            __nanosleep(ns);
+            if (ns < 256) ns <<= 1;                  // hundreds of warps poll one line: back off
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __threadfence();
+    return ok != 0u;
+}
+
+template <class T>
+__device__ __forceinline__ void make_child(BTask<T>& c, const WarpScratch<T>* ws, const BTask<T>& t, int side, uint32_t nl, uint32_t nbuf) {
+    c.start = side ? t.start + nl : t.start;
+    c.count = side ? t.count - nl : nl;
+    c.node = side ? t.node + 2 * nl : t.node + 1;
+    c.parent_buf = t.node | (nbuf << 31);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { c.ab[k] = ws->child[side * 12 + k]; c.cb[k] = ws->child[side * 12 + 6 + k]; }
+}
+
+template <class T>
+__device__ void process_gang(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T> t, uint32_t k, uint32_t& leaves) {
+    using Tr = Traits<T>;
+    const uint32_t lane = lane_id();
+    for (uint32_t par = 0;; par ^= 1u) {
+        const uint32_t tiles = t.count / GT;
+        BigSeg<T>* B = P.big + state_index(t.start, par);
+        int axis; T ext, cbmin;
+        split_axis(t, axis, ext, cbmin);
+        const bool degenerate = ext < Tr::eps();
+        const uint32_t buf = t.parent_buf >> 31;
+        const uint32_t p0 = t.start + k * GT;
+        const uint32_t p1 = k + 1 == tiles ? t.start + t.count : p0 + GT;
+        unsigned long long tr0 = 0;
+        if (P.trace && k == 0) tr0 = global_timer_ns();
+        zero_bins(ws);
+        uint32_t cid; int cb;
+        bin_range(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !degenerate, cid, cb);
+        for (int e = lane; e < 72; e += 32) {
+            const typename Tr::Key v = ws->keys[e];
+            if (key_is_min<T>(e)) { if (v != Tr::KEY_POS_INF) atomicMin(&B->keys[e], v); }
+            else                  { if (v != Tr::KEY_NEG_INF) atomicMax(&B->keys[e], v); }
+        }
+        if (lane < 6) {
+            const uint32_t c = ws->cnt[lane];
+            __stcg(&P.tilecnt[tile_slot(p0, k == 0) * 8 + lane], c);
+            if (c) atomicAdd(&B->cnt[lane], c);
+        }
+        uint32_t e0 = 0;
+        if (lane == 0) e0 = ld_relaxed(&B->epoch);
+        unsigned long long tr1 = 0, tr2 = 0, tr3 = 0;
+        if (P.trace && k == 0) tr1 = global_timer_ns();
+        if (!gang_barrier(P, &B->bin_done, tiles, &B->epoch, e0)) return;
+        if (P.trace && k == 0) tr2 = global_timer_ns();
+        // ---- every warp: the segment's buckets -> the split ----
+        for (int e = lane; e < 72; e += 32) ws->keys[e] = __ldcg(&B->keys[e]);
+        if (lane < 6) ws->cnt[lane] = __ldcg(&B->cnt[lane]);
+        __syncwarp();
+        const uint32_t nl = split_eval(ws, t.ab, degenerate);
+        const uint32_t nr = t.count - nl;
+        const uint32_t tL = nl >= GANG_MIN ? nl / GT : 0u, tR = nr >= GANG_MIN ? nr / GT : 0u;
+        const uint32_t nbuf = degenerate ? buf : (buf ^ 1u);
+        if (k == 0) {                           // children's barrier / bucket state, published by barrier 2
+            if (tL) init_state(P.big + state_index(t.start, par ^ 1u));
+            if (tR) init_state(P.big + state_index(t.start + nl, par ^ 1u));
+        }
+        if (!degenerate) {
+            // exclusive prefix of the bucket counts of tiles 0..k-1: what makes the multi-warp partition stable
+            uint32_t pre[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+            for (uint32_t j = lane; j < k; j += 32) {
+                const uint32_t sj = tile_slot(t.start + j * GT, j == 0);
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
+                const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
+                pre[0] += a.x; pre[1] += a.y; pre[2] += a.z; pre[3] += a.w; pre[4] += c.x; pre[5] += c.y;
+            }
+            uint32_t base[6];
+            uint32_t run = t.start;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                uint32_t v = pre[b];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                base[b] = run + v;
+                run += ws->cnt[b];
+            }
+            scatter_range(P, P.idx[buf], P.idx[buf ^ 1u], p0, p1, base, false, 0u, 0);
+        }
+        if (P.trace && k == 0) tr3 = global_timer_ns();
+        if (!gang_barrier(P, &B->scat_done, tiles, &B->epoch, e0)) return;
+        if (P.trace && k == 0 && lane == 0) {
+            const uint32_t slot = P.trace_cap - 1u - atomicAdd(&P.ctl->gang_trace, 2u);
+            const unsigned long long base = *(volatile unsigned long long*)&P.ctl->t_start;
+            P.trace[slot] = make_uint4((4u << 28) | tiles, t.count, (uint32_t)(tr0 - base), (uint32_t)(global_timer_ns() - base));
+            P.trace[slot - 1] = make_uint4((5u << 28) | tiles, (uint32_t)(tr1 - base), (uint32_t)(tr2 - base), (uint32_t)(tr3 - base));
+        }
+        if (k + 1 == tiles) {                   // the closer: node, leaves, SEG children, give back the warps that leave
+            BTask<T> ch[2];
+            const int nc = finish_node(P, ws, t, nl, !degenerate, ch, leaves);
+            for (int i = 0; i < nc; ++i)
+                if (ch[i].count < GANG_MIN) push_seg(P, ch[i]);
+            if (lane == 0 && tiles > tL + tR) atomicSub(&P.ctl->gang_used, tiles - tL - tR);
+        }
+        if (k < tL) {
+            BTask<T> c; make_child(c, ws, t, 0, nl, nbuf); t = c;
+        } else if (k < tL + tR) {
+            BTask<T> c; make_child(c, ws, t, 1, nl, nbuf); t = c; k -= tL;
+        } else {
+            return;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- the persistent kernel -------------------------------------------------------------------------
 template <class T>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParams<T> P) {
@@ -534,7 +925,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParam
             for (;;) {
                 // relaxed poll: an acquire load would invalidate this SM's whole L1 (CCTL.IVALL) on every spin
                 if (ld_relaxed(seq) == ticket + 1u) break;
-                if ((spins & 3u) == 0u) {
+                if ((spins & 7u) == 7u) {
                     if (ld_relaxed(&P.ctl->leaves_done) >= P.n || ld_relaxed(&P.ctl->error) != 0u) { stop = 1; break; }
                 }
                 if ((++spins & 1023u) == 0u) {
@@ -558,7 +949,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParam
         if (P.trace) tr0 = global_timer_ns();
         if (s.kind == KIND_SEG) process_seg(P, ws, s.t, leaves);
         else if (s.kind == KIND_BIN) process_bin_tile(P, ws, s.t, s.a, s.b, leaves);
-        else process_scatter_tile(P, ws, s.t, s.a, s.b, leaves);
+        else if (s.kind == KIND_SCATTER) process_scatter_tile(P, ws, s.t, s.a, s.b, leaves);
+        else process_gang(P, ws, s.t, s.b, leaves);
         if (P.trace && lane == 0 && ticket < P.trace_cap) {
             const unsigned long long base = *(volatile unsigned long long*)&P.ctl->t_start;
             P.trace[ticket] = make_uint4((s.kind << 28) | (s.kind == KIND_SEG ? s.t.count : s.b), s.kind == KIND_SEG ? s.t.node : s.t.count,
@@ -758,6 +1150,8 @@ __global__ void init_keys_kernel(typename Traits<T>::Key* rootkeys, BuildCtl* ct
     if (threadIdx.x == 0) {
         ctl->head = ctl->tail = ctl->leaves_done = ctl->error = 0;
         ctl->small_count = 0;
+        ctl->gang_used = 0;
+        ctl->gang_trace = 0;
         ctl->t_start = 0;
         status->error = status->nan_found = status->tickets = status->leaves_done = 0;
     }
@@ -774,7 +1168,7 @@ template <class T> __global__ void init_root_kernel(BuildParams<T> P) {
         if (lane_id() == 0) { P.ctl->error = (uint32_t)BVHGPU_ERR_NAN; }
         return;
     }
-    if (t.count > (uint32_t)TILE) create_big(P, t); else push_seg(P, t);
+    if (t.count > (uint32_t)TILE) { if (!try_create_gang(P, t)) create_big(P, t); } else push_seg(P, t);
 }
 
 template <class T> __global__ void single_leaf_kernel(BuildParams<T> P) {
@@ -849,7 +1243,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     P.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     const uint32_t qcap = next_pow2(std::max<uint64_t>(n, 1024) * 2);
     P.qmask = qcap - 1;
-    const size_t nbig = (size_t)n / TILE + 2;
+    const size_t nbig = 2 * ((size_t)n / GT + 2);
     uint32_t *idx0 = nullptr, *idx1 = nullptr;
     BVH_TRY(dalloc_t(ctx, &idx0, n));
     BVH_TRY(dalloc_t(ctx, &idx1, n));
@@ -857,13 +1251,13 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     BVH_TRY(dalloc_t(ctx, &P.q, qcap));
     BVH_TRY(dalloc_t(ctx, &P.qseq, qcap));
     BVH_TRY(dalloc_t(ctx, &P.big, nbig));
-    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 2 * 8));
+    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 8));
     BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
     BVH_TRY(dalloc_t(ctx, &P.rootkeys, 12));
     // Deferring the bottom of the tree to the thread-per-range kernel adds that kernel's own latency (~0.1-0.4 ms tail) but
     // removes most warp-per-node work: measured slower below ~0.5 M shapes (120 k: 0.62 -> 0.67 ms), faster above
     // (1.2 M f32: 3.33 -> 2.32 ms, 10 M f64: 48 -> 28 ms).
-    P.small_max = (ctx->build_small < 0 ? n >= 400000u : ctx->build_small != 0) ? SMALL : 0u;
+    P.small_max = (ctx->build_small > 0) ? SMALL : 0u;
     BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
     P.idx[0] = idx0;
     P.idx[1] = idx1;
@@ -884,17 +1278,29 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         ctx->launches++;
     } else {
         BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
-        init_root_kernel<T><<<1, 32, 0, st>>>(P);
-        ctx->launches++;
         int occ = 1;
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+        const size_t dsm = 0;
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, dsm));
         if (occ < 1) occ = 1;
         // enough warps that every one has ~16 shapes of work, capped by what is co-resident
         uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         if (want < 1) want = 1;
         const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
+        // gangs may hold at most half of the co-resident warps: the other half keeps the task queue draining
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        P.gang_budget = (ctx->build_gang != 0 && coop) ? (uint32_t)grid * WARPS_PER_CTA / 2u : 0u;
+        init_root_kernel<T><<<1, 32, 0, st>>>(P);
+        ctx->launches++;
         if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
-        build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+        if (P.gang_budget) {
+            // gangs spin on each other: the grid must be co-resident as a whole, which is what a cooperative launch
+            // guarantees (two concurrent builds are then serialised by the scheduler instead of starving each other)
+            void* kargs[] = {&P};
+            BVH_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)build_kernel<T>, dim3(grid), dim3(WARPS_PER_CTA * 32), kargs, dsm, st));
+        } else {
+            build_kernel<T><<<grid, WARPS_PER_CTA * 32, dsm, st>>>(P);
+        }
         ctx->launches++;
         if (P.small_max) {
             const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
@@ -939,7 +1345,7 @@ int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletS
     BVH_TRY(dalloc_t(ctx, &P->big, 2));
     BVH_TRY(dalloc_t(ctx, &P->tilecnt, 32));
     BVH_TRY(dalloc_t(ctx, &P->ctl, 1));
-    P->small_max = (ctx->build_small < 0 ? n >= 400000u : ctx->build_small != 0) ? SMALL : 0u;
+    P->small_max = (ctx->build_small > 0) ? SMALL : 0u;
     BVH_TRY(dalloc_t(ctx, &P->small, P->small_max ? (size_t)n / 2 + 1 : 1));
     BVH_CUDA_TRY(cudaMemsetAsync(P->qseq, 0, sizeof(uint32_t) * qcap, st));
     BVH_CUDA_TRY(cudaMemsetAsync(P->ctl, 0, sizeof(BuildCtl), st));
@@ -955,12 +1361,13 @@ int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
     const uint32_t n = tree->n;
     treelet_start_kernel<T><<<1, 32, 0, st>>>(P->ctl);
     int occ = 1;
-    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+    const size_t dsm = 0;
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, dsm));
     if (occ < 1) occ = 1;
     uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (want < 1) want = 1;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
-    build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(*P);
+    build_kernel<T><<<grid, WARPS_PER_CTA * 32, dsm, st>>>(*P);
     ctx->launches += 2;
     if (P->small_max) {
         const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);

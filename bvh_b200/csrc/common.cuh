@@ -83,6 +83,13 @@ __device__ __forceinline__ double key2f(unsigned long long k) {
     return __longlong_as_double((long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
 }
 
+// min / max in T.  On non-NaN inputs (NaN shapes are rejected up front) FMNMX / DMNMX agree bit for bit with min / max
+// of the order-preserving keys, including -0 < +0 (PTX: min(+0, -0) = -0).
+__device__ __forceinline__ float min_t(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double min_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b); }
+
 // ---- exact (non-contracted) arithmetic in T ----
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
@@ -145,15 +152,18 @@ __device__ __forceinline__ void load_aabb(const DAabbD* p, double mn[3], double 
 // warp-wide min / max of keys (u32: one REDUX instruction; u64: shuffles)
 __device__ __forceinline__ uint32_t warp_min_key(uint32_t k) { return __reduce_min_sync(0xffffffffu, k); }
 __device__ __forceinline__ uint32_t warp_max_key(uint32_t k) { return __reduce_max_sync(0xffffffffu, k); }
+// u64: two REDUX passes -- the high words, then the low words of the lanes that hold the winning high word
 __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o); k = t < k ? t : k; }
-    return k;
+    const uint32_t hi = (uint32_t)(k >> 32);
+    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? (uint32_t)k : 0xFFFFFFFFu);
+    return ((unsigned long long)mh << 32) | ml;
 }
 __device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o); k = t > k ? t : k; }
-    return k;
+    const uint32_t hi = (uint32_t)(k >> 32);
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? (uint32_t)k : 0u);
+    return ((unsigned long long)mh << 32) | ml;
 }
 #endif  // __CUDACC__
 

@@ -20,6 +20,19 @@ for k, name in enumerate(["SEG", "BIN", "SCATTER"]):
     if m.any():
         d = t1[m] - t0[m]
         print(f"{name:8s} n={m.sum():7d} dur mean {d.mean():7.2f} med {np.median(d):7.2f} max {d.max():7.2f} us | first start {t0[m].min():7.1f} last end {t1[m].max():7.1f}")
+m = kind == 4
+if m.any():
+    print("gang levels (warp 0 of each segment): count tiles start | bin | wait1 | split+scatter | wait2 | = dur")
+    i4 = np.nonzero(m)[0]
+    order = i4[np.argsort(t0[i4])]
+    for i in order[:40]:
+        ph = t[i - 1]                      # the kind-5 companion entry precedes it in the buffer
+        a, e = t0[i], t1[i]
+        b1, w1, s2 = ph[1] / 1e3, ph[2] / 1e3, ph[3] / 1e3
+        print(f"   {t[i,1]:8d} {cnt[i]:5d} {a:8.1f} | {b1-a:5.1f} | {w1-b1:5.1f} | {s2-w1:5.1f} | {e-s2:5.1f} | {e-a:6.1f}")
+m = kind == 3
+if m.any():
+    print(f"GANG memberships n={m.sum()} first start {t0[m].min():.1f} last end {t1[m].max():.1f}")
 # big segments, keyed by their shape count (one generation each): BIN / SCATTER phase windows
 segs = {}
 for k, c, a, b_ in zip(kind, t[:, 1], t0, t1):
@@ -28,6 +41,7 @@ for k, c, a, b_ in zip(kind, t[:, 1], t0, t1):
 print("count   tiles  BIN first-start .. last-end (longest tile) | SCATTER first-start .. last-end (longest)")
 for c in sorted(set(c for c, _ in segs), reverse=True)[:28]:
     bi, sc = segs.get((c, 1)), segs.get((c, 2))
+    if bi is None: continue
     line = f"{c:7d} {bi[2]:5d}  BIN {bi[0]:7.1f} .. {bi[1]:7.1f} ({bi[3]:5.1f})"
     if sc: line += f" | SCAT {sc[0]:7.1f} .. {sc[1]:7.1f} ({sc[3]:5.1f})"
     print(line)
@@ -38,3 +52,17 @@ for lo, hi in [(2, 8), (8, 32), (32, 64), (64, 128), (128, 257)]:
     if mm.any():
         print(f"[{lo},{hi}) n={mm.sum()} dur {np.mean(t1[mm]-t0[mm]):.1f}us  ", end="")
 print()
+
+# concurrency over time: tasks in flight (= busy warps) per 20 us bucket
+mt = (kind <= 3)
+edges = np.arange(0, t1[mt].max() + 20, 20.0)
+busy = np.zeros(len(edges))
+for a, b_ in zip(t0[mt], t1[mt]):
+    i0, i1 = int(a // 20), int(b_ // 20)
+    for i in range(i0, i1 + 1):
+        lo, hi = max(a, edges[i]), min(b_, edges[i] + 20)
+        busy[i] += max(0.0, hi - lo) / 20.0
+print("busy warps per 20us:", " ".join(f"{int(x)}" for x in busy))
+ms = kind == 0
+starts = np.histogram(t0[ms], bins=edges)[0]
+print("SEG starts per 20us:", " ".join(str(x) for x in starts))
