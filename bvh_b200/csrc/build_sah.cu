@@ -51,6 +51,8 @@ template <class T> struct BuildParams {
     uint4* trace;                   // optional task log (BVHGPU_TRACE=file): {kind<<28|count, node/sid, t0_ns, t1_ns}
     uint32_t trace_cap;
     uint32_t gang_budget;           // warps that gangs may hold at any time (0 = gang mode off)
+    uint32_t sdiv;                  // granularity of the multi-warp segment state / tile-count slots: GT with gangs, else TILE
+    uint32_t opt_subtree;           // ranges <= 32 shapes: in-register subtree builder (1) or warp-per-node (0)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -88,9 +90,13 @@ template <class T> __device__ __forceinline__ void split_axis(const BTask<T>& t,
 }
 
 // Bucket assignment + Bucket::add_aabb (bvh_node.rs:204-222, utils.rs:78-83) for positions [p0,p1); leaves the six
-// buckets of the range in ws->keys / ws->cnt.  No shared-memory atomics (an ATOMS costs the SM 64 cycles per warp and 13
-// of them per 32 shapes made the binning the longest phase of every level): the lanes of a chunk group combine their
-// own keys per bucket, one REDUX per (bucket, key) folds the warp, and lane k keeps key k of every bucket in registers.
+// buckets of the range in ws->keys / ws->cnt.  Two flavours, chosen by regime (measured, tools/build_sweep.py):
+//   bin_range         -- no shared-memory atomics: the lanes of a chunk group combine their own keys per bucket, one
+//                        REDUX per (bucket, key) folds the warp, lane k keeps key k of every bucket in registers.  More
+//                        instructions, shorter dependent chain: used by the GANG tiles, where a handful of warps per SM
+//                        sit on the critical path of a tree level (bin phase 8 -> 4.5 us).
+//   bin_range_atomic  -- 13 shared-memory atomics per shape; fewer instructions: used by SEG / queue tiles, where all
+//                        warps are busy and issue slots are what is scarce (1.2 M shapes: 2.05 ms vs 2.67 ms with REDUX).
 template <class T>
 __device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T>* ws, const uint32_t* __restrict__ src,
                                           uint32_t seg_start, uint32_t p0, uint32_t p1, int axis, T cbmin, T ext,
@@ -180,6 +186,62 @@ __device__ __forceinline__ void bin_range(const BuildParams<T>& P, WarpScratch<T
 #pragma unroll
         for (int bb = 1; bb < 6; ++bb) c = (int)lane == bb ? cnt[bb] : c;
         ws->cnt[lane] = c;
+    }
+    __syncwarp();
+}
+
+// The same with shared-memory atomics on ws->keys / ws->cnt (zeroed by the caller): fewer instructions, more LSU time.
+template <class T>
+__device__ __forceinline__ void bin_range_atomic(const BuildParams<T>& P, WarpScratch<T>* ws, const uint32_t* __restrict__ src,
+                                          uint32_t seg_start, uint32_t p0, uint32_t p1, int axis, T cbmin, T ext,
+                                          bool degenerate, uint32_t half, bool store_bkt, uint32_t& last_id, int& last_b) {
+    const uint32_t lane = lane_id();
+    const T K = sub_rn(T(6), T(0.01));                 // T::from(NUM_BUCKETS) - T::from(0.01), bvh_node.rs:214-215
+    constexpr int U = sizeof(T) == 8 ? 2 : 4;          // chunks in flight: index loads, then AABB gathers, then the math
+    for (uint32_t base = p0; base < p1; base += 32 * U) {
+        uint32_t id[U];
+        T mn[U][3], mx[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            id[u] = pos < p1 ? __ldcg(src + pos) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            if (pos < p1) load_aabb(P.aabb + id[u], mn[u], mx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t pos = base + 32 * u + lane;
+            if (base + 32 * u >= p1) break;            // warp-uniform
+            int b = 0;
+            if (pos < p1) {
+                T c[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[k] = center1(mn[u][k], mx[u][k]);
+                if (degenerate) {
+                    b = (pos - seg_start) < half ? 0 : 1;  // indices.split_at_mut(len / 2), bvh_node.rs:117
+                } else {
+                    const T ca = axis == 0 ? c[0] : (axis == 1 ? c[1] : c[2]);
+                    const T rel = div_rn(sub_rn(ca, cbmin), ext);
+                    b = (int)mul_rn(rel, K);               // to_usize(): truncation toward zero
+                    b = b < 0 ? 0 : (b > 5 ? 5 : b);       // inert for tight bounds; keeps memory safe
+                }
+                if (store_bkt) P.bkt[pos] = (uint8_t)b;
+                typename Traits<T>::Key* kb = ws->keys + b * 12;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    atomicMin(kb + k, f2key(mn[u][k]));
+                    atomicMax(kb + 3 + k, f2key(mx[u][k]));
+                    atomicMin(kb + 6 + k, f2key(c[k]));
+                    atomicMax(kb + 9 + k, f2key(c[k]));
+                }
+                atomicAdd(&ws->cnt[b], 1u);
+            }
+            last_id = id[u];
+            last_b = b;
+        }
     }
     __syncwarp();
 }
@@ -367,12 +429,12 @@ template <class T> __device__ __forceinline__ void push_tiles(const BuildParams<
     __syncwarp();
 }
 
-__device__ __forceinline__ uint32_t tile_slot(uint32_t p, bool first) { return 2u * (p / GT) + (first ? 1u : 0u); }
+__device__ __forceinline__ uint32_t tile_slot(uint32_t sdiv, uint32_t p, bool first) { return 2u * (p / sdiv) + (first ? 1u : 0u); }
 // Multi-warp segment state: live segments are >= GANG_MIN > GT shapes long and disjoint, so start / GT is unique among
 // them -- except for a gang's parent and child, alive at the same time for a moment, whose starts may share a GT block
 // (left child: same start; right child: when the left one is tiny): hence the depth-parity bit.  Queue-mode segments
 // are finished before their children exist and use parity 0.
-__device__ __forceinline__ uint32_t state_index(uint32_t start, uint32_t par) { return 2u * (start / GT) + (par & 1u); }
+__device__ __forceinline__ uint32_t state_index(uint32_t sdiv, uint32_t start, uint32_t par) { return 2u * (start / sdiv) + (par & 1u); }
 
 template <class T> __device__ __forceinline__ void init_state(BigSeg<T>* B) {
     using Tr = Traits<T>;
@@ -385,7 +447,7 @@ template <class T> __device__ __forceinline__ void init_state(BigSeg<T>* B) {
 }
 
 template <class T> __device__ __forceinline__ void create_big(const BuildParams<T>& P, const BTask<T>& t) {
-    const uint32_t sid = state_index(t.start, 0u);
+    const uint32_t sid = state_index(P.sdiv, t.start, 0u);
     const uint32_t tiles = (t.count + TILE - 1) / TILE;
     init_state(P.big + sid);
     __syncwarp();            // push_tiles fences (every lane) before it publishes: the stores above are covered
@@ -405,7 +467,7 @@ template <class T> __device__ __forceinline__ bool try_create_gang(const BuildPa
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     if (!ok) return false;
-    init_state(P.big + state_index(t.start, 0u));
+    init_state(P.big + state_index(P.sdiv, t.start, 0u));
     __syncwarp();
     push_tiles(P, KIND_GANG, 0u, tiles, t);
     return true;
@@ -596,7 +658,7 @@ __device__ void process_seg(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T
     using Tr = Traits<T>;
     int sp = 0;
     for (;;) {
-        if (t.count <= SUBW) {
+        if (t.count <= SUBW && P.opt_subtree) {
             process_subtree(P, ws, t, leaves);
             if (sp == 0) return;
             --sp;
@@ -610,9 +672,9 @@ __device__ void process_seg(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<T
         const uint32_t buf = t.parent_buf >> 31;
         const uint32_t p0 = t.start, p1 = t.start + t.count;
         const bool single = t.count <= 32;
-        zero_bins(ws);
         uint32_t cid = 0; int cb = 0;
-        bin_range(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !single && !degenerate, cid, cb);
+        zero_bins(ws);
+        bin_range_atomic(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !single && !degenerate, cid, cb);
         const uint32_t nl = split_eval(ws, t.ab, degenerate);
         if (!degenerate) {
             uint32_t base[6];
@@ -664,16 +726,16 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, co
     const uint32_t p0 = t.start + k * TILE;
     const uint32_t pend = t.start + t.count;
     const uint32_t p1 = p0 + TILE < pend ? p0 + TILE : pend;
-    zero_bins(ws);
     uint32_t cid; int cb;
-    bin_range(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !degenerate, cid, cb);
+    zero_bins(ws);
+    bin_range_atomic(P, ws, P.idx[buf], t.start, p0, p1, axis, cbmin, ext, degenerate, t.count / 2, !degenerate, cid, cb);
     // flush this tile's buckets into the segment's global buckets
     for (int e = lane; e < 72; e += 32) {
         const typename Tr::Key v = ws->keys[e];
         if (key_is_min<T>(e)) { if (v != Tr::KEY_POS_INF) atomicMin(&B->keys[e], v); }
         else                  { if (v != Tr::KEY_NEG_INF) atomicMax(&B->keys[e], v); }
     }
-    const uint32_t slot = tile_slot(p0, k == 0);
+    const uint32_t slot = tile_slot(P.sdiv, p0, k == 0);
     if (lane < 6) {
         const uint32_t c = ws->cnt[lane];
         __stcg(&P.tilecnt[slot * 8 + lane], c);
@@ -710,7 +772,7 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, co
         for (uint32_t q = 0; q < m; ++q) {
             const uint32_t j = lane * m + q;
             if (j < tiles) {
-                const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+                const uint32_t sj = tile_slot(P.sdiv, t.start + j * TILE, j == 0);
                 const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
                 const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
                 sum[0] += a.x; sum[1] += a.y; sum[2] += a.z; sum[3] += a.w; sum[4] += c.x; sum[5] += c.y;
@@ -727,7 +789,7 @@ __device__ void process_bin_tile(const BuildParams<T>& P, WarpScratch<T>* ws, co
         for (uint32_t q = 0; q < m; ++q) {
             const uint32_t j = lane * m + q;
             if (j < tiles) {
-                const uint32_t sj = tile_slot(t.start + j * TILE, j == 0);
+                const uint32_t sj = tile_slot(P.sdiv, t.start + j * TILE, j == 0);
                 const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
                 const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
                 __stcg(reinterpret_cast<uint4*>(P.tilecnt + sj * 8), make_uint4(run[0], run[1], run[2], run[3]));
@@ -749,7 +811,7 @@ __device__ void process_scatter_tile(const BuildParams<T>& P, WarpScratch<T>* ws
     const uint32_t p0 = t.start + k * TILE;
     const uint32_t pend = t.start + t.count;
     const uint32_t p1 = p0 + TILE < pend ? p0 + TILE : pend;
-    const uint32_t slot = tile_slot(p0, k == 0);
+    const uint32_t slot = tile_slot(P.sdiv, p0, k == 0);
     uint32_t base[6];
 #pragma unroll
     for (int b = 0; b < 6; ++b) base[b] = __ldcg(&B->base[b]) + __ldcg(&P.tilecnt[slot * 8 + b]);
@@ -821,7 +883,7 @@ __device__ void process_gang(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<
     const uint32_t lane = lane_id();
     for (uint32_t par = 0;; par ^= 1u) {
         const uint32_t tiles = t.count / GT;
-        BigSeg<T>* B = P.big + state_index(t.start, par);
+        BigSeg<T>* B = P.big + state_index(P.sdiv, t.start, par);
         int axis; T ext, cbmin;
         split_axis(t, axis, ext, cbmin);
         const bool degenerate = ext < Tr::eps();
@@ -840,7 +902,7 @@ __device__ void process_gang(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<
         }
         if (lane < 6) {
             const uint32_t c = ws->cnt[lane];
-            __stcg(&P.tilecnt[tile_slot(p0, k == 0) * 8 + lane], c);
+            __stcg(&P.tilecnt[tile_slot(P.sdiv, p0, k == 0) * 8 + lane], c);
             if (c) atomicAdd(&B->cnt[lane], c);
         }
         uint32_t e0 = 0;
@@ -858,15 +920,15 @@ __device__ void process_gang(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<
         const uint32_t tL = nl >= GANG_MIN ? nl / GT : 0u, tR = nr >= GANG_MIN ? nr / GT : 0u;
         const uint32_t nbuf = degenerate ? buf : (buf ^ 1u);
         if (k == 0) {                           // children's barrier / bucket state, published by barrier 2
-            if (tL) init_state(P.big + state_index(t.start, par ^ 1u));
-            if (tR) init_state(P.big + state_index(t.start + nl, par ^ 1u));
+            if (tL) init_state(P.big + state_index(P.sdiv, t.start, par ^ 1u));
+            if (tR) init_state(P.big + state_index(P.sdiv, t.start + nl, par ^ 1u));
         }
         if (!degenerate) {
             // exclusive prefix of the bucket counts of tiles 0..k-1: what makes the multi-warp partition stable
             uint32_t pre[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll 4
             for (uint32_t j = lane; j < k; j += 32) {
-                const uint32_t sj = tile_slot(t.start + j * GT, j == 0);
+                const uint32_t sj = tile_slot(P.sdiv, t.start + j * GT, j == 0);
                 const uint4 a = __ldcg(reinterpret_cast<const uint4*>(P.tilecnt + sj * 8));
                 const uint2 c = __ldcg(reinterpret_cast<const uint2*>(P.tilecnt + sj * 8 + 4));
                 pre[0] += a.x; pre[1] += a.y; pre[2] += a.z; pre[3] += a.w; pre[4] += c.x; pre[5] += c.y;
@@ -911,7 +973,7 @@ __device__ void process_gang(const BuildParams<T>& P, WarpScratch<T>* ws, BTask<
 
 // ---- the persistent kernel -------------------------------------------------------------------------
 template <class T>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) build_kernel(BuildParams<T> P) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, BUILD_MIN_CTAS) build_kernel(BuildParams<T> P) {
     __shared__ WarpScratch<T> wsall[WARPS_PER_CTA];
     WarpScratch<T>* ws = &wsall[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -1243,7 +1305,23 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     P.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
     const uint32_t qcap = next_pow2(std::max<uint64_t>(n, 1024) * 2);
     P.qmask = qcap - 1;
-    const size_t nbig = 2 * ((size_t)n / GT + 2);
+    // launch shape of the persistent kernel, and whether gangs will be used (they need finer-grained segment state)
+    int occ = 1;
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+    if (occ < 1) occ = 1;
+    // enough warps that every one has ~16 shapes of work, capped by what is co-resident
+    uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (want < 1) want = 1;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    // gangs may hold at most half of the co-resident warps: the other half keeps the task queue draining
+    P.gang_budget = (ctx->build_gang != 0 && coop) ? (uint32_t)grid * WARPS_PER_CTA / 2u : 0u;
+    // Gang warps spin instead of draining the queue: worth it only while the machine would otherwise idle, i.e. when
+    // the whole root fits one gang (measured at 1.2 M shapes: 2.7 ms without gangs, 4.5 ms with).
+    if (ctx->build_gang < 0 && (uint64_t)n / GT > P.gang_budget) P.gang_budget = 0;
+    P.sdiv = P.gang_budget ? GT : TILE;
+    const size_t nbig = 2 * ((size_t)n / P.sdiv + 2);
     uint32_t *idx0 = nullptr, *idx1 = nullptr;
     BVH_TRY(dalloc_t(ctx, &idx0, n));
     BVH_TRY(dalloc_t(ctx, &idx1, n));
@@ -1257,7 +1335,13 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
     // Deferring the bottom of the tree to the thread-per-range kernel adds that kernel's own latency (~0.1-0.4 ms tail) but
     // removes most warp-per-node work: measured slower below ~0.5 M shapes (120 k: 0.62 -> 0.67 ms), faster above
     // (1.2 M f32: 3.33 -> 2.32 ms, 10 M f64: 48 -> 28 ms).
-    P.small_max = (ctx->build_small > 0) ? SMALL : 0u;
+    // Bottom of the tree (measured, tools/build_sweep.py): f32 -- the in-register subtree builder everywhere (120 k:
+    // 0.51 -> 0.35 ms; 1.2 M: 2.05 ms, the same as deferring <= 16-shape ranges to the thread-per-range kernel).
+    // f64 -- 64-bit shuffles and DMNMX make the subtree builder the slower one (10 M: 36.7 ms vs 23.5 ms): large f64
+    // scenes defer to the thread-per-range kernel instead, whose own ~0.1-0.4 ms tail only pays off above ~0.4 M shapes.
+    const bool defer_small = ctx->build_small < 0 ? (sizeof(T) == 8 && n >= 400000u) : ctx->build_small != 0;
+    P.small_max = defer_small ? SMALL : 0u;
+    P.opt_subtree = ctx->build_subtree < 0 ? !defer_small : ctx->build_subtree != 0;
     BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
     P.idx[0] = idx0;
     P.idx[1] = idx1;
@@ -1278,18 +1362,7 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         ctx->launches++;
     } else {
         BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
-        int occ = 1;
         const size_t dsm = 0;
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, dsm));
-        if (occ < 1) occ = 1;
-        // enough warps that every one has ~16 shapes of work, capped by what is co-resident
-        uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        if (want < 1) want = 1;
-        const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
-        // gangs may hold at most half of the co-resident warps: the other half keeps the task queue draining
-        int coop = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        P.gang_budget = (ctx->build_gang != 0 && coop) ? (uint32_t)grid * WARPS_PER_CTA / 2u : 0u;
         init_root_kernel<T><<<1, 32, 0, st>>>(P);
         ctx->launches++;
         if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
@@ -1342,10 +1415,13 @@ int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletS
     BVH_TRY(dalloc_t(ctx, &P->bkt, n));
     BVH_TRY(dalloc_t(ctx, &P->q, qcap));
     BVH_TRY(dalloc_t(ctx, &P->qseq, qcap));
+    P->sdiv = TILE;
     BVH_TRY(dalloc_t(ctx, &P->big, 2));
     BVH_TRY(dalloc_t(ctx, &P->tilecnt, 32));
     BVH_TRY(dalloc_t(ctx, &P->ctl, 1));
-    P->small_max = (ctx->build_small > 0) ? SMALL : 0u;
+    const bool defer_small = ctx->build_small < 0 ? (sizeof(T) == 8 && n >= 400000u) : ctx->build_small != 0;
+    P->small_max = defer_small ? SMALL : 0u;
+    P->opt_subtree = ctx->build_subtree < 0 ? !defer_small : ctx->build_subtree != 0;
     BVH_TRY(dalloc_t(ctx, &P->small, P->small_max ? (size_t)n / 2 + 1 : 1));
     BVH_CUDA_TRY(cudaMemsetAsync(P->qseq, 0, sizeof(uint32_t) * qcap, st));
     BVH_CUDA_TRY(cudaMemsetAsync(P->ctl, 0, sizeof(BuildCtl), st));

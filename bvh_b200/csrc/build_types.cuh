@@ -7,6 +7,9 @@ namespace bvhb200 {
 
 constexpr int TILE = 512;              // shapes per tile task of a multi-warp segment (measured: 128 / 256 / 512 / 1024 -> 0.67 / 0.60 / 0.59 / 0.64 ms at 120 k)
 constexpr int WARPS_PER_CTA = 8;
+#ifndef BUILD_MIN_CTAS
+#define BUILD_MIN_CTAS 2
+#endif
 constexpr int LOCAL_STACK = 24;        // per-warp DFS stack (entries)
 constexpr uint32_t LOCAL_MAX = 6;      // right children up to this size stay on the warp's own stack; larger ones go to
                                        // the global queue: idle warps are plentiful, the critical path is what matters

@@ -411,6 +411,7 @@ BVH_EXPORT int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t valu
     if (!strcmp(name, "profile")) { ctx->profile = value; return BVHGPU_OK; }
     if (!strcmp(name, "build_small")) { ctx->build_small = value; return BVHGPU_OK; }
     if (!strcmp(name, "build_gang")) { ctx->build_gang = value; return BVHGPU_OK; }
+    if (!strcmp(name, "build_subtree")) { ctx->build_subtree = value; return BVHGPU_OK; }
     if (!strcmp(name, "traverse_persistent")) { ctx->traverse_persistent = value; return BVHGPU_OK; }
     set_error("set_option: unknown option '%s'", name);
     return BVHGPU_ERR_INVALID;

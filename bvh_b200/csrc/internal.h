@@ -44,6 +44,7 @@ struct bvhgpu_ctx {
     int64_t traverse_persistent = 2;   // 0: one ray per thread, 1: persistent refill kernel, 2: coherence probe decides on the device
     int walk_grid = 0;             // persistent grid size (computed once)
     int64_t build_gang = -1;       // exact builder: co-resident warp gangs for the top levels (-1 / 1 on, 0 off = queue tiles only)
+    int64_t build_subtree = -1;    // exact builder: in-register subtrees for ranges <= 32 shapes (-1 auto, 0 never, 1 always)
     int64_t build_small = -1;      // exact builder: defer ranges <= 16 shapes to the thread-per-range kernel (-1 auto by size, 0 never, 1 always)
     uint32_t* h_pinned = nullptr;  // small pinned read-back area (256 words)
     int64_t profile = 0;           // bracket dominant kernels with events

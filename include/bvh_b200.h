@@ -98,7 +98,10 @@ int bvhgpu_synchronize(bvhgpu_ctx* ctx);
 uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
 /* Tunables: "traverse_slots" (per-ray hit slots of the single-pass path, 0 = two-pass count/fill, -1 = auto),
  * "traverse_persistent" (0 = one ray per thread, 1 = persistent refill kernel, 2 = decided per batch by a coherence probe),
- * "build_small" (exact builder: finish ranges of <= 16 shapes with one thread each in a second kernel; -1 auto by size, 0 never, 1 always),
+ * "build_small" (exact builder: finish ranges of <= 16 shapes with one thread each in a second kernel; -1 auto by type and size, 0 never, 1 always),
+ * "build_subtree" (exact builder: build ranges of <= 32 shapes in registers, one warp per subtree; -1 auto, 0 never, 1 always),
+ * "build_gang" (exact builder: co-resident warp gangs walk the top levels behind device-wide barriers; -1 auto by size, 0 never, 1 always),
+ * -- every combination produces the same bits; the switches exist for measurement (tools/build_sweep.py) --
  * "profile" (1: bracket the dominant kernels with CUDA events, read back with bvhgpu_get_metric). */
 int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value);
 /* Measurements of the last profiled call on this context: "walk_ms" (traversal walk kernel),

@@ -520,6 +520,65 @@ def test_thread_per_range_kernel_forced(api, name, prec):
         ctx.set_option("build_small", -1)
 
 
+@pytest.mark.parametrize("small,subtree,gang", [(0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1), (1, 1, 1), (1, 0, 1)])
+@pytest.mark.parametrize("name,prec", [("cubes1000", "f32"), ("random5000", "f32"), ("points3000", "f32"), ("huge2000", "f32"), ("skew3000", "f32"),
+                                       ("random33", "f32"), ("random700", "f32"), ("line2000", "f32"), ("cubes200", "f64"), ("random3000", "f64"), ("huge300", "f64")])
+def test_builder_strategies_are_bit_identical(api, name, prec, small, subtree, gang):
+    """The exact builder picks its strategies by size and type (warp gangs for the top levels, in-register subtrees or the
+    thread-per-range kernel for the bottom); every combination must produce the reference's bits, on the degenerate
+    ("halve by position") and "no split wins" scenes too."""
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    ctx = api.Context.default()
+    ctx.set_option("build_small", small); ctx.set_option("build_subtree", subtree); ctx.set_option("build_gang", gang)
+    try:
+        bvh = api.Bvh.build(shapes, prec=prec)
+        assert _nodes_equal(bvh.nodes, want.nodes), name
+        assert np.array_equal(bvh.node_index, want.node_index)
+        assert _flat_equal(bvh.flatten().nodes, O.flatten(want.nodes, prec))
+        bvh.free()
+    finally:
+        ctx.set_option("build_small", -1); ctx.set_option("build_subtree", -1); ctx.set_option("build_gang", -1)
+
+
+def test_forced_gangs_on_a_large_scene(api):
+    """Gangs are normally off above ~150 k shapes; forced on, they coexist with queue-mode tile tasks (300 k shapes)."""
+    from bvh_b200 import scenes as S
+    shapes = S.create_n_cubes_aabbs(25000)
+    want = O.build(shapes, "f32")
+    ctx = api.Context.default()
+    ctx.set_option("build_gang", 1)
+    try:
+        bvh = api.Bvh.build(shapes)
+        assert _nodes_equal(bvh.nodes, want.nodes)
+        assert np.array_equal(bvh.node_index, want.node_index)
+        bvh.free()
+    finally:
+        ctx.set_option("build_gang", -1)
+
+
+def test_concurrent_builds_on_two_contexts(api):
+    """Two contexts building at the same time: the cooperative launch serialises the gang kernels instead of letting them
+    starve each other of SMs."""
+    import threading
+    from bvh_b200 import scenes as S
+    shapes = S.create_n_cubes_aabbs(8000)
+    want = O.build(shapes, "f32")
+    ctxs = [api.Context(0), api.Context(0)]
+    res = [None, None]
+    def work(i):
+        ok = True
+        for _ in range(10):
+            b = api.Bvh.build(shapes, ctx=ctxs[i])
+            ok = ok and np.array_equal(b.node_index, want.node_index)
+            b.free()
+        res[i] = ok
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th: t.start()
+    for t in th: t.join(120)
+    assert res == [True, True]
+
+
 def test_capacity_error_and_fetch(api):
     """Caller buffer too small: BVHGPU_ERR_CAPACITY with the needed size, and bvhgpu_traverse_fetch_* returns the retained result."""
     import ctypes as C
