@@ -26,6 +26,7 @@
 #include <cmath>
 #include <limits>
 #include <vector>
+#include <stdexcept>
 #include <array>
 #include <string>
 #include <atomic>
@@ -641,6 +642,202 @@ inline void sah_cost(const Node<T>* nodes, uint32_t n_nodes, double& pseudo, dou
     }
     pseudo /= rp;
     geometric /= rg;
+}
+
+// ----------------------------------------------------------------------------
+// Bvh::update_shapes = remove_shape* then add_shape* (src/bvh/optimization.rs:70-389): the reference's
+// sequential re-insertion.  It appends / swap-removes nodes, so the result is NOT in build's preorder
+// layout any more (child_l != i+1 in general); every function above only follows child indices and
+// works on it unchanged.  The per-node shape count in `Node::shape` (our extra, not in the reference
+// enum) is not maintained by these functions; recount() restores it.
+// `shapes` are the CURRENT (already moved) AABBs, as in the reference, where `shapes[i].aabb()` is
+// evaluated at the time of the call.
+// ----------------------------------------------------------------------------
+template <class T> struct DynBvh {
+    std::vector<Node<T>> nodes;
+    std::vector<uint32_t> node_index;           // BHShape::bh_node_index of every shape
+};
+
+template <class T> inline Aabb3<T> get_node_aabb(const DynBvh<T>& b, uint32_t i, const Aabb3<T>* shapes) {   // bvh_node.rs:616-625
+    const Node<T>& nd = b.nodes[i];
+    return nd.is_leaf() ? shapes[nd.shape] : aabb_join(nd.l_aabb, nd.r_aabb);
+}
+template <class T> inline Node<T> make_leaf(uint32_t parent, uint32_t shape) {
+    Node<T> nd;
+    nd.parent = parent; nd.child_l = U32_MAX; nd.child_r = U32_MAX; nd.shape = shape;
+    nd.l_aabb = aabb_empty<T>(); nd.r_aabb = aabb_empty<T>();
+    return nd;
+}
+template <class T> inline bool node_is_left_child(const DynBvh<T>& b, uint32_t i) {     // optimization.rs:18-24
+    return b.nodes[b.nodes[i].parent].child_l == i;
+}
+template <class T> inline bool node_is_right_child(const DynBvh<T>& b, uint32_t i) {    // :26-32
+    return b.nodes[b.nodes[i].parent].child_r == i;
+}
+// optimization.rs:34-65
+template <class T> inline void connect_nodes(DynBvh<T>& b, uint32_t child, uint32_t parent, bool left_child, const Aabb3<T>* shapes) {
+    const Aabb3<T> child_aabb = get_node_aabb(b, child, shapes);
+    Node<T>& p = b.nodes[parent];
+    if (p.is_leaf()) throw std::logic_error("connect_nodes: parent is a leaf");           // unreachable!() in the reference
+    if (left_child) { p.child_l = child; p.l_aabb = child_aabb; }
+    else            { p.child_r = child; p.r_aabb = child_aabb; }
+    b.nodes[child].parent = parent;
+}
+// optimization.rs:317-351
+template <class T> inline void fix_aabbs_ascending(DynBvh<T>& b, const Aabb3<T>* shapes, uint32_t node_index) {
+    uint32_t index_to_fix = node_index;
+    auto differs = [](const Aabb3<T>& x, const Aabb3<T>& y) {                              // Aabb: PartialEq on min and max
+        for (int k = 0; k < 3; ++k) if (x.min[k] != y.min[k] || x.max[k] != y.max[k]) return true;
+        return false;
+    };
+    while (index_to_fix != 0) {
+        const uint32_t parent = b.nodes[index_to_fix].parent;
+        Node<T>& pn = b.nodes[parent];
+        if (pn.is_leaf()) { index_to_fix = 0; continue; }
+        const Aabb3<T> l = get_node_aabb(b, pn.child_l, shapes), r = get_node_aabb(b, pn.child_r, shapes);
+        bool stop = true;
+        if (differs(l, pn.l_aabb)) { stop = false; pn.l_aabb = l; }
+        if (differs(r, pn.r_aabb)) { stop = false; pn.r_aabb = r; }
+        index_to_fix = stop ? 0 : parent;
+    }
+}
+// optimization.rs:353-389
+template <class T> inline void swap_and_remove_index(DynBvh<T>& b, uint32_t node_index) {
+    const uint32_t end = (uint32_t)b.nodes.size() - 1;
+    if (node_index != end) {
+        b.nodes[node_index] = b.nodes[end];
+        const uint32_t parent_index = b.nodes[node_index].parent;
+        Node<T>& parent = b.nodes[parent_index];
+        if (parent.is_leaf()) throw std::logic_error("swap_and_remove_index: parent is a leaf");
+        if (parent.child_l == end) parent.child_l = node_index;
+        else {
+            if (parent.child_r != end) throw std::logic_error("swap_and_remove_index: moved node is not a child of its parent");
+            parent.child_r = node_index;
+        }
+        const Node<T>& moved = b.nodes[node_index];
+        if (moved.is_leaf()) b.node_index[moved.shape] = node_index;
+        else { b.nodes[moved.child_l].parent = node_index; b.nodes[moved.child_r].parent = node_index; }
+    }
+    b.nodes.resize(end);
+}
+// optimization.rs:70-206
+template <class T> inline void add_shape(DynBvh<T>& b, const Aabb3<T>* shapes, uint32_t new_shape_index) {
+    uint32_t node_index = 0;
+    const Aabb3<T> shape_aabb = shapes[new_shape_index];
+    const T shape_sa = aabb_surface_area(shape_aabb);
+    if (b.nodes.empty()) {
+        b.nodes.push_back(make_leaf<T>(0, new_shape_index));
+        b.node_index[new_shape_index] = 0;
+        return;
+    }
+    for (;;) {
+        const Node<T> cur = b.nodes[node_index];                // copy: the vector may grow below
+        if (!cur.is_leaf()) {
+            const Aabb3<T> left_expand = aabb_join(cur.l_aabb, shape_aabb);
+            const Aabb3<T> right_expand = aabb_join(cur.r_aabb, shape_aabb);
+            const T send_left = aabb_surface_area(cur.r_aabb) + aabb_surface_area(left_expand);
+            const T send_right = aabb_surface_area(cur.l_aabb) + aabb_surface_area(right_expand);
+            const Aabb3<T> merged_aabb = aabb_join(cur.r_aabb, cur.l_aabb);
+            const T merged = aabb_surface_area(merged_aabb) + shape_sa;
+            const T min_send = send_left < send_right ? send_left : send_right;
+            if (merged < min_send * T(3) / T(10)) {             // "merge is more expensive only do when it's significantly better"
+                const uint32_t l_index = (uint32_t)b.nodes.size();
+                b.node_index[new_shape_index] = l_index;
+                b.nodes.push_back(make_leaf<T>(node_index, new_shape_index));
+                const uint32_t r_index = (uint32_t)b.nodes.size();
+                Node<T> new_right = cur;
+                new_right.parent = node_index;
+                b.nodes.push_back(new_right);
+                b.nodes[cur.child_r].parent = r_index;
+                b.nodes[cur.child_l].parent = r_index;
+                Node<T>& here = b.nodes[node_index];
+                here.l_aabb = shape_aabb; here.child_l = l_index; here.r_aabb = merged_aabb; here.child_r = r_index; here.parent = cur.parent;
+                return;
+            } else if (send_left < send_right) {
+                if (node_index == cur.child_l) throw std::logic_error("broken loop");
+                b.nodes[node_index].l_aabb = left_expand;
+                node_index = cur.child_l;
+            } else {
+                if (node_index == cur.child_r) throw std::logic_error("broken loop");
+                b.nodes[node_index].r_aabb = right_expand;
+                node_index = cur.child_r;
+            }
+        } else {                                                  // split the leaf into a node over {new, old}
+            const uint32_t l_index = (uint32_t)b.nodes.size();
+            b.node_index[new_shape_index] = l_index;
+            b.nodes.push_back(make_leaf<T>(node_index, new_shape_index));
+            const Aabb3<T> child_r_aabb = shapes[cur.shape];
+            const uint32_t child_r_index = (uint32_t)b.nodes.size();
+            b.node_index[cur.shape] = child_r_index;
+            b.nodes.push_back(make_leaf<T>(node_index, cur.shape));
+            Node<T>& here = b.nodes[node_index];
+            here.parent = cur.parent; here.child_l = l_index; here.child_r = child_r_index; here.shape = 2;
+            here.l_aabb = shape_aabb; here.r_aabb = child_r_aabb;
+            fix_aabbs_ascending(b, shapes, cur.parent);
+            return;
+        }
+    }
+}
+// optimization.rs:208-288 (swap_shape == false: the variant update_shapes uses)
+template <class T> inline void remove_shape(DynBvh<T>& b, const Aabb3<T>* shapes, uint32_t deleted_shape_index) {
+    if (b.nodes.empty()) throw std::logic_error("can't remove a node from a bvh with only one node");
+    const uint32_t dead = b.node_index[deleted_shape_index];
+    if (b.nodes.size() == 1) {
+        if (dead != 0 || !b.nodes[0].is_leaf()) throw std::logic_error("remove_shape: single node is not this leaf");
+        b.nodes.clear();
+        return;
+    }
+    if (!b.nodes[dead].is_leaf()) throw std::logic_error("remove_shape: bh_node_index is not a leaf");
+    const uint32_t parent_index = b.nodes[dead].parent;
+    const uint32_t gp_index = b.nodes[parent_index].parent;
+    uint32_t sibling_index;
+    if (node_is_left_child(b, dead)) sibling_index = b.nodes[parent_index].child_r;
+    else {
+        if (!node_is_right_child(b, dead)) throw std::logic_error("remove_shape: node is neither child of its parent");
+        sibling_index = b.nodes[parent_index].child_l;
+    }
+    if (parent_index == gp_index) {                               // a child of the root goes: the sibling becomes the root
+        if (parent_index != 0) throw std::logic_error("Circular node that wasn't root");
+        const Node<T> sib = b.nodes[sibling_index];
+        if (!sib.is_leaf()) {
+            connect_nodes(b, sib.child_l, parent_index, true, shapes);
+            connect_nodes(b, sib.child_r, parent_index, false, shapes);
+        } else {
+            b.nodes[0] = sib;
+            b.nodes[0].parent = 0;
+            b.node_index[b.nodes[0].shape] = 0;
+        }
+        swap_and_remove_index(b, std::max(sibling_index, dead));
+        swap_and_remove_index(b, std::min(sibling_index, dead));
+    } else {
+        const bool parent_is_left = node_is_left_child(b, parent_index);
+        connect_nodes(b, sibling_index, gp_index, parent_is_left, shapes);
+        fix_aabbs_ascending(b, shapes, gp_index);
+        swap_and_remove_index(b, std::max(dead, parent_index));
+        swap_and_remove_index(b, std::min(parent_index, dead));
+    }
+}
+// optimization.rs:290-302: all removals first, then all insertions, both in the caller's order.
+template <class T> inline void update_shapes(DynBvh<T>& b, const uint32_t* changed, uint32_t n_changed, const Aabb3<T>* shapes) {
+    for (uint32_t i = 0; i < n_changed; ++i) remove_shape(b, shapes, changed[i]);
+    for (uint32_t i = 0; i < n_changed; ++i) add_shape(b, shapes, changed[i]);
+}
+// Node::shape of inner nodes = number of shapes below (our extra field): recomputed after updates.
+template <class T> inline void recount(DynBvh<T>& b) {
+    if (b.nodes.empty() || b.nodes[0].is_leaf()) return;
+    std::vector<std::pair<uint32_t, int>> stack;
+    stack.push_back({0u, 0});
+    while (!stack.empty()) {
+        auto& f = stack.back();
+        Node<T>& nd = b.nodes[f.first];
+        if (nd.is_leaf()) { stack.pop_back(); continue; }
+        if (f.second == 0) { f.second = 1; const uint32_t l = nd.child_l, r = nd.child_r; stack.push_back({l, 0}); stack.push_back({r, 0}); }
+        else {
+            auto cnt = [&](uint32_t c) { return b.nodes[c].is_leaf() ? 1u : b.nodes[c].shape; };
+            nd.shape = cnt(nd.child_l) + cnt(nd.child_r);
+            stack.pop_back();
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------

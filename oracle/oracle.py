@@ -73,6 +73,8 @@ def lib():
         _lib.orc_last_build_ns.restype = C.c_uint64
         _lib.orc_hardware_threads.restype = C.c_uint32
         _lib.orc_sizeof.restype = C.c_uint32
+        _lib.orc_update_shapes_f32.restype = C.c_uint32
+        _lib.orc_update_shapes_f64.restype = C.c_uint32
         # struct layout must agree with the numpy dtypes
         sizes = [_lib.orc_sizeof(i) for i in range(8)]
         want = [d.itemsize for d in (AABB3F, RAY3F, NODE3F, FLAT3F, AABB3D, RAY3D, NODE3D, FLAT3D)]
@@ -206,6 +208,32 @@ def sah_cost(nodes, prec="f32"):
     out = np.zeros(2, dtype=np.float64)
     getattr(lib(), f"orc_sah_cost_{prec}")(_p(nodes), C.c_uint32(len(nodes)), _p(out))
     return float(out[0]), float(out[1])
+
+
+def update_shapes(nodes, node_index, shapes, changed, prec="f32"):
+    """Bvh::update_shapes (src/bvh/optimization.rs:290-302): remove then re-insert `changed` (in this order) given the shapes'
+    CURRENT AABBs.  Returns new (nodes, node_index); the node array is no longer in build's preorder layout."""
+    d = _DT[prec]
+    nodes = np.array(nodes, dtype=d["node"], copy=True)
+    node_index = np.array(node_index, dtype=np.uint32, copy=True)
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    changed = np.ascontiguousarray(changed, dtype=np.uint32)
+    n = getattr(lib(), f"orc_update_shapes_{prec}")(_p(nodes), C.c_uint32(len(nodes)), _p(node_index), C.c_uint32(len(shapes)),
+                                                   _p(shapes), _p(changed), C.c_uint32(len(changed)))
+    if n == 0xFFFFFFFF:
+        raise RuntimeError("update_shapes: the reference would have panicked on this input")
+    return nodes[:n], node_index
+
+
+def connect_nodes(nodes, shapes, child, parent, left_child, prec="f32"):
+    """Bvh::connect_nodes (src/bvh/optimization.rs:34-65) on a copy of `nodes`."""
+    d = _DT[prec]
+    nodes = np.array(nodes, dtype=d["node"], copy=True)
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    ok = getattr(lib(), f"orc_connect_nodes_{prec}")(_p(nodes), C.c_uint32(len(nodes)), _p(shapes), C.c_uint32(child), C.c_uint32(parent),
+                                                   C.c_int(1 if left_child else 0))
+    assert ok
+    return nodes
 
 
 # ---------------------------------------------------------------- fixtures (src/testbase.rs)

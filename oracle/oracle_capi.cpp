@@ -133,6 +133,26 @@ static uint64_t g_last_build_ns = 0;
     ORC_API void orc_sah_cost_##SUF(const Node<T>* nodes, uint32_t n_nodes, double* out2) {                  \
         sah_cost(nodes, n_nodes, out2[0], out2[1]);                                                          \
     }                                                                                                        \
+    /* Bvh::update_shapes on (nodes, node_index) in place; returns the node count or U32_MAX on a reference panic path */ \
+    ORC_API uint32_t orc_update_shapes_##SUF(Node<T>* nodes, uint32_t n_nodes, uint32_t* node_index, uint32_t n_shapes, \
+                                             const Aabb3<T>* shapes, const uint32_t* changed, uint32_t n_changed) { \
+        DynBvh<T> b;                                                                                         \
+        b.nodes.assign(nodes, nodes + n_nodes);                                                              \
+        b.node_index.assign(node_index, node_index + n_shapes);                                              \
+        try { update_shapes(b, changed, n_changed, shapes); recount(b); } catch (const std::logic_error&) { return U32_MAX; } \
+        if (b.nodes.size() > n_nodes) return U32_MAX;                                                        \
+        std::memcpy(nodes, b.nodes.data(), sizeof(Node<T>) * b.nodes.size());                                \
+        std::memcpy(node_index, b.node_index.data(), sizeof(uint32_t) * n_shapes);                           \
+        return (uint32_t)b.nodes.size();                                                                     \
+    }                                                                                                        \
+    ORC_API int orc_connect_nodes_##SUF(Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes, uint32_t child, \
+                                        uint32_t parent, int left_child) {                                   \
+        DynBvh<T> b;                                                                                         \
+        b.nodes.assign(nodes, nodes + n_nodes);                                                              \
+        try { connect_nodes(b, child, parent, left_child != 0, shapes); } catch (const std::logic_error&) { return 0; } \
+        std::memcpy(nodes, b.nodes.data(), sizeof(Node<T>) * n_nodes);                                       \
+        return 1;                                                                                            \
+    }                                                                                                        \
     ORC_API void orc_create_n_cubes_##SUF(uint32_t n_cubes, const Aabb3<T>* bounds, T* tris_out /*108 per cube*/, \
                                           Aabb3<T>* aabbs_out /*12 per cube*/) {                             \
         std::vector<T> tris;                                                                                 \

@@ -336,3 +336,126 @@ def test_bench_build_byte_model_constant():
 
     res = O.build(O.create_n_cubes(10_000))
     assert res.prim_visits == bench.BUILD_PRIM_VISITS
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Bvh::update_shapes (src/bvh/optimization.rs): the reference's own tests, restated on the oracle.
+# ---------------------------------------------------------------------------------------------------------------------
+def _leaf_parent(nodes, node_index, shape):
+    return int(nodes[int(node_index[shape])]["parent"])
+
+
+def test_update_shapes_simple_update():                    # optimization.rs:420-487
+    pos = np.array([[-50.0, 0, 0], [-40.0, 0, 0], [50.0, 0, 0]])
+    shapes = O.unit_boxes(pos)
+    b = O.build(shapes)
+    assert _leaf_parent(b.nodes, b.node_index, 0) == _leaf_parent(b.nodes, b.node_index, 1)     # SAH joined #0 and #1
+    pos[1] = [40.0, 0, 0]
+    shapes = O.unit_boxes(pos)
+    nodes, node_index = O.update_shapes(b.nodes, b.node_index, shapes, [1])
+    assert O.is_consistent(nodes, shapes)
+    assert _leaf_parent(nodes, node_index, 1) == _leaf_parent(nodes, node_index, 2)             # now #1 and #2
+
+
+def test_consistent_after_update_shapes():                 # optimization.rs:405-417
+    shapes = O.aligned_boxes()
+    b = O.build(shapes)
+    moved = O.unit_boxes([[10.0, 1.0, 2.0], [-10.0, -10.0, 10.0], [-10.0, 10.0, 10.0], [-10.0, 10.0, -10.0], [11.0, 1.0, 2.0], [11.0, 2.0, 2.0]])
+    shapes = shapes.copy()
+    shapes[:6] = moved
+    nodes, node_index = O.update_shapes(b.nodes, b.node_index, shapes, np.arange(6))
+    assert len(nodes) == 41
+    assert O.is_consistent(nodes, shapes)
+    for s in range(21):                                       # every shape is still in exactly one leaf, and knows which
+        nd = nodes[int(node_index[s])]
+        assert nd["child_l"] == 0xFFFFFFFF and nd["shape"] == s
+
+
+def _predictable_bvh():                                     # optimization.rs:489-541
+    shapes = O.unit_boxes([[0.0, 0, 0], [2.0, 0, 0], [4.0, 0, 0], [6.0, 0, 0]])
+    nodes = np.zeros(7, dtype=O.NODE3F)
+    INV = 0xFFFFFFFF
+    def join(a, b):
+        out = np.zeros((), dtype=O.AABB3F)
+        out["min"] = np.minimum(a["min"], b["min"]); out["max"] = np.maximum(a["max"], b["max"])
+        return out
+    empty = np.zeros((), dtype=O.AABB3F); empty["min"] = np.inf; empty["max"] = -np.inf
+    def node(i, parent, l, r, la, ra, cnt):
+        nodes[i]["parent"], nodes[i]["child_l"], nodes[i]["child_r"], nodes[i]["shape"] = parent, l, r, cnt
+        nodes[i]["l_aabb"], nodes[i]["r_aabb"] = la, ra
+    node(0, 0, 1, 2, join(shapes[0], shapes[1]), join(shapes[2], shapes[3]), 4)
+    node(1, 0, 3, 4, shapes[0], shapes[1], 2)
+    node(2, 0, 5, 6, shapes[2], shapes[3], 2)
+    for i, (p, s) in enumerate([(1, 0), (1, 1), (2, 2), (2, 3)]):
+        node(3 + i, p, INV, INV, empty, empty, s)
+    return shapes, nodes
+
+
+def _same(a, b):
+    return np.array_equal(a["min"], b["min"]) and np.array_equal(a["max"], b["max"])
+
+
+def test_connect_grandchildren():                          # optimization.rs:543-589
+    shapes, nodes = _predictable_bvh()
+    nodes = O.connect_nodes(nodes, shapes, 3, 2, True)
+    nodes = O.connect_nodes(nodes, shapes, 5, 1, True)
+    assert [int(nodes[i]["parent"]) for i in range(7)] == [0, 0, 0, 2, 1, 1, 2]
+    assert (int(nodes[0]["child_l"]), int(nodes[0]["child_r"])) == (1, 2)
+    assert (int(nodes[1]["child_l"]), int(nodes[1]["child_r"])) == (5, 4)
+    assert (int(nodes[2]["child_l"]), int(nodes[2]["child_r"])) == (3, 6)
+    assert _same(nodes[1]["l_aabb"], shapes[2]) and _same(nodes[1]["r_aabb"], shapes[1])
+    assert _same(nodes[2]["l_aabb"], shapes[0]) and _same(nodes[2]["r_aabb"], shapes[3])
+
+
+def test_connect_child_grandchild():                       # optimization.rs:591-637
+    shapes, nodes = _predictable_bvh()
+    nodes = O.connect_nodes(nodes, shapes, 1, 2, True)
+    nodes = O.connect_nodes(nodes, shapes, 5, 0, True)
+    assert [int(nodes[i]["parent"]) for i in range(7)] == [0, 2, 0, 1, 1, 0, 2]
+    assert (int(nodes[0]["child_l"]), int(nodes[0]["child_r"])) == (5, 2)
+    assert (int(nodes[1]["child_l"]), int(nodes[1]["child_r"])) == (3, 4)
+    assert (int(nodes[2]["child_l"]), int(nodes[2]["child_r"])) == (1, 6)
+    assert _same(nodes[0]["l_aabb"], shapes[2]) and _same(nodes[2]["r_aabb"], shapes[3])
+    assert _same(nodes[1]["l_aabb"], shapes[0]) and _same(nodes[1]["r_aabb"], shapes[1])
+
+
+def _move_shapes(shapes, amount, rng, max_offset=None):
+    """randomly_transform_scene analogue (testbase.rs:640-681): translate `amount` distinct shapes by a random offset that
+    keeps them inside the default bounds (the reference shuffles with StdRng, which cannot be restated: seeded numpy here)."""
+    bounds = O.default_bounds()
+    idx = rng.permutation(len(shapes))[:amount]
+    out = shapes.copy()
+    lo = bounds["min"][0] - shapes["min"][idx]
+    hi = bounds["max"][0] - shapes["max"][idx]
+    off = rng.uniform(lo, hi).astype(np.float32)
+    if max_offset is not None:
+        off = np.clip(off, -max_offset, max_offset)
+    out["min"][idx] = (shapes["min"][idx] + off).astype(np.float32)
+    out["max"][idx] = (shapes["max"][idx] + off).astype(np.float32)
+    return out, idx.astype(np.uint32)
+
+
+def _brute_force(shapes, ray):
+    """Every shape whose AABB the ray hits (intersect_default.rs:16-37, vectorised in f32: sub, mul, min/max -- no FMA in numpy)."""
+    with np.errstate(all="ignore"):
+        l = (shapes["min"] - ray["origin"]) * ray["inv_direction"]
+        r = (shapes["max"] - ray["origin"]) * ray["inv_direction"]
+    nan = np.isnan(l).any(axis=1) | np.isnan(r).any(axis=1)
+    tmin, tmax = np.minimum(l, r).max(axis=1), np.maximum(l, r).min(axis=1)
+    return np.nonzero(~nan & (tmax >= np.where(tmin > 0, tmin, np.float32(0))))[0].tolist()
+
+
+def test_update_shapes_bvh_12k_75p():                      # optimization.rs:639-662
+    shapes = O.create_n_cubes(1000)
+    b = O.build(shapes)
+    assert O.is_consistent(b.nodes, shapes) and O.is_tight(b.nodes)
+    moved, idx = _move_shapes(shapes, 9000, np.random.default_rng(0))
+    assert not O.is_consistent(b.nodes, moved)
+    nodes, node_index = O.update_shapes(b.nodes, b.node_index, moved, idx)
+    assert len(nodes) == 2 * len(shapes) - 1
+    assert O.is_consistent(nodes, moved) and O.is_tight(nodes)
+    # and the updated (non-preorder) tree still answers ray queries like a brute-force scan of the moved shapes
+    rays, _ = O.create_rays(64)
+    r = O.traverse(nodes, moved, rays, O.MODE_RECURSIVE)
+    for k, got in enumerate(O.per_ray_lists(r.offsets, r.hits)):
+        assert sorted(got.tolist()) == _brute_force(moved, rays[k])
