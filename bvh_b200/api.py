@@ -308,3 +308,14 @@ class Bvh:
         aabbs = _gather_aabbs(shapes, self.prec)
         capi.check(getattr(capi.lib(), f"bvhgpu_refit_{self._d['suffix']}")(self._h, _ptr(aabbs), len(aabbs)))
         self._nodes = self._node_index = None
+
+    def optimize(self, shapes, max_growth: float = 1.5) -> int:
+        """Bvh::update_shapes counterpart (src/bvh/optimization.rs:290-302): refit, then rebuild in place the subtrees whose
+        surface area grew by more than `max_growth`.  `shapes` = all shapes with their current AABBs.  Returns the number
+        of shapes in the rebuilt subtrees; `node_index` must be re-read (set_bh_node_index) afterwards."""
+        aabbs = _gather_aabbs(shapes, self.prec)
+        rebuilt = C.c_size_t(0)
+        capi.check(getattr(capi.lib(), f"bvhgpu_optimize_{self._d['suffix']}")(self._h, _ptr(aabbs), len(aabbs), C.c_double(max_growth),
+                                                                              C.byref(rebuilt)))
+        self._nodes = self._node_index = None
+        return int(rebuilt.value)

@@ -1214,6 +1214,7 @@ __global__ void init_keys_kernel(typename Traits<T>::Key* rootkeys, BuildCtl* ct
         ctl->small_count = 0;
         ctl->gang_used = 0;
         ctl->gang_trace = 0;
+        ctl->rebuilt = 0;
         ctl->t_start = 0;
         status->error = status->nan_found = status->tickets = status->leaves_done = 0;
     }
@@ -1241,6 +1242,7 @@ template <class T> __global__ void finish_status_kernel(BuildCtl* ctl, BuildStat
     if (threadIdx.x == 0) {
         status->tickets = ctl->tail;
         status->leaves_done = ctl->leaves_done;
+        status->rebuilt = ctl->rebuilt;
         uint32_t e = ctl->error;
         if (status->nan_found) e = (uint32_t)BVHGPU_ERR_NAN;
         if (e == 0 && ctl->leaves_done != n) e = (uint32_t)BVHGPU_ERR_INTERNAL;
@@ -1459,6 +1461,97 @@ int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
     S->params = nullptr;
     return BVHGPU_OK;
 }
+
+// ---- rebuild session: the exact builder restarted from inner nodes (bvhgpu_optimize, flatten.cu: optimize) ---------------
+// One task per rebuild root: its shape range in leaf order (index buffer 0), its node index, its parent, its AABB (the
+// join of its two stored child AABBs, tight after the refit) and the bounds of its shape centres (carried up by the
+// refit).  From there on it is the ordinary build: the subtree of a node with k shapes occupies the node range
+// [i, i + 2k - 1) and the leaf range [start, start + k), and child_l = i + 1 / child_r = i + 2 n_l stay inside it.
+template <class T>
+__global__ void __launch_bounds__(256) rebuild_push_kernel(BuildParams<T> P, const uint32_t* __restrict__ roots, const uint32_t* __restrict__ n_roots,
+                                                           const T* __restrict__ cb) {
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t nr = *n_roots;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nr; i += warps) {
+        const uint32_t r = roots[i];
+        const typename Traits<T>::Node& nd = P.nodes[r];
+        BTask<T> t;
+        t.start = P.node_start[r]; t.count = nd.shape; t.node = r; t.parent_buf = nd.parent;          // range lives in index buffer 0
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            t.ab[k] = min_t(nd.l_aabb.min[k], nd.r_aabb.min[k]); t.ab[3 + k] = max_t(nd.l_aabb.max[k], nd.r_aabb.max[k]);
+            t.cb[k] = cb[6 * (size_t)r + k]; t.cb[3 + k] = cb[6 * (size_t)r + 3 + k];
+        }
+        if (lane_id() == 0) { atomicSub(&P.ctl->leaves_done, t.count); atomicAdd(&P.ctl->rebuilt, t.count); }
+        __syncwarp();
+        if (t.count > (uint32_t)TILE) { if (!try_create_gang(P, t)) create_big(P, t); } else push_seg(P, t);
+    }
+}
+template <class T> __global__ void rebuild_start_kernel(BuildCtl* ctl, uint32_t n) {
+    if (threadIdx.x == 0) { ctl->t_start = global_timer_ns(); ctl->leaves_done = n; }
+}
+
+template <class T>
+int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = tree->n;
+    BuildParams<T> P{};
+    P.aabb = tree->d_aabb; P.nodes = tree->d_nodes; P.node_index = tree->d_node_index; P.node_start = tree->d_node_start;
+    P.n = n; P.status = tree->d_status; P.timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+    const uint32_t qcap = next_pow2(std::max<uint64_t>(n, 1024) * 2);
+    P.qmask = qcap - 1;
+    int occ = 1;
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
+    if (occ < 1) occ = 1;
+    uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (want < 1) want = 1;
+    const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    P.gang_budget = (ctx->build_gang != 0 && coop) ? (uint32_t)grid * WARPS_PER_CTA / 2u : 0u;
+    if (ctx->build_gang < 0 && (uint64_t)n / GT > P.gang_budget) P.gang_budget = 0;
+    P.sdiv = P.gang_budget ? GT : TILE;
+    const size_t nbig = 2 * ((size_t)n / P.sdiv + 2);
+    const bool defer_small = ctx->build_small < 0 ? (sizeof(T) == 8 && n >= 400000u) : ctx->build_small != 0;
+    P.small_max = defer_small ? SMALL : 0u;
+    P.opt_subtree = ctx->build_subtree < 0 ? !defer_small : ctx->build_subtree != 0;
+    P.idx[0] = idx0;
+    BVH_TRY(dalloc_t(ctx, &P.idx[1], n));
+    BVH_TRY(dalloc_t(ctx, &P.bkt, n));
+    BVH_TRY(dalloc_t(ctx, &P.q, qcap));
+    BVH_TRY(dalloc_t(ctx, &P.qseq, qcap));
+    BVH_TRY(dalloc_t(ctx, &P.big, nbig));
+    BVH_TRY(dalloc_t(ctx, &P.tilecnt, nbig * 8));
+    BVH_TRY(dalloc_t(ctx, &P.ctl, 1));
+    BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
+    BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
+    BVH_CUDA_TRY(cudaMemsetAsync(P.ctl, 0, sizeof(BuildCtl), st));
+    rebuild_start_kernel<T><<<1, 32, 0, st>>>(P.ctl, n);
+    const int pblocks = (int)std::min<uint64_t>(((uint64_t)n + 63) / 64, (uint64_t)ctx->sm_count * 4);
+    rebuild_push_kernel<T><<<pblocks, 256, 0, st>>>(P, d_roots, d_n_roots, cb);
+    if (P.gang_budget) {
+        void* kargs[] = {&P};
+        BVH_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)build_kernel<T>, dim3(grid), dim3(WARPS_PER_CTA * 32), kargs, 0, st));
+    } else {
+        build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+    }
+    ctx->launches += 3;
+    if (P.small_max) {
+        const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
+        small_subtrees_kernel<T><<<sgrid, 128, 0, st>>>(P);
+        ctx->launches++;
+    }
+    finish_status_kernel<T><<<1, 32, 0, st>>>(P.ctl, P.status, n);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    dfree(ctx, P.idx[1]); dfree(ctx, P.bkt); dfree(ctx, P.q); dfree(ctx, P.qseq); dfree(ctx, P.big); dfree(ctx, P.tilecnt);
+    dfree(ctx, P.ctl); dfree(ctx, P.small);
+    tree->status_pending = true;
+    return BVHGPU_OK;
+}
+template int rebuild_subtrees<float>(bvhgpu_ctx*, Tree<float>*, const uint32_t*, const uint32_t*, const float*, uint32_t*);
+template int rebuild_subtrees<double>(bvhgpu_ctx*, Tree<double>*, const uint32_t*, const uint32_t*, const double*, uint32_t*);
+
 template int treelet_begin<float>(bvhgpu_ctx*, Tree<float>*, uint32_t*, TreeletSession<float>*);
 template int treelet_begin<double>(bvhgpu_ctx*, Tree<double>*, uint32_t*, TreeletSession<double>*);
 template int treelet_finish<float>(bvhgpu_ctx*, Tree<float>*, TreeletSession<float>*);

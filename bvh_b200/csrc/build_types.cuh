@@ -57,7 +57,8 @@ struct __align__(128) BuildCtl {
     uint32_t small_count;            // ranges of <= SMALL shapes deferred to small_subtrees_kernel
     uint32_t gang_used;              // warps currently reserved by gangs (bounded by BuildParams::gang_budget)
     uint32_t gang_trace;             // BVHGPU_TRACE: gang levels are logged from the end of the trace buffer
-    uint32_t pad3[27];
+    uint32_t rebuilt;                // rebuild session: shapes in the rebuilt subtrees
+    uint32_t pad3[26];
 };
 constexpr uint32_t SMALL = 16;       // ranges this small are finished by ONE THREAD each in a second kernel
 

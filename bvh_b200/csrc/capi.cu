@@ -327,6 +327,31 @@ static int refit_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size
     return resolve_status(tree);
 }
 
+template <class T>
+static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n, double max_growth, size_t* rebuilt) {
+    if (!tree || (n && !aabbs)) { set_error("optimize: null argument"); return BVHGPU_ERR_INVALID; }
+    if (n != tree->n) { set_error("optimize: %zu AABBs for a tree over %u shapes", n, tree->n); return BVHGPU_ERR_INVALID; }
+    if (!(max_growth >= 1.0)) { set_error("optimize: max_growth = %g, must be >= 1", max_growth); return BVHGPU_ERR_INVALID; }
+    if (rebuilt) *rebuilt = 0;
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (n == 0) return BVHGPU_OK;
+    typename Traits<T>::Aabb* staged = nullptr;
+    BVH_TRY(dalloc_t(ctx, &staged, n));
+    BVH_CUDA_TRY(cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream));
+    BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
+    BVH_TRY(convert_aabbs<T>(ctx, staged, (uint32_t)n, tree->d_aabb, &tree->d_status->nan_found));
+    dfree(ctx, staged);
+    BVH_TRY(optimize(tree, max_growth));
+    tree->status_pending = true;
+    BuildStatus h;
+    BVH_CUDA_TRY(cudaMemcpyAsync(&h, tree->d_status, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_TRY(resolve_status(tree));                                      // synchronises
+    if (rebuilt) *rebuilt = h.rebuilt;
+    return BVHGPU_OK;
+}
+
 }  // namespace bvhb200
 
 using namespace bvhb200;
@@ -553,7 +578,10 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
         BVH_TRY(resolve_status<T>(tree));                                                                                 \
         return sah_cost<T>(tree, out2);                                                                                   \
     }                                                                                                                     \
-    BVH_EXPORT int bvhgpu_refit_##SUF(TREE* tree, const AABB* aabbs, size_t n) { return refit_impl<T>(tree, aabbs, n); }
+    BVH_EXPORT int bvhgpu_refit_##SUF(TREE* tree, const AABB* aabbs, size_t n) { return refit_impl<T>(tree, aabbs, n); } \
+    BVH_EXPORT int bvhgpu_optimize_##SUF(TREE* tree, const AABB* aabbs, size_t n, double max_growth, size_t* rebuilt) { \
+        return optimize_impl<T>(tree, aabbs, n, max_growth, rebuilt);                                                  \
+    }
 
 DEFINE_API(float, f32x3, bvhgpu_tree3f, bvh_aabb3f, bvh_ray3f, bvh_node3f, bvh_flat3f)
 DEFINE_API(double, f64x3, bvhgpu_tree3d, bvh_aabb3d, bvh_ray3d, bvh_node3d, bvh_flat3d)

@@ -163,31 +163,44 @@ template <class T> int sah_cost(Tree<T>* tree, double* out2) {
 // ---- refit: bottom-up recomputation of the child AABBs from the (new) shape AABBs ---------------------
 // (the data-parallel part of Bvh::update_shapes: fix_aabbs_ascending, src/bvh/optimization.rs:317-351).
 // One thread per shape climbs from its leaf; the second thread to reach a node carries on.
-template <class T>
+// WITH_CB (bvhgpu_optimize): the climb also carries the bounds of the shape CENTRES below every node into cb[node][6]
+// (min xyz, max xyz) -- what the builder needs, next to the AABB, to restart from an inner node.
+template <class T, bool WITH_CB>
 __global__ void __launch_bounds__(256) refit_kernel(typename Traits<T>::Node* nodes, const uint32_t* __restrict__ node_index,
-                                                    const typename Traits<T>::DAabb* __restrict__ aabb, uint32_t n, uint32_t* arrivals) {
+                                                    const typename Traits<T>::DAabb* __restrict__ aabb, uint32_t n, uint32_t* arrivals, T* cb) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    T mn[3], mx[3];
+    T mn[3], mx[3], cmn[3], cmx[3];
     load_aabb(aabb + s, mn, mx);
+    for (int k = 0; k < 3; ++k) cmn[k] = cmx[k] = center1(mn[k], mx[k]);
     uint32_t node = node_index[s];
     while (node != 0) {
         const uint32_t p = __ldcg(&nodes[node].parent);
         typename Traits<T>::Node* pn = nodes + p;
-        const bool is_left = __ldcg(&pn->child_l) == node;
+        const uint32_t pl = __ldcg(&pn->child_l);
+        const bool is_left = pl == node;
         auto* dst = is_left ? &pn->l_aabb : &pn->r_aabb;
         for (int k = 0; k < 3; ++k) { __stcg(&dst->min[k], mn[k]); __stcg(&dst->max[k], mx[k]); }
+        if (WITH_CB) for (int k = 0; k < 3; ++k) { __stcg(cb + 6 * (size_t)node + k, cmn[k]); __stcg(cb + 6 * (size_t)node + 3 + k, cmx[k]); }
         __threadfence();
         if (atomicAdd(arrivals + p, 1u) == 0u) return;      // sibling subtree not finished yet
         __threadfence();
         const auto* sib = is_left ? &pn->r_aabb : &pn->l_aabb;
         for (int k = 0; k < 3; ++k) {
             const T smn = __ldcg(&sib->min[k]), smx = __ldcg(&sib->max[k]);
-            mn[k] = smn < mn[k] ? smn : mn[k];
-            mx[k] = smx > mx[k] ? smx : mx[k];
+            mn[k] = min_t(smn, mn[k]);
+            mx[k] = max_t(smx, mx[k]);
+        }
+        if (WITH_CB) {
+            const uint32_t sn = is_left ? __ldcg(&pn->child_r) : pl;
+            for (int k = 0; k < 3; ++k) {
+                cmn[k] = min_t(__ldcg(cb + 6 * (size_t)sn + k), cmn[k]);
+                cmx[k] = max_t(__ldcg(cb + 6 * (size_t)sn + 3 + k), cmx[k]);
+            }
         }
         node = p;
     }
+    if (WITH_CB) for (int k = 0; k < 3; ++k) { __stcg(cb + k, cmn[k]); __stcg(cb + 3 + k, cmx[k]); }     // the root's
 }
 
 template <class T> int refit(Tree<T>* tree) {
@@ -196,7 +209,7 @@ template <class T> int refit(Tree<T>* tree) {
     uint32_t* arrivals = nullptr;
     BVH_TRY(dalloc_t(ctx, &arrivals, tree->n_nodes));
     BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * tree->n_nodes, ctx->stream));
-    refit_kernel<T><<<(tree->n + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, tree->n, arrivals);
+    refit_kernel<T, false><<<(tree->n + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, tree->n, arrivals, nullptr);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
     dfree(ctx, arrivals);
@@ -205,7 +218,99 @@ template <class T> int refit(Tree<T>* tree) {
     return BVHGPU_OK;
 }
 
+
+// ---- optimize: refit + exact rebuild of the subtrees the motion degraded (replaces Bvh::update_shapes) --------------------
+// The reference re-inserts every changed shape sequentially (optimization.rs:290-302).  The data-parallel counterpart:
+//   1. remember SA(node) of every inner node, refit bottom-up (new AABBs and centroid bounds of every node);
+//   2. a node is BAD when its surface area grew by more than `max_growth`; bad nodes form chains from the moved leaves
+//      upwards, ending where the ancestor is big enough to have absorbed the motion;
+//   3. rebuild roots = the outermost nodes that are not bad but have a bad child (or the tree root if it is bad itself):
+//      the smallest subtrees inside which every moved shape can be placed properly again;
+//   4. those subtrees are rebuilt IN PLACE by the exact builder (build_sah.cu: rebuild_subtrees): preorder layout makes
+//      the subtree of a node with k shapes the contiguous node range [i, i + 2k - 1) over the contiguous leaf range
+//      [start(i), start(i) + k), so a rebuild only rewrites its own ranges.
+template <class T>
+__global__ void __launch_bounds__(256) node_sa_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes, T* __restrict__ sa) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const typename Traits<T>::Node& nd = nodes[i];
+    if (nd.child_l == BVH_INVALID) { sa[i] = T(0); return; }
+    T mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) { mn[k] = min_t(nd.l_aabb.min[k], nd.r_aabb.min[k]); mx[k] = max_t(nd.l_aabb.max[k], nd.r_aabb.max[k]); }
+    sa[i] = surface_area(mn, mx);
+}
+template <class T>
+__global__ void __launch_bounds__(256) mark_bad_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes,
+                                                       const T* __restrict__ sa_old, T max_growth, uint8_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const typename Traits<T>::Node& nd = nodes[i];
+    if (nd.child_l == BVH_INVALID) { bad[i] = 0; return; }
+    T mn[3], mx[3];
+    for (int k = 0; k < 3; ++k) { mn[k] = min_t(nd.l_aabb.min[k], nd.r_aabb.min[k]); mx[k] = max_t(nd.l_aabb.max[k], nd.r_aabb.max[k]); }
+    bad[i] = surface_area(mn, mx) > mul_rn(max_growth, sa_old[i]) ? 1 : 0;
+}
+__device__ __forceinline__ bool rebuild_candidate(uint32_t i, uint32_t child_l, uint32_t child_r, const uint8_t* bad) {
+    if (child_l == BVH_INVALID) return false;
+    if (bad[i]) return i == 0;
+    return bad[child_l] || bad[child_r];
+}
+template <class T>
+__global__ void __launch_bounds__(256) select_roots_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes,
+                                                           const uint8_t* __restrict__ bad, uint32_t* __restrict__ roots, uint32_t* n_roots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);      // parent, child_l, child_r, count
+    if (!rebuild_candidate(i, meta.y, meta.z, bad)) return;
+    uint32_t a = i;
+    while (a != 0) {                                                   // an outer candidate takes this subtree with it
+        a = nodes[a].parent;
+        const uint4 m = *reinterpret_cast<const uint4*>(nodes + a);
+        if (rebuild_candidate(a, m.y, m.z, bad)) return;
+    }
+    roots[atomicAdd(n_roots, 1u)] = i;
+}
+// shapes in leaf order: position of a leaf = its node_start
+__global__ void __launch_bounds__(256) leaf_order_kernel(const uint32_t* __restrict__ node_index, const uint32_t* __restrict__ node_start,
+                                                         uint32_t n, uint32_t* __restrict__ idx) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) idx[node_start[node_index[s]]] = s;
+}
+
+template <class T> int optimize(Tree<T>* tree, double max_growth) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    if (tree->n < 3) return refit(tree);                                // one or two shapes: nothing a rebuild could change
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = tree->n, nn = tree->n_nodes;
+    T *sa_old = nullptr, *cb = nullptr;
+    uint8_t* bad = nullptr;
+    uint32_t *roots = nullptr, *n_roots = nullptr, *idx0 = nullptr, *arrivals = nullptr;
+    BVH_TRY(dalloc_t(ctx, &sa_old, nn));
+    BVH_TRY(dalloc_t(ctx, &cb, (size_t)nn * 6));
+    BVH_TRY(dalloc_t(ctx, &bad, nn));
+    BVH_TRY(dalloc_t(ctx, &roots, n));
+    BVH_TRY(dalloc_t(ctx, &n_roots, 1));
+    BVH_TRY(dalloc_t(ctx, &idx0, n));
+    BVH_TRY(dalloc_t(ctx, &arrivals, nn));
+    BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * nn, st));
+    BVH_CUDA_TRY(cudaMemsetAsync(n_roots, 0, sizeof(uint32_t), st));
+    const unsigned gn = (nn + 255) / 256, gs = (n + 255) / 256;
+    node_sa_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, sa_old);
+    refit_kernel<T, true><<<gs, 256, 0, st>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, n, arrivals, cb);
+    mark_bad_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, sa_old, (T)max_growth, bad);
+    select_roots_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, bad, roots, n_roots);
+    leaf_order_kernel<<<gs, 256, 0, st>>>(tree->d_node_index, tree->d_node_start, n, idx0);
+    ctx->launches += 5;
+    BVH_CUDA_TRY(cudaGetLastError());
+    BVH_TRY(rebuild_subtrees(ctx, tree, roots, n_roots, cb, idx0));
+    dfree(ctx, sa_old); dfree(ctx, cb); dfree(ctx, bad); dfree(ctx, roots); dfree(ctx, n_roots); dfree(ctx, idx0); dfree(ctx, arrivals);
+    BVH_TRY(build_traversal_records(tree));
+    if (tree->have_flat) BVH_TRY(build_flat(tree));
+    return BVHGPU_OK;
+}
+
 #define INST(T)                                           \
+    template int optimize<T>(Tree<T>*, double);           \
     template int build_traversal_records<T>(Tree<T>*);    \
     template int build_flat<T>(Tree<T>*);                 \
     template int sah_cost<T>(Tree<T>*, double*);          \

@@ -32,6 +32,8 @@ struct BuildStatus {
     uint32_t nan_found;    // prep kernel saw a NaN coordinate
     uint32_t tickets;      // queue tickets handed out (diagnostics)
     uint32_t leaves_done;  // must equal n at the end
+    uint32_t rebuilt;      // optimize: shapes in the subtrees that were rebuilt
+    uint32_t pad[3];
 };
 
 struct bvhgpu_ctx {
@@ -110,6 +112,11 @@ template <class T> struct TreeletSession { void* params = nullptr; QSlot<T>* q =
 template <class T> int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletSession<T>* S);
 template <class T> int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S);
 
+// ---- rebuild session (build_sah.cu), used by optimize(): the exact builder restarted from inner nodes.  d_roots[0 .. *d_n_roots)
+// are node indices of disjoint subtrees, cb[node][6] the bounds of the shape centres below every node, idx0 the shapes in
+// leaf order.  Rewrites d_nodes / d_node_index / d_node_start of those subtrees in place.
+template <class T> int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0);
+
 // ---- lbvh.cu ----
 template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree, bool treelets);
 
@@ -118,6 +125,7 @@ template <class T> int build_traversal_records(Tree<T>* tree);   // d_tnodes
 template <class T> int build_flat(Tree<T>* tree);                // d_flat (reference FlatNode layout)
 template <class T> int sah_cost(Tree<T>* tree, double* out2);
 template <class T> int refit(Tree<T>* tree);                     // recompute child AABBs bottom-up from d_aabb
+template <class T> int optimize(Tree<T>* tree, double max_growth);   // refit + exact rebuild of the degraded subtrees
 
 // ---- traverse.cu ----
 // d_rays: rays on the device, or nullptr with h_rays = rays in host memory (chunked, overlapped H2D).

@@ -237,6 +237,19 @@ int bvhgpu_sah_cost_f64x3(bvhgpu_tree3d* tree, double* out2);
 int bvhgpu_refit_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n);
 int bvhgpu_refit_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n);
 
+/* ---- optimize: replaces Bvh::update_shapes after shapes moved (src/bvh/optimization.rs:290-302) ----
+ * The reference removes and re-inserts every changed shape sequentially (remove_shape :208-288, add_shape :70-206).
+ * The data-parallel counterpart: refit, then rebuild -- in place, with the exact 6-bucket SAH builder -- the
+ * outermost subtrees that contain a node whose surface area grew by more than `max_growth` (>= 1; e.g. 1.5).
+ * `aabbs` are the CURRENT AABBs of all n shapes (no list of changed indices is needed: unchanged subtrees are
+ * found by the growth test).  The node array stays in Bvh::build's preorder layout (the reference's does not,
+ * it appends and swap-removes nodes), node indices of shapes in rebuilt subtrees change: fetch them with
+ * bvhgpu_tree_nodes_* and pass them to BHShape::set_bh_node_index.  *rebuilt (may be NULL) = number of shapes in
+ * the rebuilt subtrees (0: the call was a pure refit).  Not the reference's tree: parity is on the invariants
+ * (assert_consistent, assert_tight), on hit sets, and on SAH cost against the oracle's update_shapes. */
+int bvhgpu_optimize_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n, double max_growth, size_t* rebuilt);
+int bvhgpu_optimize_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n, double max_growth, size_t* rebuilt);
+
 #ifdef __cplusplus
 }
 #endif

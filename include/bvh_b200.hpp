@@ -93,6 +93,7 @@ template <> struct Abi<float> {
     static int traverse(tree* t, int m, const ray* r, size_t n, uint32_t* off, uint32_t* h, size_t cap, size_t* tot) { return bvhgpu_traverse_f32x3(t, m, r, n, off, h, cap, tot); }
     static int fetch(tree* t, uint32_t* h, size_t cap) { return bvhgpu_traverse_fetch_f32x3(t, h, cap); }
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f32x3(t, a, n); }
+    static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f32x3(t, a, n, g, r); }
 };
 template <> struct Abi<double> {
     using aabb = bvh_aabb3d; using ray = bvh_ray3d; using node = bvh_node3d; using flat = bvh_flat3d; using tree = bvhgpu_tree3d;
@@ -103,6 +104,7 @@ template <> struct Abi<double> {
     static int traverse(tree* t, int m, const ray* r, size_t n, uint32_t* off, uint32_t* h, size_t cap, size_t* tot) { return bvhgpu_traverse_f64x3(t, m, r, n, off, h, cap, tot); }
     static int fetch(tree* t, uint32_t* h, size_t cap) { return bvhgpu_traverse_fetch_f64x3(t, h, cap); }
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f64x3(t, a, n); }
+    static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f64x3(t, a, n, g, r); }
 };
 struct Ctx {
     bvhgpu_ctx* h = nullptr;
@@ -244,6 +246,23 @@ template <class T> class Bvh {
             for (int k = 0; k < 3; ++k) { boxes[i].min[k] = a.min[k]; boxes[i].max[k] = a.max[k]; }
         }
         check(A::refit(tree_, boxes.data(), boxes.size()));
+    }
+    // Bvh::update_shapes (src/bvh/optimization.rs:290-302): refit + in-place exact rebuild of the subtrees that grew by more
+    // than `max_growth`; writes the new leaf node indices back (BHShape::set_bh_node_index).  Returns the rebuilt shape count.
+    template <class Shape> size_t update_shapes(std::vector<Shape>& shapes, double max_growth = 1.5) {
+        std::vector<typename A::aabb> boxes(shapes.size());
+        for (size_t i = 0; i < shapes.size(); ++i) {
+            const Aabb<T> a = shapes[i].aabb();
+            for (int k = 0; k < 3; ++k) { boxes[i].min[k] = a.min[k]; boxes[i].max[k] = a.max[k]; }
+        }
+        size_t rebuilt = 0;
+        check(A::optimize(tree_, boxes.data(), boxes.size(), max_growth, &rebuilt));
+        if (rebuilt) {
+            std::vector<uint32_t> idx(shapes.size());
+            check(A::nodes(tree_, nullptr, idx.data()));
+            for (size_t i = 0; i < shapes.size(); ++i) shapes[i].set_bh_node_index(idx[i]);
+        }
+        return rebuilt;
     }
     size_t num_shapes() const { return n_; }
 

@@ -235,6 +235,84 @@ def test_refit_keeps_the_tree_valid(api):
     _check_traverse(api, bvh, bvh.nodes, shapes, rays)
 
 
+def _preorder_layout_ok(nodes):
+    """Bvh::build's layout rule (bvh_node.rs:138-142): child_l = i + 1, child_r = i + 2 * (shapes under the left child)."""
+    inner = np.nonzero(nodes["child_l"] != 0xFFFFFFFF)[0]
+    cnt = np.where(nodes["child_l"] == 0xFFFFFFFF, 1, nodes["shape"]).astype(np.int64)
+    l, r = nodes["child_l"][inner].astype(np.int64), nodes["child_r"][inner].astype(np.int64)
+    return bool(np.all(l == inner + 1) and np.all(r == inner + 2 * cnt[l]) and np.all(cnt[inner] == cnt[l] + cnt[r])
+                and np.all(nodes["parent"][l] == inner) and np.all(nodes["parent"][r] == inner))
+
+
+@pytest.mark.parametrize("name,prec,frac,offset", [("cubes1000", "f32", 0.01, 10.0), ("cubes1000", "f32", 0.10, 10.0), ("cubes1000", "f32", 0.75, None),
+                                                   ("random5000", "f32", 0.05, 300.0), ("points3000", "f32", 0.2, 3.0),
+                                                   ("random3000", "f64", 0.1, 200.0), ("cubes200", "f64", 0.5, None)])
+def test_optimize_after_shapes_moved(api, name, prec, frac, offset):
+    """bvhgpu_optimize = the counterpart of Bvh::update_shapes (optimization.rs:290-302): refit + in-place exact rebuild of the
+    degraded subtrees.  Not the reference's tree (that is a sequential re-insertion), so parity is on the reference's own
+    acceptance criteria (optimization.rs:639-662: consistent and tight), on the layout rule, on hit sets, and on SAH cost
+    against the oracle's update_shapes run on the same motion."""
+    shapes = scene(name, prec).copy()
+    F = shapes["min"].dtype
+    bvh = api.Bvh.build(shapes, prec=prec)
+    built = O.build(shapes, prec)
+    rng = np.random.default_rng(5)
+    m = max(1, int(len(shapes) * frac))
+    moved = rng.choice(len(shapes), m, replace=False)
+    ext = float(shapes["max"].max() - shapes["min"].min())
+    delta = rng.uniform(-(offset or ext / 2), (offset or ext / 2), (m, 3)).astype(F)
+    shapes["min"][moved] += delta
+    shapes["max"][moved] += delta
+    # reference path: sequential re-insertion on the oracle
+    ref_nodes, _ = O.update_shapes(built.nodes, built.node_index, shapes, moved, prec)
+    assert O.is_consistent(ref_nodes, shapes, prec)
+    c_ref = O.sah_cost(ref_nodes, prec)[0]
+    # pure refit (on a second tree: optimize measures growth against the tree's state before the call), for comparison
+    other = api.Bvh.build(scene(name, prec), prec=prec)
+    other.refit(shapes)
+    c_refit = other.sah_cost()[0]
+    other.free()
+    rebuilt = bvh.optimize(shapes, 1.5)
+    nodes, node_index = bvh.nodes, bvh.node_index
+    assert 0 < rebuilt <= len(shapes)
+    assert _preorder_layout_ok(nodes)
+    assert O.is_consistent(nodes, shapes, prec) and O.is_tight(nodes, prec)
+    assert np.array_equal(nodes["shape"][node_index], np.arange(len(shapes)))           # set_bh_node_index targets
+    assert np.all(nodes["child_l"][node_index] == 0xFFFFFFFF)
+    c_opt = bvh.sah_cost()[0]
+    c_fresh = O.sah_cost(O.build(shapes, prec).nodes, prec)[0]
+    assert c_opt <= c_refit * (1 + 1e-9), (c_opt, c_refit)
+    assert c_opt <= 1.10 * c_ref, (c_opt, c_ref, c_fresh)                               # at least as good as the reference's update
+    rays = rays_for(shapes, 2000, seed=6, prec=prec)
+    _check_traverse(api, bvh, nodes, shapes, rays, prec=prec)
+    assert _flat_equal(bvh.flatten().nodes, O.flatten(nodes, prec))
+    bvh.free()
+
+
+def test_optimize_without_motion_is_a_no_op(api):
+    shapes = scene("random5000")
+    bvh = api.Bvh.build(shapes)
+    before, idx = bvh.nodes.copy(), bvh.node_index.copy()
+    assert bvh.optimize(shapes, 1.5) == 0
+    assert _nodes_equal(bvh.nodes, before) and np.array_equal(bvh.node_index, idx)
+    bvh.free()
+
+
+def test_optimize_global_motion_is_a_full_rebuild(api):
+    """Everything moved far: the tree root itself is degraded, the rebuild root is node 0, and the result is Bvh::build of the
+    moved shapes (general-position scene: the only order dependence of the builder, the degenerate halving, does not occur)."""
+    shapes = scene("random5000").copy()
+    bvh = api.Bvh.build(shapes)
+    rng = np.random.default_rng(8)
+    delta = rng.uniform(-20000, 20000, (len(shapes), 3)).astype(np.float32)
+    shapes["min"] += delta
+    shapes["max"] += delta
+    assert bvh.optimize(shapes, 1.5) == len(shapes)
+    want = O.build(shapes)
+    assert _nodes_equal(bvh.nodes, want.nodes) and np.array_equal(bvh.node_index, want.node_index)
+    bvh.free()
+
+
 def test_config2_full_size(api):
     """BASELINE.json configs[1]: 120k-triangle scene, 1M create_ray rays: bit-exact build + flatten, identical
     hit lists for all 1M rays (the oracle needs a few seconds for this)."""

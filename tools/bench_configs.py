@@ -98,6 +98,39 @@ ms = build_time(a64, "f64", capi.BUILD_LBVH_TREELET)
 out["build_lbvh_treelet_10M_f64"] = {"ms": ms, "Mprims_per_s": len(a64) / ms / 1e3}
 b64 = api.Bvh.build(a64, prec="f64", ctx=ctx)
 t0 = time.perf_counter(); b64.refit(a64); out["refit_10M_f64_host_call_ms"] = (time.perf_counter() - t0) * 1e3
+# optimize (Bvh::update_shapes counterpart): move 1 % of the 10 M shapes by <= 10.0 (optimization.rs:702), host call incl. the 480 MB H2D
+rng = np.random.default_rng(11)
+mv = rng.choice(len(a64), len(a64) // 100, replace=False)
+a64m = a64.copy(); dl = rng.uniform(-10.0, 10.0, (len(mv), 3)); a64m["min"][mv] += dl; a64m["max"][mv] += dl
+c0 = b64.sah_cost()[0]
+t0 = time.perf_counter(); rb = b64.optimize(a64m, 1.5); t_opt = (time.perf_counter() - t0) * 1e3
+c_opt = b64.sah_cost()[0]
+b64.free()
+b64r = api.Bvh.build(a64, prec="f64", ctx=ctx); b64r.refit(a64m); c_refit = b64r.sah_cost()[0]; b64r.free()
+b64f = api.Bvh.build(a64m, prec="f64", ctx=ctx); c_fresh = b64f.sah_cost()[0]; b64f.free()
+out["optimize_10M_f64_1pct"] = {"host_call_ms": t_opt, "rebuilt_shapes": rb, "sah_cost_before_motion": c0, "sah_cost_refit_only": c_refit,
+                                "sah_cost_optimize": c_opt, "sah_cost_fresh_build": c_fresh}
+del a64, a64m
+# the reference's own update benchmark shape (optimization.rs:693-725): 120 k triangles, p % moved by <= 10.0; oracle update_shapes beside it
+from oracle import oracle as O
+a = scenes.create_n_cubes_aabbs(10000)
+ob = O.build(a)
+for pct in (1, 10, 50):
+    rng = np.random.default_rng(pct)
+    mv = rng.choice(len(a), len(a) * pct // 100, replace=False)
+    am = a.copy(); dl = rng.uniform(-10.0, 10.0, (len(mv), 3)).astype(np.float32); am["min"][mv] += dl; am["max"][mv] += dl
+    t0 = time.perf_counter(); rn, _ = O.update_shapes(ob.nodes, ob.node_index, am, mv); t_ref = (time.perf_counter() - t0) * 1e3
+    g = api.Bvh.build(a, ctx=ctx)
+    ts = []
+    for k in range(5):
+        gg = api.Bvh.build(a, ctx=ctx); ctx.synchronize()
+        t0 = time.perf_counter(); rb = gg.optimize(am, 1.5); ts.append((time.perf_counter() - t0) * 1e3)
+        c_opt = gg.sah_cost()[0]; gg.free()
+    g.refit(am); c_refit = g.sah_cost()[0]; g.free()
+    f = api.Bvh.build(am, ctx=ctx); c_fresh = f.sah_cost()[0]; f.free()
+    out[f"optimize_120k_f32_{pct}pct"] = {"host_call_ms": sorted(ts)[2], "rebuilt_shapes": rb, "oracle_update_shapes_ms_1thread": t_ref,
+                                         "sah_cost_oracle_update_shapes": O.sah_cost(rn)[0], "sah_cost_refit_only": c_refit,
+                                         "sah_cost_optimize": c_opt, "sah_cost_fresh_build": c_fresh}
 print(json.dumps(out, indent=1))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
