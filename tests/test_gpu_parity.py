@@ -289,6 +289,45 @@ def test_optimize_after_shapes_moved(api, name, prec, frac, offset):
     bvh.free()
 
 
+@pytest.mark.parametrize("pct", [1, 10, 50])
+def test_optimize_vs_reference_update_120k(api, pct):
+    """The reference's update benchmark shape (optimization.rs:693-725: 120 k triangles, p % moved by at most 10.0): the oracle's
+    update_shapes and bvhgpu_optimize on the same motion; SAH cost of the result and wall time of both are recorded in
+    gpurun_out/optimize_vs_reference.json (the timing is informative, the assertions are on validity and cost)."""
+    import json, os, time
+    from bvh_b200 import scenes as S
+    a = S.create_n_cubes_aabbs(10000)
+    ob = O.build(a)
+    rng = np.random.default_rng(pct)
+    mv = rng.choice(len(a), len(a) * pct // 100, replace=False)
+    am = a.copy()
+    dl = rng.uniform(-10.0, 10.0, (len(mv), 3)).astype(np.float32)
+    am["min"][mv] += dl
+    am["max"][mv] += dl
+    t0 = time.perf_counter()
+    rn, _ = O.update_shapes(ob.nodes, ob.node_index, am, mv)
+    t_ref = (time.perf_counter() - t0) * 1e3
+    assert O.is_consistent(rn, am) and O.is_tight(rn)
+    g = api.Bvh.build(a)
+    g.ctx.synchronize()
+    t0 = time.perf_counter()
+    rebuilt = g.optimize(am, 1.5)
+    t_gpu = (time.perf_counter() - t0) * 1e3
+    nodes = g.nodes
+    assert O.is_consistent(nodes, am) and O.is_tight(nodes) and _preorder_layout_ok(nodes)
+    c_ref, c_opt = O.sah_cost(rn)[0], g.sah_cost()[0]
+    c_fresh = O.sah_cost(O.build(am, threads=O.hardware_threads()).nodes)[0]
+    assert c_opt <= 1.10 * c_ref, (c_opt, c_ref)
+    g.free()
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "optimize_vs_reference.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    rec = json.load(open(path)) if os.path.exists(path) else {}
+    rec[f"120k_f32_{pct}pct"] = {"moved": int(len(mv)), "oracle_update_shapes_ms_1thread": t_ref, "gpu_optimize_host_call_ms": t_gpu,
+                                 "rebuilt_shapes": int(rebuilt), "sah_cost_oracle_update_shapes": c_ref, "sah_cost_gpu_optimize": c_opt,
+                                 "sah_cost_fresh_build": c_fresh}
+    json.dump(rec, open(path, "w"), indent=1)
+
+
 def test_optimize_without_motion_is_a_no_op(api):
     shapes = scene("random5000")
     bvh = api.Bvh.build(shapes)
