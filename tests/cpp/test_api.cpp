@@ -1,5 +1,5 @@
 // tests/cpp/test_api.cpp -- the reference's fixed-scene tests (src/testbase.rs:66-267, src/bvh/bvh_impl.rs:557-690,
-// src/flat_bvh.rs:602-625, src/bvh/iter.rs:256-308, src/bvh/optimization.rs:421-455) written against the C++ host
+// src/flat_bvh.rs:602-625, src/bvh/iter.rs:256-308, src/bvh/optimization.rs:405-487) written against the C++ host
 // mirror include/bvh_b200.hpp, i.e. through the C ABI on the GPU.  Exit code 0 = all passed.
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +121,39 @@ int main() {
         auto after = bvh.nodes();
         const auto& root = after[0];
         REQUIRE(root.child_l_aabb.join(root.child_r_aabb).max[0] == 50.5f);
+    }
+    // test_update_shapes_simple_update, the update half (optimization.rs:456-487): after moving #1 to x = 40, update_shapes
+    // must make #1 and #2 siblings
+    {
+        std::vector<UnitBox> s{UnitBox(0, -50.0f, 0.0f, 0.0f), UnitBox(1, -40.0f, 0.0f, 0.0f), UnitBox(2, 50.0f, 0.0f, 0.0f)};
+        TBvh3 bvh = TBvh3::build(s);
+        s[1].pos[0] = 40.0f;
+        REQUIRE(bvh.update_shapes(s) == 3);                       // the whole (tiny) tree is the degraded subtree
+        auto nodes = bvh.nodes();
+        for (size_t i = 0; i < s.size(); ++i) REQUIRE(nodes[s[i].bh_node_index()].leaf && nodes[s[i].bh_node_index()].shape_index == i);
+        REQUIRE(nodes[s[1].bh_node_index()].parent_index == nodes[s[2].bh_node_index()].parent_index);
+    }
+    // test_consistent_after_update_shapes (optimization.rs:405-417): 21 boxes, six moved; the tree must contain every shape
+    // inside every ancestor's stored AABB afterwards (assert_consistent)
+    {
+        auto s = generate_aligned_boxes();
+        TBvh3 bvh = TBvh3::build(s);
+        const float to[6][3] = {{10, 1, 2}, {-10, -10, 10}, {-10, 10, 10}, {-10, 10, -10}, {11, 1, 2}, {11, 2, 2}};
+        for (int i = 0; i < 6; ++i) for (int k = 0; k < 3; ++k) s[i].pos[k] = to[i][k];
+        bvh.update_shapes(s);
+        auto nodes = bvh.nodes();
+        for (size_t i = 0; i < s.size(); ++i) {
+            size_t v = s[i].bh_node_index();
+            REQUIRE(nodes[v].leaf && nodes[v].shape_index == i);
+            const TAabb3 box = s[i].aabb();
+            while (v != 0) {
+                const size_t p = nodes[v].parent_index;
+                const TAabb3 stored = nodes[p].child_l_index == v ? nodes[p].child_l_aabb : nodes[p].child_r_aabb;
+                for (int k = 0; k < 3; ++k) REQUIRE(stored.min[k] <= box.min[k] && stored.max[k] >= box.max[k]);
+                v = p;
+            }
+        }
+        traverse_and_verify(TRay3({10.0f, -1000.0f, 2.0f}, {0.0f, 1.0f, 0.0f}), s, bvh, {-10});     // the box moved to (10, 1, 2)
     }
     // ray / aabb known answers (ray_impl.rs:244-299)
     {
