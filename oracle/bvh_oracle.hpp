@@ -645,6 +645,134 @@ inline void sah_cost(const Node<T>* nodes, uint32_t n_nodes, double& pseudo, dou
 }
 
 // ----------------------------------------------------------------------------
+// nearest_to (src/bvh/bvh_impl.rs:221-238, src/bvh/bvh_node.rs:327-372, src/flat_bvh.rs:513-562).
+// The shape distance is the caller's PointDistance::distance_squared; two are restated here:
+//   DIST_AABB     : the shape's AABB distance, as the reference's UnitBox does (testbase.rs:101-105)
+//   DIST_TRIANGLE : the reference's test triangle (testbase.rs:353-443, closest_point_triangle, "adapted from Embree")
+// ----------------------------------------------------------------------------
+template <class T> inline T aabb_min_distance_squared(const Aabb3<T>& a, const T p[3]) {    // aabb_impl.rs:618-629
+    T o[3];
+    for (int k = 0; k < 3; ++k) {
+        const T hs = (a.max[k] - a.min[k]) * T(0.5);          // half_size(), :479-481
+        const T c = a.min[k] + hs;
+        const T d = p[k] - c;
+        const T q = std::fabs(d) - hs;
+        o[k] = q > T(0) ? q : T(0);                            // x.max(0): 0 for NaN as well
+    }
+    return (o[0] * o[0] + o[1] * o[1]) + o[2] * o[2];
+}
+template <class T> inline T dot3(const T a[3], const T b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+template <class T> inline void closest_point_segment(const T p[3], const T a[3], const T b[3], T out[3]) {   // testbase.rs:353-363
+    T ab[3], ap[3];
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ap[k] = p[k] - a[k]; }
+    const T m = dot3(ab, ab);
+    T s = dot3(ab, ap) / m;
+    s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);               // clamp (NaN propagates as in Rust)
+    for (int k = 0; k < 3; ++k) out[k] = a[k] + s * ab[k];
+}
+template <class T> inline void closest_point_triangle(const T p[3], const T a[3], const T b[3], const T c[3], T out[3]) {   // :367-434
+    auto eq = [](const T* x, const T* y) { return x[0] == y[0] && x[1] == y[1] && x[2] == y[2]; };
+    const bool e_ab = eq(a, b), e_bc = eq(b, c), e_ac = eq(a, c);
+    if (e_ab && e_bc && e_ac) { for (int k = 0; k < 3; ++k) out[k] = a[k]; return; }
+    if (e_ab) { closest_point_segment(p, a, c, out); return; }
+    if (e_bc) { closest_point_segment(p, a, b, out); return; }
+    if (e_ac) { closest_point_segment(p, a, b, out); return; }
+    T ab[3], ac[3], ap[3], bp[3], cp[3];
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+    const T d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= T(0) && d2 <= T(0)) { for (int k = 0; k < 3; ++k) out[k] = a[k]; return; }
+    for (int k = 0; k < 3; ++k) bp[k] = p[k] - b[k];
+    const T d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= T(0) && d4 <= d3) { for (int k = 0; k < 3; ++k) out[k] = b[k]; return; }
+    for (int k = 0; k < 3; ++k) cp[k] = p[k] - c[k];
+    const T d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= T(0) && d5 <= d6) { for (int k = 0; k < 3; ++k) out[k] = c[k]; return; }
+    const T vc = d1 * d4 - d3 * d2;
+    if (vc <= T(0) && d1 >= T(0) && d3 <= T(0)) { const T v = d1 / (d1 - d3); for (int k = 0; k < 3; ++k) out[k] = a[k] + v * ab[k]; return; }
+    const T vb = d5 * d2 - d1 * d6;
+    if (vb <= T(0) && d2 >= T(0) && d6 <= T(0)) { const T v = d2 / (d2 - d6); for (int k = 0; k < 3; ++k) out[k] = a[k] + v * ac[k]; return; }
+    const T va = d3 * d6 - d5 * d4;
+    if (va <= T(0) && d4 - d3 >= T(0) && d5 - d6 >= T(0)) {
+        const T v = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int k = 0; k < 3; ++k) out[k] = b[k] + v * (c[k] - b[k]);
+        return;
+    }
+    const T denom = T(1) / (va + vb + vc);
+    const T v = vb * denom, w = vc * denom;
+    for (int k = 0; k < 3; ++k) out[k] = (a[k] + v * ab[k]) + w * ac[k];
+}
+enum { DIST_AABB = 0, DIST_TRIANGLE = 1 };
+template <class T> struct ShapeDist {
+    int kind; const Aabb3<T>* shapes; const T* tris;            // tris: 9 scalars per shape (a, b, c) for DIST_TRIANGLE
+    T operator()(uint32_t s, const T p[3]) const {
+        if (kind == DIST_AABB) return aabb_min_distance_squared(shapes[s], p);
+        T q[3], d[3];
+        closest_point_triangle(p, tris + 9 * (size_t)s, tris + 9 * (size_t)s + 3, tris + 9 * (size_t)s + 6, q);   // testbase.rs:436-443
+        for (int k = 0; k < 3; ++k) d[k] = p[k] - q[k];
+        return dot3(d, d);
+    }
+};
+// Bvh::nearest_to: returns the shape index (U32_MAX for an empty tree) and the distance (sqrt of the squared one, :237)
+template <class T>
+inline uint32_t nearest_to(const Node<T>* nodes, uint32_t n_nodes, const T p[3], const ShapeDist<T>& dist, T& out_dist, uint64_t* evals = nullptr) {
+    out_dist = T(0);
+    if (n_nodes == 0) return U32_MAX;
+    uint32_t best = U32_MAX;
+    T best_d = T(0);
+    // explicit stack replay of nearest_to_recursive (bvh_node.rs:327-372): a frame = (node, which of the two ordered children is next)
+    struct F { uint32_t idx[2]; T d[2]; int next; };
+    std::vector<F> stack;
+    auto enter = [&](uint32_t i) {
+        const Node<T>& nd = nodes[i];
+        if (nd.is_leaf()) {
+            const T d = dist(nd.shape, p);
+            if (evals) ++*evals;
+            if (best == U32_MAX || d < best_d) { best = nd.shape; best_d = d; }
+            return;
+        }
+        F f;
+        f.idx[0] = nd.child_l; f.d[0] = aabb_min_distance_squared(nd.l_aabb, p);
+        f.idx[1] = nd.child_r; f.d[1] = aabb_min_distance_squared(nd.r_aabb, p);
+        if (f.d[0] > f.d[1]) { std::swap(f.idx[0], f.idx[1]); std::swap(f.d[0], f.d[1]); }
+        f.next = 0;
+        stack.push_back(f);
+    };
+    enter(0);
+    while (!stack.empty()) {
+        F& f = stack.back();
+        if (f.next == 2) { stack.pop_back(); continue; }
+        const int k = f.next++;
+        const uint32_t child = f.idx[k];
+        const T cd = f.d[k];
+        if (best == U32_MAX || cd < best_d) enter(child);       // may push: `f` is not used after this
+    }
+    out_dist = std::sqrt(best_d);
+    return best;
+}
+// FlatBvh::nearest_to (flat_bvh.rs:513-562)
+template <class T>
+inline uint32_t nearest_to_flat(const FlatNode<T>* flat, uint32_t n_flat, const T p[3], const ShapeDist<T>& dist, T& out_dist) {
+    out_dist = T(0);
+    if (n_flat == 0) return U32_MAX;
+    uint32_t best = U32_MAX;
+    T best_d = T(0);
+    uint32_t index = 0;
+    while (index < n_flat) {
+        const FlatNode<T>& nd = flat[index];
+        if (nd.entry_index == U32_MAX) {                        // is_leaf()
+            const T d = dist(nd.shape_index, p);
+            if (best == U32_MAX || d < best_d) { best = nd.shape_index; best_d = d; }
+            index = nd.exit_index;
+        } else {
+            const T md = aabb_min_distance_squared(nd.aabb, p);
+            index = (best == U32_MAX || md < best_d) ? nd.entry_index : nd.exit_index;
+        }
+    }
+    out_dist = std::sqrt(best_d);
+    return best;
+}
+
+// ----------------------------------------------------------------------------
 // Bvh::update_shapes = remove_shape* then add_shape* (src/bvh/optimization.rs:70-389): the reference's
 // sequential re-insertion.  It appends / swap-removes nodes, so the result is NOT in build's preorder
 // layout any more (child_l != i+1 in general); every function above only follows child indices and

@@ -210,6 +210,35 @@ def sah_cost(nodes, prec="f32"):
     return float(out[0]), float(out[1])
 
 
+DIST_AABB, DIST_TRIANGLE = 0, 1
+
+
+def nearest_to(tree, shapes, points, prec="f32", flat=False, kind=DIST_AABB, tris=None):
+    """Bvh::nearest_to (bvh_impl.rs:221-238) / FlatBvh::nearest_to (flat_bvh.rs:513-562) for a batch of points.
+    Returns (shape index per point, 0xFFFFFFFF for an empty tree; distance per point)."""
+    d = _DT[prec]
+    tree = np.ascontiguousarray(tree, dtype=d["flat"] if flat else d["node"])
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    pts = np.ascontiguousarray(points, dtype=d["f"]).reshape(-1, 3)
+    tr = None if tris is None else np.ascontiguousarray(tris, dtype=d["f"]).reshape(-1, 9)
+    out_s = np.zeros(len(pts), dtype=np.uint32)
+    out_d = np.zeros(len(pts), dtype=d["f"])
+    getattr(lib(), f"orc_nearest_batch_{prec}")(C.c_int(1 if flat else 0), C.c_int(kind), _p(tree), C.c_uint32(len(tree)), _p(shapes), _p(tr),
+                                                _p(pts), C.c_uint64(len(pts)), _p(out_s), _p(out_d))
+    return out_s, out_d
+
+
+def shape_distances_squared(shapes, point, prec="f32", kind=DIST_AABB, tris=None):
+    """PointDistance::distance_squared of every shape to one point (brute-force side of nearest_to_and_verify, testbase.rs:290-312)."""
+    d = _DT[prec]
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    tr = None if tris is None else np.ascontiguousarray(tris, dtype=d["f"]).reshape(-1, 9)
+    pt = np.ascontiguousarray(point, dtype=d["f"]).reshape(3)
+    out = np.zeros(len(shapes), dtype=d["f"])
+    getattr(lib(), f"orc_shape_distance_{prec}")(C.c_int(kind), _p(shapes), _p(tr), C.c_uint32(len(shapes)), _p(pt), _p(out))
+    return out
+
+
 def update_shapes(nodes, node_index, shapes, changed, prec="f32"):
     """Bvh::update_shapes (src/bvh/optimization.rs:290-302): remove then re-insert `changed` (in this order) given the shapes'
     CURRENT AABBs.  Returns new (nodes, node_index); the node array is no longer in build's preorder layout."""

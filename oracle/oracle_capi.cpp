@@ -133,6 +133,18 @@ static uint64_t g_last_build_ns = 0;
     ORC_API void orc_sah_cost_##SUF(const Node<T>* nodes, uint32_t n_nodes, double* out2) {                  \
         sah_cost(nodes, n_nodes, out2[0], out2[1]);                                                          \
     }                                                                                                        \
+    /* nearest_to for nq points; use_flat: FlatBvh::nearest_to; kind 0 = AABB distance, 1 = triangle distance (tris: 9 per shape) */ \
+    ORC_API void orc_nearest_batch_##SUF(int use_flat, int kind, const void* tree, uint32_t n_tree, const Aabb3<T>* shapes, const T* tris, \
+                                         const T* points, uint64_t nq, uint32_t* out_shape, T* out_dist) {     \
+        const ShapeDist<T> sd{kind, shapes, tris};                                                           \
+        for (uint64_t i = 0; i < nq; ++i)                                                                    \
+            out_shape[i] = use_flat ? nearest_to_flat((const FlatNode<T>*)tree, n_tree, points + 3 * i, sd, out_dist[i]) \
+                                    : nearest_to((const Node<T>*)tree, n_tree, points + 3 * i, sd, out_dist[i]); \
+    }                                                                                                        \
+    ORC_API void orc_shape_distance_##SUF(int kind, const Aabb3<T>* shapes, const T* tris, uint32_t n, const T* point, T* out_d2) { \
+        const ShapeDist<T> sd{kind, shapes, tris};                                                           \
+        for (uint32_t s = 0; s < n; ++s) out_d2[s] = sd(s, point);                                           \
+    }                                                                                                        \
     /* Bvh::update_shapes on (nodes, node_index) in place; returns the node count or U32_MAX on a reference panic path */ \
     ORC_API uint32_t orc_update_shapes_##SUF(Node<T>* nodes, uint32_t n_nodes, uint32_t* node_index, uint32_t n_shapes, \
                                              const Aabb3<T>* shapes, const uint32_t* changed, uint32_t n_changed) { \

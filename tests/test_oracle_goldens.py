@@ -459,3 +459,50 @@ def test_update_shapes_bvh_12k_75p():                      # optimization.rs:639
     r = O.traverse(nodes, moved, rays, O.MODE_RECURSIVE)
     for k, got in enumerate(O.per_ray_lists(r.offsets, r.hits)):
         assert sorted(got.tolist()) == _brute_force(moved, rays[k])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nearest_to (src/bvh/bvh_impl.rs:221-238, src/flat_bvh.rs:513-562)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flat", [False, True], ids=["bvh", "flat"])
+def test_nearest_to_doc_example(flat):                     # bvh_impl.rs / flat_bvh.rs doc tests: 1000 unit boxes on the diagonal
+    pos = np.repeat(np.arange(1000, dtype=np.float32)[:, None], 3, axis=1)
+    shapes = O.unit_boxes(pos)
+    b = O.build(shapes)
+    tree = O.flatten(b.nodes) if flat else b.nodes
+    s, d = O.nearest_to(tree, shapes, [[5.0, 5.7, 5.3]], flat=flat)
+    assert int(s[0]) == 5
+    q = abs(np.float32(5.7) - np.float32(5.0)) - np.float32(0.5)                 # outside only along y
+    assert d[0] == np.sqrt(q * q)
+
+
+def test_aabb_min_distance_squared_doc():                  # aabb_impl.rs:598-614: the doc test's 10.0
+    box = O.make_aabbs([[-1.0, -1.0, -1.0]], [[1.0, 1.0, 1.0]])
+    assert np.sqrt(O.shape_distances_squared(box, [11.0, 0.0, 0.0])[0]) == 10.0
+    assert O.shape_distances_squared(box, [0.5, -0.5, 0.0])[0] == 0.0            # inside
+
+
+@pytest.mark.parametrize("flat", [False, True], ids=["bvh", "flat"])
+def test_nearest_to_some_bh(flat):                         # testbase.rs:270-312 on 12 000 triangles
+    shapes, tris = O.create_n_cubes(1000, want_tris=True)
+    b = O.build(shapes)
+    tree = O.flatten(b.nodes) if flat else b.nodes
+    bounds = O.make_aabbs([[-1000.0] * 3], [[1000.0] * 3])
+    ref_point, _ = O.next_points(1, bounds=bounds, seed=0)                       # the reference re-seeds with 0 for every query
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([ref_point.reshape(1, 3), rng.uniform(-100000, 100000, (60, 3)).astype(np.float32),
+                          tris.reshape(-1, 3)[rng.integers(0, len(tris) * 3, 20)]])          # some points ON the geometry
+    s, d = O.nearest_to(tree, shapes, pts, flat=flat, kind=O.DIST_TRIANGLE, tris=tris)
+    for k, p in enumerate(pts):
+        d2 = O.shape_distances_squared(shapes, p, kind=O.DIST_TRIANGLE, tris=tris)
+        assert d[k] == np.sqrt(d2.min()), k                                       # same arithmetic on both sides: exact
+        assert d2[int(s[k])] == d2.min()
+
+
+def test_nearest_to_empty_and_single():
+    s, d = O.nearest_to(np.zeros(0, dtype=O.NODE3F), np.zeros(0, dtype=O.AABB3F), [[0.0, 0.0, 0.0]])
+    assert int(s[0]) == 0xFFFFFFFF
+    one = O.unit_boxes([[3.0, 0.0, 0.0]])
+    b = O.build(one)
+    s, d = O.nearest_to(b.nodes, one, [[0.0, 0.0, 0.0]])
+    assert int(s[0]) == 0 and d[0] == 2.5
