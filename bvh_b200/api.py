@@ -272,6 +272,43 @@ class Bvh:
             capi.check(st)
         return offsets, hits[: total.value]
 
+    def nearest_to_batch(self, points, mode: int = capi.TRAVERSE_BVH):
+        """Bvh::nearest_to / FlatBvh::nearest_to (bvh_impl.rs:221-238, flat_bvh.rs:513-562) for shapes whose PointDistance is their AABB
+        distance (the reference's UnitBox): (shape index per point, U32_MAX for an empty tree; distance per point)."""
+        p = np.ascontiguousarray(points, dtype=self._d["scalar"]).reshape(-1, 3)
+        shape = np.zeros(len(p), dtype=np.uint32)
+        dist = np.zeros(len(p), dtype=self._d["scalar"])
+        capi.check(getattr(capi.lib(), f"bvhgpu_nearest_{self._d['suffix']}")(self._h, mode, _ptr(p), len(p), _ptr(shape), _ptr(dist)))
+        return shape, dist
+
+    def nearest_candidates(self, points):
+        """For shapes with their own PointDistance: CSR (offsets, shape indices) of candidate lists that contain the nearest shape of
+        every point; evaluate distance_squared on each list and keep the minimum (see `nearest_to`)."""
+        p = np.ascontiguousarray(points, dtype=self._d["scalar"]).reshape(-1, 3)
+        n = len(p)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        cap = max(64 * n, 1024)
+        cand = np.zeros(cap, dtype=np.uint32)
+        total = C.c_size_t(0)
+        st = getattr(capi.lib(), f"bvhgpu_nearest_candidates_{self._d['suffix']}")(self._h, _ptr(p), n, _ptr(offsets), _ptr(cand), cap, C.byref(total))
+        if st == capi.ERR_CAPACITY and total.value <= U32_MAX:
+            cand = np.zeros(total.value, dtype=np.uint32)
+            capi.check(getattr(capi.lib(), f"bvhgpu_traverse_fetch_{self._d['suffix']}")(self._h, _ptr(cand), total.value))
+        else:
+            capi.check(st)
+        return offsets, cand[: total.value]
+
+    def nearest_to(self, point, shapes, distance_squared):
+        """BoundingHierarchy::nearest_to for one point and an arbitrary shape distance: `distance_squared(shape, point)` is the shape's
+        PointDistance::distance_squared.  Returns (shape, distance) or None for an empty tree."""
+        off, cand = self.nearest_candidates([point])
+        best = None
+        for s in cand[off[0]:off[1]]:
+            d = distance_squared(shapes[int(s)], point)
+            if best is None or d < best[1]:
+                best = (shapes[int(s)], d)
+        return None if best is None else (best[0], float(np.sqrt(best[1])))
+
     def traverse_dev(self, rays_ptr: int, nrays: int, offsets_ptr: int, hits_ptr: int, cap: int, mode: int = capi.TRAVERSE_BVH,
                      want_total: bool = False):
         total = C.c_size_t(0)

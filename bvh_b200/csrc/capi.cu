@@ -268,6 +268,60 @@ static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, 
 }
 
 template <class T>
+static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist) {
+    if (!tree || (n && (!points || !out_shape || !out_dist))) { set_error("nearest: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (n == 0) return BVHGPU_OK;
+    T *d_p = nullptr, *d_d = nullptr;
+    uint32_t* d_s = nullptr;
+    BVH_TRY(dalloc_t(ctx, &d_p, n * 3));
+    BVH_TRY(dalloc_t(ctx, &d_d, n));
+    BVH_TRY(dalloc_t(ctx, &d_s, n));
+    BVH_CUDA_TRY(cudaMemcpyAsync(d_p, points, sizeof(T) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = nearest_device<T>(tree, mode, d_p, n, d_s, d_d);
+    if (rc == BVHGPU_OK) {
+        BVH_CUDA_TRY(cudaMemcpyAsync(out_shape, d_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BVH_CUDA_TRY(cudaMemcpyAsync(out_dist, d_d, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    dfree(ctx, d_p); dfree(ctx, d_d); dfree(ctx, d_s);
+    return rc;
+}
+
+template <class T>
+static int nearest_candidates_host_impl(Tree<T>* tree, const T* points, size_t n, uint32_t* offsets, uint32_t* cand, size_t cap, size_t* total) {
+    if (!tree || (n && !points) || !offsets) { set_error("nearest_candidates: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    T* d_p = nullptr;
+    if (n) {
+        BVH_TRY(dalloc_t(ctx, &d_p, n * 3));
+        BVH_CUDA_TRY(cudaMemcpyAsync(d_p, points, sizeof(T) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 16 * n), 1024), tot = 0;
+    int rc = BVHGPU_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_result_buffers(tree, n, want);
+        if (rc != BVHGPU_OK) break;
+        rc = nearest_candidates_device<T>(tree, d_p, n, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
+        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }
+        break;
+    }
+    dfree(ctx, d_p);
+    if (total) *total = tot;
+    if (rc != BVHGPU_OK) return rc;
+    BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int ret = BVHGPU_OK;
+    if (cand && tot <= cap) { if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(cand, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream)); }
+    else if (tot > cap) { set_error("nearest_candidates: %zu candidates do not fit the caller's capacity %zu (use bvhgpu_traverse_fetch_*)", tot, cap); ret = BVHGPU_ERR_CAPACITY; }
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ret;
+}
+
+template <class T>
 static int ordered_host_impl(Tree<T>* tree, const typename Traits<T>::Ray* rays, size_t nrays, int ascending,
                              uint32_t* offsets, uint32_t* hits, T* dists, size_t cap, size_t* total) {
     if (!tree || (nrays && !rays) || !offsets || (cap && (!hits || !dists))) { set_error("traverse_ordered: null argument"); return BVHGPU_ERR_INVALID; }
@@ -557,6 +611,13 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
         if (!tree || !dev_offsets || (n && !dev_queries)) { set_error("query_dev: null argument"); return BVHGPU_ERR_INVALID; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
         return query_device<T>(tree, mode, kind, (const T*)dev_queries, n, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_nearest_##SUF(TREE* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist) { \
+        return nearest_host_impl<T>(tree, mode, points, n, out_shape, out_dist);                                         \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_nearest_candidates_##SUF(TREE* tree, const T* points, size_t n, uint32_t* offsets, uint32_t* cand, \
+                                                   size_t cap, size_t* total) {                                           \
+        return nearest_candidates_host_impl<T>(tree, points, n, offsets, cand, cap, total);                               \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_ordered_##SUF(TREE* tree, const RAY* rays, size_t nrays, int ascending, uint32_t* offsets,      \
                                                  uint32_t* hits, T* dists, size_t cap, size_t* total) {                  \

@@ -141,6 +141,9 @@ template <class T> int traverse_ordered_device(Tree<T>* tree, const typename Tra
                                                uint32_t* d_offsets, uint32_t* d_hits, T* d_dists, size_t cap, size_t* total);
 // Aabb / Point / Ball queries (device pointers); two-pass count / fill.
 template <class T> int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t nq, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total);
+// nearest_to for a batch of points (device pointers): exact reference walk for AABB-distance shapes; candidate lists for any shape
+template <class T> int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist);
+template <class T> int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint32_t* d_offsets, uint32_t* d_cand, size_t cap, size_t* total);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
                                        typename Traits<T>::Ray* d_rays);
 

@@ -655,6 +655,38 @@ template <class T> struct Query<T, BVHGPU_QUERY_BALL> {
     }
 };
 
+// Internal kind: every shape whose AABB lies within squared distance U of a point, record {p, U}.  The lower bound
+// sum_k max(min_k - p_k, p_k - max_k, 0)^2 is monotone under box containment in floating point (subtraction, squaring
+// and addition of non-negative terms are monotone), so pruning an inner box can never lose a shape it contains.
+constexpr int QUERY_WITHIN = 4;
+template <class T> __device__ __forceinline__ T box_lower_d2(const T p[3], const T bmn[3], const T bmx[3]) {
+    T d2 = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const T a = sub_rn(bmn[i], p[i]), b = sub_rn(p[i], bmx[i]);
+        T d = a > b ? a : b;
+        d = d > T(0) ? d : T(0);
+        d2 = add_rn(d2, mul_rn(d, d));
+    }
+    return d2;
+}
+template <class T> __device__ __forceinline__ T box_upper_d2(const T p[3], const T bmn[3], const T bmx[3]) {   // farthest corner
+    T d2 = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const T a = fabs(sub_rn(p[i], bmn[i])), b = fabs(sub_rn(p[i], bmx[i]));
+        const T d = a > b ? a : b;
+        d2 = add_rn(d2, mul_rn(d, d));
+    }
+    return d2;
+}
+template <class T> struct Query<T, QUERY_WITHIN> {
+    T p[3], u;
+    __device__ __forceinline__ void load(const T* q) { for (int k = 0; k < 3; ++k) p[k] = __ldg(q + k); u = __ldg(q + 3); }
+    static constexpr int STRIDE = 4;
+    __device__ __forceinline__ bool hit(const T bmn[3], const T bmx[3]) const { return box_lower_d2(p, bmn, bmx) <= u; }
+};
+
 template <class T, int KIND, bool FLAT, class Emit>
 __device__ __forceinline__ void walk_query(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                            const typename Traits<T>::DAabb* __restrict__ aabb, const Query<T, KIND>& q, Emit emit) {
@@ -719,7 +751,7 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
     cudaStream_t st = ctx->stream;
     if (nq > 0x7FFFFFFFull) { set_error("query: too many queries"); return BVHGPU_ERR_INVALID; }
     if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("query: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
-    if (kind != BVHGPU_QUERY_AABB && kind != BVHGPU_QUERY_POINT && kind != BVHGPU_QUERY_BALL) { set_error("query: bad kind %d", kind); return BVHGPU_ERR_INVALID; }
+    if (kind != BVHGPU_QUERY_AABB && kind != BVHGPU_QUERY_POINT && kind != BVHGPU_QUERY_BALL && kind != QUERY_WITHIN) { set_error("query: bad kind %d", kind); return BVHGPU_ERR_INVALID; }
     if (nq == 0 || tree->n == 0) {
         BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nq + 1), st));
         if (total) *total = 0;
@@ -738,7 +770,8 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     int rc = kind == BVHGPU_QUERY_AABB  ? query_launch<T, BVHGPU_QUERY_AABB>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
            : kind == BVHGPU_QUERY_POINT ? query_launch<T, BVHGPU_QUERY_POINT>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
-                                        : query_launch<T, BVHGPU_QUERY_BALL>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap);
+           : kind == BVHGPU_QUERY_BALL  ? query_launch<T, BVHGPU_QUERY_BALL>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
+                                        : query_launch<T, QUERY_WITHIN>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap);
     if (rc == BVHGPU_OK && total) {
         unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
         BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -752,6 +785,169 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
 }
 template int query_device<float>(Tree<float>*, int, int, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 template int query_device<double>(Tree<double>*, int, int, const double*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+
+
+// ---- nearest_to: Bvh::nearest_to (src/bvh/bvh_impl.rs:221-238, src/bvh/bvh_node.rs:327-372) and
+// FlatBvh::nearest_to (src/flat_bvh.rs:513-562) for a batch of points ---------------------------------------------------
+// The reference calls the shape's own PointDistance::distance_squared at the leaves -- user code.  Two device forms:
+//   nearest_kernel        : shapes whose distance IS their AABB distance (the reference's UnitBox, testbase.rs:101-105):
+//                           the reference's walk replayed exactly -- children ordered by Aabb::min_distance_squared
+//                           (aabb_impl.rs:618-629, same operation order), strict `<` pruning, first minimum kept.
+//                           The recursion becomes a stackless walk over parent links: on the way back up the two child
+//                           distances are recomputed (same bits), so any tree depth works without a stack.
+//   nearest_bound_kernel  : any shape inside its AABB: U = min over shapes of the squared distance to the FARTHEST
+//                           corner of the shape's AABB bounds the true nearest distance from above; the candidates
+//                           {s : lower(AABB_s) <= U} (QUERY_WITHIN) contain the nearest shape, and the caller evaluates its
+//                           own distance on that short list.
+template <class T> __device__ __forceinline__ T aabb_min_d2(const T p[3], const T mn[3], const T mx[3]) {     // aabb_impl.rs:618-629
+    T o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T hs = mul_rn(sub_rn(mx[k], mn[k]), T(0.5));             // half_size(), :479-481
+        const T c = add_rn(mn[k], hs);
+        const T q = sub_rn(fabs(sub_rn(p[k], c)), hs);
+        o[k] = q > T(0) ? q : T(0);
+    }
+    return add_rn(add_rn(mul_rn(o[0], o[0]), mul_rn(o[1], o[1])), mul_rn(o[2], o[2]));
+}
+__device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ double sqrt_rn(double x) { return __dsqrt_rn(x); }
+
+// One walk for both kernels.  EXACT: reference semantics (order by min distance, prune with `<`, leaf value = AABB distance).
+// !EXACT: leaf value = farthest-corner bound, children ordered and pruned by the monotone lower bound, ties kept (`<=`).
+template <class T, bool EXACT>
+__device__ __forceinline__ void nearest_walk(const typename Traits<T>::Node* __restrict__ nodes, const typename Traits<T>::DAabb* __restrict__ aabb,
+                                             const T p[3], uint32_t& best, T& best_d) {
+    best = BVH_INVALID;
+    best_d = Traits<T>::inf();
+    uint32_t node = 0, from = BVH_INVALID;                 // from: the child we are returning from (BVH_INVALID = arriving from the parent)
+    for (;;) {
+        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nodes + node));      // parent, child_l, child_r, shape
+        if (meta.y == BVH_INVALID) {                       // leaf
+            T mn[3], mx[3];
+            load_aabb(aabb + meta.w, mn, mx);
+            const T d = EXACT ? aabb_min_d2(p, mn, mx) : box_upper_d2(p, mn, mx);
+            if (best == BVH_INVALID || d < best_d) { best = meta.w; best_d = d; }
+            if (node == 0) return;
+            from = node; node = meta.x;
+            continue;
+        }
+        const typename Traits<T>::Node& nd = nodes[node];
+        T lmn[3], lmx[3], rmn[3], rmx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lmn[k] = __ldg(&nd.l_aabb.min[k]); lmx[k] = __ldg(&nd.l_aabb.max[k]); rmn[k] = __ldg(&nd.r_aabb.min[k]); rmx[k] = __ldg(&nd.r_aabb.max[k]); }
+        const T dl = EXACT ? aabb_min_d2(p, lmn, lmx) : box_lower_d2(p, lmn, lmx);
+        const T dr = EXACT ? aabb_min_d2(p, rmn, rmx) : box_lower_d2(p, rmn, rmx);
+        const bool swap = dl > dr;                          // bvh_node.rs:349-351
+        const uint32_t near_i = swap ? meta.z : meta.y, far_i = swap ? meta.y : meta.z;
+        const T near_d = swap ? dr : dl, far_d = swap ? dl : dr;
+        uint32_t next = BVH_INVALID;
+        if (from == BVH_INVALID) {                          // first visit: the nearer child, if it can still win
+            if (best == BVH_INVALID || (EXACT ? near_d < best_d : near_d <= best_d)) next = near_i;
+            else from = near_i;                             // skipped: as if we had just returned from it
+        }
+        if (next == BVH_INVALID && from == near_i) {        // back from (or past) the nearer child: now the farther one
+            if (best == BVH_INVALID || (EXACT ? far_d < best_d : far_d <= best_d)) next = far_i;
+            else from = far_i;
+        }
+        if (next != BVH_INVALID) { node = next; from = BVH_INVALID; continue; }
+        if (node == 0) return;                              // back from the farther child of the root
+        from = node; node = meta.x;
+    }
+}
+template <class T, bool FLAT>
+__global__ void __launch_bounds__(128) nearest_kernel(const typename Traits<T>::Node* __restrict__ nodes, const typename Traits<T>::Flat* __restrict__ flat,
+                                                      uint32_t n_flat, const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                      const T* __restrict__ points, uint32_t nq, uint32_t* __restrict__ out_shape, T* __restrict__ out_dist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    T p[3];
+    for (int k = 0; k < 3; ++k) p[k] = points[3 * (size_t)i + k];
+    uint32_t best = BVH_INVALID;
+    T best_d = T(0);
+    if (!FLAT) {
+        nearest_walk<T, true>(nodes, aabb, p, best, best_d);
+    } else {                                                // flat_bvh.rs:524-558
+        uint32_t index = 0;
+        while (index < n_flat) {
+            const typename Traits<T>::Flat& f = flat[index];
+            const uint32_t entry = f.entry_index, exit_i = f.exit_index;
+            if (entry == BVH_INVALID) {
+                T mn[3], mx[3];
+                const uint32_t shape = f.shape_index;
+                load_aabb(aabb + shape, mn, mx);
+                const T d = aabb_min_d2(p, mn, mx);
+                if (best == BVH_INVALID || d < best_d) { best = shape; best_d = d; }
+                index = exit_i;
+            } else {
+                T mn[3], mx[3];
+                for (int k = 0; k < 3; ++k) { mn[k] = f.aabb.min[k]; mx[k] = f.aabb.max[k]; }
+                const T md = aabb_min_d2(p, mn, mx);
+                index = (best == BVH_INVALID || md < best_d) ? entry : exit_i;
+            }
+        }
+    }
+    out_shape[i] = best;
+    out_dist[i] = sqrt_rn(best_d);                          // bvh_impl.rs:237
+}
+template <class T>
+__global__ void __launch_bounds__(128) nearest_bound_kernel(const typename Traits<T>::Node* __restrict__ nodes, const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                            const T* __restrict__ points, uint32_t nq, T* __restrict__ records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    T p[3];
+    for (int k = 0; k < 3; ++k) p[k] = points[3 * (size_t)i + k];
+    uint32_t best;
+    T u;
+    nearest_walk<T, false>(nodes, aabb, p, best, u);
+    u = mul_rn(u, add_rn(T(1), mul_rn(T(16), Traits<T>::eps())));      // the bound itself is a rounded sum: keep it an upper bound
+    for (int k = 0; k < 3; ++k) records[4 * (size_t)i + k] = p[k];
+    records[4 * (size_t)i + 3] = u;
+}
+
+template <class T>
+int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (nq > 0x7FFFFFFFull) { set_error("nearest: too many points"); return BVHGPU_ERR_INVALID; }
+    if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("nearest: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
+    if (nq == 0) return BVHGPU_OK;
+    BVH_TRY(resolve_status(tree));
+    if (tree->n == 0) {                                     // empty tree: None (bvh_impl.rs:229-231)
+        BVH_CUDA_TRY(cudaMemsetAsync(d_shape, 0xFF, sizeof(uint32_t) * nq, st));
+        BVH_CUDA_TRY(cudaMemsetAsync(d_dist, 0, sizeof(T) * nq, st));
+        return BVHGPU_OK;
+    }
+    const unsigned grid = (unsigned)((nq + 127) / 128);
+    if (mode == BVHGPU_TRAVERSE_FLAT) {
+        if (!tree->have_flat) BVH_TRY(build_flat(tree));
+        nearest_kernel<T, true><<<grid, 128, 0, st>>>(tree->d_nodes, tree->d_flat, (uint32_t)tree->n_flat, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist);
+    } else {
+        nearest_kernel<T, false><<<grid, 128, 0, st>>>(tree->d_nodes, nullptr, 0u, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist);
+    }
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+template <class T>
+int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint32_t* d_offsets, uint32_t* d_cand, size_t cap, size_t* total) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    if (nq > 0x7FFFFFFFull) { set_error("nearest_candidates: too many points"); return BVHGPU_ERR_INVALID; }
+    BVH_TRY(resolve_status(tree));
+    if (nq == 0 || tree->n == 0) return query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, nullptr, nq, d_offsets, d_cand, cap, total);
+    T* rec = nullptr;
+    BVH_TRY(dalloc_t(ctx, &rec, nq * 4));
+    nearest_bound_kernel<T><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(tree->d_nodes, tree->d_aabb, d_points, (uint32_t)nq, rec);
+    ctx->launches++;
+    const int rc = query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, rec, nq, d_offsets, d_cand, cap, total);
+    dfree(ctx, rec);
+    return rc;
+}
+template int nearest_device<float>(Tree<float>*, int, const float*, size_t, uint32_t*, float*);
+template int nearest_device<double>(Tree<double>*, int, const double*, size_t, uint32_t*, double*);
+template int nearest_candidates_device<float>(Tree<float>*, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int nearest_candidates_device<double>(Tree<double>*, const double*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 
 // ---- ordered traversal: hits of every ray sorted by AABB entry distance (nearest first) or by exit
 // distance (farthest first), with the distance.  The reference's DistanceTraverseIterator (src/bvh/distance_traverse.rs) is

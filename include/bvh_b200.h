@@ -222,6 +222,25 @@ int bvhgpu_traverse_ordered_f32x3(bvhgpu_tree3f* tree, const bvh_ray3f* rays, si
 int bvhgpu_traverse_ordered_f64x3(bvhgpu_tree3d* tree, const bvh_ray3d* rays, size_t nrays, int ascending,
                                   uint32_t* offsets, uint32_t* hits, double* dists, size_t cap, size_t* total);
 
+/* ---- nearest_to: batched Bvh::nearest_to (src/bvh/bvh_impl.rs:221-238, src/bvh/bvh_node.rs:327-372) and
+ * FlatBvh::nearest_to (src/flat_bvh.rs:513-562).  The reference calls the shape's own PointDistance::distance_squared at the
+ * leaves (user code), so there are two forms.  `points`: 3 T per query point, host pointers.
+ *   bvhgpu_nearest_*            for shapes whose distance IS their AABB's (as the reference's UnitBox, src/testbase.rs:101-105):
+ *                               the reference's walk replayed exactly (children ordered by Aabb::min_distance_squared,
+ *                               src/aabb/aabb_impl.rs:618-629; strict `<`; first minimum kept).  out_shape[i] = shape index
+ *                               (BVHGPU_INVALID_INDEX for an empty tree), out_dist[i] = distance (sqrt, as the reference returns).
+ *                               `mode` selects Bvh (BVHGPU_TRAVERSE_BVH) or FlatBvh (BVHGPU_TRAVERSE_FLAT) visiting order.
+ *   bvhgpu_nearest_candidates_* for ANY shape contained in its AABB: CSR lists that are guaranteed to contain the nearest shape
+ *                               of every point (all shapes whose AABB is at most as far as the smallest farthest-corner
+ *                               distance of any shape's AABB); the shim evaluates distance_squared on that short list and
+ *                               keeps the minimum. */
+int bvhgpu_nearest_f32x3(bvhgpu_tree3f* tree, int mode, const float* points, size_t n, uint32_t* out_shape, float* out_dist);
+int bvhgpu_nearest_f64x3(bvhgpu_tree3d* tree, int mode, const double* points, size_t n, uint32_t* out_shape, double* out_dist);
+int bvhgpu_nearest_candidates_f32x3(bvhgpu_tree3f* tree, const float* points, size_t n, uint32_t* offsets, uint32_t* cand,
+                                    size_t cap, size_t* total);
+int bvhgpu_nearest_candidates_f64x3(bvhgpu_tree3d* tree, const double* points, size_t n, uint32_t* offsets, uint32_t* cand,
+                                    size_t cap, size_t* total);
+
 /* Ray::new for a batch (src/ray/ray_impl.rs:70-80): normalise, inv = 1/direction. Device pointers. */
 int bvhgpu_rays_new_dev_f32x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);
 int bvhgpu_rays_new_dev_f64x3(bvhgpu_ctx* ctx, const void* dev_origins, const void* dev_directions, size_t n, void* dev_rays);

@@ -328,6 +328,65 @@ def test_optimize_vs_reference_update_120k(api, pct):
     json.dump(rec, open(path, "w"), indent=1)
 
 
+# ---- nearest_to ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,prec", [("cubes1000", "f32"), ("random5000", "f32"), ("points3000", "f32"), ("skew3000", "f32"), ("boxes21", "f32"),
+                                       ("cubes1", "f32"), ("random3000", "f64"), ("huge300", "f64")])
+def test_nearest_to_matches_the_reference_walk(api, name, prec):
+    """bvhgpu_nearest_* replays Bvh::nearest_to / FlatBvh::nearest_to for AABB-distance shapes: same shape (ties included: the walk
+    order is the reference's) and bit-identical distance as the oracle, in both visiting orders."""
+    from bvh_b200 import capi
+    shapes = scene(name, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    want = O.build(shapes, prec)
+    rng = np.random.default_rng(12)
+    lo, hi = shapes["min"].min(axis=0).astype(float), shapes["max"].max(axis=0).astype(float)
+    pts = rng.uniform(lo - (hi - lo) * 0.2 - 1, hi + (hi - lo) * 0.2 + 1, (3000, 3))
+    pts[:200] = (shapes["min"][rng.integers(0, len(shapes), 200)] + shapes["max"][rng.integers(0, len(shapes), 200)]) * 0.5   # inside / on boxes: ties at 0
+    for flat, mode in ((False, capi.TRAVERSE_BVH), (True, capi.TRAVERSE_FLAT)):
+        tree = O.flatten(want.nodes, prec) if flat else want.nodes
+        ws, wd = O.nearest_to(tree, shapes, pts, prec, flat=flat)
+        gs, gd = bvh.nearest_to_batch(pts, mode=mode)
+        assert np.array_equal(gs, ws), (name, flat, int(np.sum(gs != ws)))
+        assert np.array_equal(gd, wd), (name, flat)
+    bvh.free()
+
+
+def test_nearest_to_empty_tree(api):
+    bvh = api.Bvh.build(scene("empty"))
+    s, d = bvh.nearest_to_batch([[0.0, 0.0, 0.0], [1.0, 2.0, 3.0]])
+    assert np.all(s == 0xFFFFFFFF) and np.all(d == 0)
+    off, cand = bvh.nearest_candidates([[0.0, 0.0, 0.0]])
+    assert off.tolist() == [0, 0] and len(cand) == 0
+
+
+def test_nearest_to_doc_example_and_some_bh(api):
+    """The reference's doc example (1000 unit boxes on the diagonal, query (5, 5.7, 5.3) -> shape 5) and nearest_to_some_bh
+    (testbase.rs:270-312: 12 000 triangles with their own PointDistance, brute force as the judge): the candidate lists from
+    the device plus the shape's distance function on the host give the brute-force answer."""
+    pos = np.repeat(np.arange(1000, dtype=np.float32)[:, None], 3, axis=1)
+    boxes = O.unit_boxes(pos)
+    b = api.Bvh.build(boxes)
+    s, d = b.nearest_to_batch([[5.0, 5.7, 5.3]])
+    assert int(s[0]) == 5
+    b.free()
+    shapes, tris = O.create_n_cubes(1000, want_tris=True)
+    bvh = api.Bvh.build(shapes)
+    bounds = O.make_aabbs([[-1000.0] * 3], [[1000.0] * 3])
+    ref_point, _ = O.next_points(1, bounds=bounds, seed=0)
+    rng = np.random.default_rng(3)
+    pts = np.concatenate([ref_point.reshape(1, 3), rng.uniform(-100000, 100000, (300, 3)).astype(np.float32),
+                          tris.reshape(-1, 3)[rng.integers(0, len(tris) * 3, 50)]])
+    off, cand = bvh.nearest_candidates(pts)
+    assert np.all(np.diff(off.astype(np.int64)) >= 1)
+    sizes = np.diff(off.astype(np.int64))
+    assert sizes.mean() < 200, sizes.mean()                                       # short lists: this is a pruned search, not a scan
+    for k, p in enumerate(pts):
+        d2 = O.shape_distances_squared(shapes, p, kind=O.DIST_TRIANGLE, tris=tris)          # PointDistance of every triangle
+        mine = cand[off[k]:off[k + 1]]
+        assert d2[mine].min() == d2.min(), k
+    bvh.free()
+
+
 def test_optimize_without_motion_is_a_no_op(api):
     shapes = scene("random5000")
     bvh = api.Bvh.build(shapes)
