@@ -94,6 +94,7 @@ template <> struct Abi<float> {
     static int fetch(tree* t, uint32_t* h, size_t cap) { return bvhgpu_traverse_fetch_f32x3(t, h, cap); }
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f32x3(t, a, n); }
     static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f32x3(t, a, n, g, r); }
+    static int candidates(tree* t, const float* p, size_t n, uint32_t* off, uint32_t* c, size_t cap, size_t* tot) { return bvhgpu_nearest_candidates_f32x3(t, p, n, off, c, cap, tot); }
 };
 template <> struct Abi<double> {
     using aabb = bvh_aabb3d; using ray = bvh_ray3d; using node = bvh_node3d; using flat = bvh_flat3d; using tree = bvhgpu_tree3d;
@@ -105,6 +106,7 @@ template <> struct Abi<double> {
     static int fetch(tree* t, uint32_t* h, size_t cap) { return bvhgpu_traverse_fetch_f64x3(t, h, cap); }
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f64x3(t, a, n); }
     static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f64x3(t, a, n, g, r); }
+    static int candidates(tree* t, const double* p, size_t n, uint32_t* off, uint32_t* c, size_t cap, size_t* tot) { return bvhgpu_nearest_candidates_f64x3(t, p, n, off, c, cap, tot); }
 };
 struct Ctx {
     bvhgpu_ctx* h = nullptr;
@@ -246,6 +248,25 @@ template <class T> class Bvh {
             for (int k = 0; k < 3; ++k) { boxes[i].min[k] = a.min[k]; boxes[i].max[k] = a.max[k]; }
         }
         check(A::refit(tree_, boxes.data(), boxes.size()));
+    }
+    // Bvh::nearest_to (src/bvh/bvh_impl.rs:221-238) for shapes with `T distance_squared(const T (&point)[3]) const`
+    // (PointDistance, src/point_query.rs:7-10): the device returns a short candidate list that contains the nearest shape, the
+    // shape's own distance decides.  Returns {nullptr, 0} for an empty tree.
+    template <class Shape> std::pair<const Shape*, T> nearest_to(const T (&point)[3], const std::vector<Shape>& shapes) const {
+        uint32_t off[2] = {0, 0};
+        std::vector<uint32_t> cand(1024);
+        size_t total = 0;
+        const int st = A::candidates(tree_, point, 1, off, cand.data(), cand.size(), &total);
+        if (st == BVHGPU_ERR_CAPACITY && total <= UINT32_MAX) { cand.resize(total); check(A::fetch(tree_, cand.data(), total)); }
+        else check(st);
+        const Shape* best = nullptr;
+        T best_d = T(0);
+        for (size_t i = 0; i < total; ++i) {
+            const Shape& s = shapes.at(cand[i]);
+            const T d = s.distance_squared(point);
+            if (!best || d < best_d) { best = &s; best_d = d; }
+        }
+        return {best, best ? std::sqrt(best_d) : T(0)};
     }
     // Bvh::update_shapes (src/bvh/optimization.rs:290-302): refit + in-place exact rebuild of the subtrees that grew by more
     // than `max_growth`; writes the new leaf node indices back (BHShape::set_bh_node_index).  Returns the rebuilt shape count.

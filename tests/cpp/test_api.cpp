@@ -1,6 +1,7 @@
 // tests/cpp/test_api.cpp -- the reference's fixed-scene tests (src/testbase.rs:66-267, src/bvh/bvh_impl.rs:557-690,
 // src/flat_bvh.rs:602-625, src/bvh/iter.rs:256-308, src/bvh/optimization.rs:405-487) written against the C++ host
 // mirror include/bvh_b200.hpp, i.e. through the C ABI on the GPU.  Exit code 0 = all passed.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <set>
@@ -30,6 +31,17 @@ struct UnitBox {
     }
     void set_bh_node_index(size_t i) { node_index = i; }
     size_t bh_node_index() const { return node_index; }
+    // testbase.rs:101-105: PointDistance = Aabb::min_distance_squared (aabb_impl.rs:618-629)
+    float distance_squared(const float (&p)[3]) const {
+        float d2 = 0.0f;
+        for (int k = 0; k < 3; ++k) {
+            const float hs = 0.5f, c = (pos[k] + -0.5f) + hs;
+            float q = std::fabs(p[k] - c) - hs;
+            q = q > 0.0f ? q : 0.0f;
+            d2 += q * q;
+        }
+        return d2;
+    }
 };
 
 // testbase.rs:109-116
@@ -154,6 +166,19 @@ int main() {
             }
         }
         traverse_and_verify(TRay3({10.0f, -1000.0f, 2.0f}, {0.0f, 1.0f, 0.0f}), s, bvh, {-10});     // the box moved to (10, 1, 2)
+    }
+    // nearest_to doc example (bvh_impl.rs / flat_bvh.rs:493-507): 1000 unit boxes on the diagonal, query (5, 5.7, 5.3) -> id 5
+    {
+        std::vector<UnitBox> s;
+        for (int i = 0; i < 1000; ++i) s.emplace_back(i, (float)i, (float)i, (float)i);
+        TBvh3 bvh = TBvh3::build(s);
+        const float q[3] = {5.0f, 5.7f, 5.3f};
+        auto near = bvh.nearest_to(q, s);
+        REQUIRE(near.first != nullptr && near.first->id == 5);
+        REQUIRE(std::fabs(near.second - 0.2f) < 1e-6f);
+        std::vector<UnitBox> none;
+        TBvh3 e = TBvh3::build(none);
+        REQUIRE(e.nearest_to(q, none).first == nullptr);
     }
     // ray / aabb known answers (ray_impl.rs:244-299)
     {
