@@ -387,6 +387,29 @@ def test_nearest_to_doc_example_and_some_bh(api):
     bvh.free()
 
 
+def test_optimize_large_scene_without_gangs(api):
+    """1.2 M shapes: above the gang threshold, so rebuild roots larger than 512 shapes run as queue-mode BIN / SCATTER tile tasks."""
+    from bvh_b200 import scenes as S
+    shapes = S.create_n_cubes_aabbs(100000).copy()
+    bvh = api.Bvh.build(shapes)
+    rng = np.random.default_rng(21)
+    mv = rng.choice(len(shapes), len(shapes) // 20, replace=False)
+    dl = rng.uniform(-3000.0, 3000.0, (len(mv), 3)).astype(np.float32)
+    shapes["min"][mv] += dl
+    shapes["max"][mv] += dl
+    rebuilt = bvh.optimize(shapes, 1.5)
+    nodes = bvh.nodes
+    assert 512 < rebuilt <= len(shapes)
+    assert _preorder_layout_ok(nodes)
+    assert O.is_consistent(nodes, shapes) and O.is_tight(nodes)
+    assert np.array_equal(nodes["shape"][bvh.node_index], np.arange(len(shapes)))
+    rays = rays_for(shapes, 20000, seed=2)
+    r = O.traverse(nodes, shapes, rays, O.MODE_RECURSIVE, threads=O.hardware_threads())
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    bvh.free()
+
+
 def test_optimize_without_motion_is_a_no_op(api):
     shapes = scene("random5000")
     bvh = api.Bvh.build(shapes)
@@ -542,6 +565,17 @@ def test_config5_ten_million_f64(api):
     rebuilt = O.build(shapes, "f64", threads=O.hardware_threads())
     c_refit, c_rebuild = bvh.sah_cost()[0], O.sah_cost(rebuilt.nodes, "f64")[0]
     assert c_refit <= 1.10 * c_rebuild, (c_refit, c_rebuild)
+    # a second motion, this time fixed by bvhgpu_optimize (refit + in-place rebuild; queue-mode tile tasks and the thread-per-range
+    # kernel at this size): same acceptance criteria, cost no worse than the refit-only tree
+    moved2 = rng.choice(len(shapes), len(shapes) // 100, replace=False)
+    shapes["min"][moved2] += 25.0
+    shapes["max"][moved2] += 25.0
+    n_rebuilt = bvh.optimize(shapes, 1.5)
+    nodes = bvh.nodes
+    assert 0 < n_rebuilt <= len(shapes)
+    assert _preorder_layout_ok(nodes)
+    assert O.is_consistent(nodes, shapes, "f64") and O.is_tight(nodes, "f64")
+    assert np.array_equal(nodes["shape"][bvh.node_index], np.arange(len(shapes)))
 
 
 # ---- BVHGPU_BUILD_LBVH: different topology, same layout rule, same hit sets ------------------------------------------
