@@ -1364,7 +1364,6 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
         ctx->launches++;
     } else {
         BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
-        const size_t dsm = 0;
         init_root_kernel<T><<<1, 32, 0, st>>>(P);
         ctx->launches++;
         if (ctx->profile) cudaEventRecord(ctx->ev_build[0], st);
@@ -1372,9 +1371,9 @@ int build_exact_sah(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, u
             // gangs spin on each other: the grid must be co-resident as a whole, which is what a cooperative launch
             // guarantees (two concurrent builds are then serialised by the scheduler instead of starving each other)
             void* kargs[] = {&P};
-            BVH_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)build_kernel<T>, dim3(grid), dim3(WARPS_PER_CTA * 32), kargs, dsm, st));
+            BVH_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)build_kernel<T>, dim3(grid), dim3(WARPS_PER_CTA * 32), kargs, 0, st));
         } else {
-            build_kernel<T><<<grid, WARPS_PER_CTA * 32, dsm, st>>>(P);
+            build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
         }
         ctx->launches++;
         if (P.small_max) {
@@ -1439,13 +1438,12 @@ int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
     const uint32_t n = tree->n;
     treelet_start_kernel<T><<<1, 32, 0, st>>>(P->ctl);
     int occ = 1;
-    const size_t dsm = 0;
-    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, dsm));
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
     if (occ < 1) occ = 1;
     uint64_t want = ((uint64_t)n / 16 + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (want < 1) want = 1;
     const int grid = (int)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * occ);
-    build_kernel<T><<<grid, WARPS_PER_CTA * 32, dsm, st>>>(*P);
+    build_kernel<T><<<grid, WARPS_PER_CTA * 32, 0, st>>>(*P);
     ctx->launches += 2;
     if (P->small_max) {
         const unsigned sgrid = (unsigned)(((size_t)n / 2 + 1 + 127) / 128);
