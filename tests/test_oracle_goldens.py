@@ -506,3 +506,51 @@ def test_nearest_to_empty_and_single():
     b = O.build(one)
     s, d = O.nearest_to(b.nodes, one, [[0.0, 0.0, 0.0]])
     assert int(s[0]) == 0 and d[0] == 2.5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Property tests (the reference uses proptest for the same purpose, src/bvh/optimization.rs / src/testbase.rs fuzz helpers)
+# ---------------------------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+from tests.scenes import rays_for
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 400), st.integers(0, 2**31 - 1), st.floats(0.0, 1.0), st.sampled_from([0.5, 50.0, 5000.0]))
+def test_update_shapes_property(n, seed, frac, reach):
+    """Any scene, any subset moved anywhere: update_shapes leaves a consistent, tight tree over all shapes with 2n-1 nodes, whose
+    traversal agrees with a brute-force scan."""
+    rng = np.random.default_rng(seed)
+    mn = rng.uniform(-100, 100, (n, 3))
+    shapes = O.make_aabbs(mn, mn + rng.uniform(0, 4, (n, 3)))
+    b = O.build(shapes)
+    m = int(round(n * frac))
+    idx = rng.permutation(n)[:m].astype(np.uint32)
+    moved = shapes.copy()
+    d = rng.uniform(-reach, reach, (m, 3)).astype(np.float32)
+    moved["min"][idx] += d
+    moved["max"][idx] += d
+    nodes, node_index = O.update_shapes(b.nodes, b.node_index, moved, idx)
+    assert len(nodes) == 2 * n - 1
+    assert O.is_consistent(nodes, moved) and O.is_tight(nodes)
+    assert np.array_equal(nodes["shape"][node_index], np.arange(n)) and np.all(nodes["child_l"][node_index] == 0xFFFFFFFF)
+    rays = rays_for(moved, 8, seed=seed % 1000)
+    r = O.traverse(nodes, moved, rays, O.MODE_RECURSIVE)
+    for k, got in enumerate(O.per_ray_lists(r.offsets, r.hits)):
+        assert sorted(got.tolist()) == _brute_force(moved, rays[k])
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 600), st.integers(0, 2**31 - 1), st.booleans())
+def test_nearest_to_property(n, seed, flat):
+    """nearest_to returns a shape at the minimum AABB distance (brute force), for the Bvh and the FlatBvh walk."""
+    rng = np.random.default_rng(seed)
+    mn = rng.uniform(-50, 50, (n, 3))
+    shapes = O.make_aabbs(mn, mn + rng.uniform(0, 6, (n, 3)))
+    b = O.build(shapes)
+    tree = O.flatten(b.nodes) if flat else b.nodes
+    pts = rng.uniform(-80, 80, (12, 3)).astype(np.float32)
+    s, d = O.nearest_to(tree, shapes, pts, flat=flat)
+    for k in range(len(pts)):
+        d2 = O.shape_distances_squared(shapes, pts[k])
+        assert d2[int(s[k])] == d2.min() and d[k] == np.sqrt(d2.min())
