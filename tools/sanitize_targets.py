@@ -21,12 +21,17 @@ for prec, ncubes in (("f32", 60), ("f32", 700), ("f64", 300)):
     rays = api.Ray.new(o, d, prec=prec)
     for mode in (capi.TRAVERSE_BVH, capi.TRAVERSE_FLAT):
         off, hits = b.traverse_batch(rays, mode=mode)
+    pts = rng.uniform(-120000, 120000, (512, 3))
+    for mode in (capi.TRAVERSE_BVH, capi.TRAVERSE_FLAT):
+        ns, nd = b.nearest_to_batch(pts, mode=mode)
+    coff, cand = b.nearest_candidates(pts)
+    qoff, qh = b.query_batch(capi.QUERY_BALL, np.concatenate([pts[:64], np.full((64, 1), 5000.0)], axis=1))
     m = a.copy()
     mv = rng.choice(len(a), len(a) // 10, replace=False)
     dl = rng.uniform(-10, 10, (len(mv), 3)).astype(a["min"].dtype)
     m["min"][mv] += dl; m["max"][mv] += dl
     b.refit(m)
     m["min"][mv] += dl; m["max"][mv] += dl
-    print(prec, ncubes, "optimize rebuilt", b.optimize(m, 1.5), "hits", len(hits))
+    print(prec, ncubes, "optimize rebuilt", b.optimize(m, 1.5), "hits", len(hits), "candidates", len(cand))
     b.free()
 print("sanitize targets done")
