@@ -39,6 +39,7 @@ class Context:
         self._h = C.c_void_p()
         capi.check(capi.lib().bvhgpu_create(device, C.byref(self._h)))
         self.device = device
+        self._host = {}
 
     @classmethod
     def default(cls, device: int = 0) -> "Context":
@@ -66,6 +67,18 @@ class Context:
         out = C.c_double(0.0)
         capi.check(capi.lib().bvhgpu_get_metric(self._h, name.encode(), C.byref(out)))
         return out.value
+
+    def host_alloc(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """Pinned host memory on the device's NUMA node (bvhgpu_host_alloc) as a numpy array; release with host_free(arr)."""
+        p = C.c_void_p()
+        capi.check(capi.lib().bvhgpu_host_alloc(self._h, nbytes, C.byref(p)))
+        arr = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(p.value)).view(dtype)
+        self._host.setdefault(arr.ctypes.data, p)
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        p = self._host.pop(arr.ctypes.data)
+        capi.check(capi.lib().bvhgpu_host_free(self._h, p))
 
     def close(self):
         if self._h:
@@ -219,8 +232,10 @@ class Bvh:
         return ln.value
 
     # ---- traversal ---------------------------------------------------------------------------------
-    def traverse_batch(self, rays: np.ndarray, mode: int = capi.TRAVERSE_BVH, cap: int | None = None):
-        """CSR (offsets u32[nrays+1], hits u32[total]); hits of a ray are in the reference's DFS order."""
+    def traverse_batch(self, rays: np.ndarray, mode: int = capi.TRAVERSE_BVH, cap: int | None = None, compact: bool = False):
+        """CSR (offsets u32[nrays+1], hits u32[total]); hits of a ray are in the reference's DFS order.
+        compact=True ships only origin + direction (BVHGPU_RAYS_OD, 6 scalars per ray); the device recomputes inv_direction with
+        the division Ray::new uses, so the result is bit-identical."""
         rays = np.ascontiguousarray(rays, dtype=self._d["ray"])
         nrays = len(rays)
         offsets = np.zeros(nrays + 1, dtype=np.uint32)
@@ -228,6 +243,10 @@ class Bvh:
         hits = np.zeros(cap, dtype=np.uint32)
         total = C.c_size_t(0)
         fn = getattr(capi.lib(), f"bvhgpu_traverse_{self._d['suffix']}")
+        if compact:
+            od = np.empty((nrays, 6), dtype=self._d["scalar"])
+            od[:, :3], od[:, 3:] = rays["origin"], rays["direction"]
+            rays, fn = od, getattr(capi.lib(), f"bvhgpu_traverse_od_{self._d['suffix']}")
         st = fn(self._h, mode, _ptr(rays), nrays, _ptr(offsets), _ptr(hits), cap, C.byref(total))
         if st == capi.ERR_CAPACITY and total.value <= U32_MAX:
             hits = np.zeros(total.value, dtype=np.uint32)

@@ -16,14 +16,22 @@ TRAVERSE_BVH, TRAVERSE_FLAT = 0, 1
 QUERY_AABB, QUERY_POINT, QUERY_BALL = 1, 2, 3
 
 
-MAX_PEERS, MAILBOX_BYTES, IPC_HANDLE_BYTES = 8, 1024, 64
+RAYS_FULL, RAYS_OD = 0, 1
+MAX_PEERS, MAILBOX_BYTES, IPC_HANDLE_BYTES = 8, 65536, 64
+MB_TRACE_WORD, MB_TRACE_LEN = 128, 1024          # mailbox trace ring (u64 words), see traverse.cu
+
+
+def shard_stage_bytes(nrays_global: int) -> int:
+    """BVHGPU_SHARD_STAGE_BYTES"""
+    return 4 * nrays_global + 16 * MAX_PEERS + 32
 
 
 class Shard(C.Structure):
     """bvhgpu_shard (include/bvh_b200.h)."""
     _fields_ = [("rank", C.c_int), ("world", C.c_int),
-                ("peer_offsets", C.c_void_p * MAX_PEERS), ("peer_hits", C.c_void_p * MAX_PEERS), ("peer_mailbox", C.c_void_p * MAX_PEERS),
-                ("seq", C.c_uint64), ("rays_before", C.c_size_t), ("nrays_global", C.c_size_t), ("cap", C.c_size_t)]
+                ("peer_counts", C.c_void_p * MAX_PEERS), ("peer_hits", C.c_void_p * MAX_PEERS), ("peer_mailbox", C.c_void_p * MAX_PEERS),
+                ("offsets", C.c_void_p), ("seq", C.c_uint64), ("shard_rays", C.c_size_t * MAX_PEERS), ("cap", C.c_size_t),
+                ("ray_layout", C.c_int)]
 
 
 class BvhGpuError(RuntimeError):
@@ -71,6 +79,9 @@ def lib() -> C.CDLL:
     L.bvhgpu_peer_close.argtypes = [vp, vp]
     L.bvhgpu_peer_free.argtypes = [vp, vp]
     L.bvhgpu_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.bvhgpu_memcpy_h2d_async.argtypes = [vp, vp, vp, sz]
+    L.bvhgpu_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.bvhgpu_host_free.argtypes = [vp, vp]
     for s in ("f32x3", "f64x3"):
         getattr(L, f"bvhgpu_build_{s}").argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
         getattr(L, f"bvhgpu_build_dev_{s}").argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
@@ -84,6 +95,10 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_flatten_{s}").argtypes = [vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_fetch_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_traverse_od_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
+        getattr(L, f"bvhgpu_traverse_od_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
+        getattr(L, f"bvhgpu_refit_dev_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_optimize_dev_{s}").argtypes = [vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
         getattr(L, f"bvhgpu_traverse_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_stats_{s}").argtypes = [vp, u64p]
         getattr(L, f"bvhgpu_traverse_ordered_{s}").argtypes = [vp, vp, sz, i32, vp, vp, vp, sz, szp]

@@ -358,6 +358,13 @@ __device__ __forceinline__ int finish_node(const BuildParams<T>& P, WarpScratch<
     const uint32_t buf = t.parent_buf >> 31, parent = t.parent_buf & 0x7FFFFFFFu;
     const uint32_t nbuf = moved ? (buf ^ 1u) : buf;
     const uint32_t cl = t.node + 1, cr = cl + 2 * nl - 1;
+    if (nl == 0u || nl >= t.count) {
+        // An empty side cannot come out of a split of NaN-free shapes (buckets 0 and 5 are never empty: tight centroid bounds).
+        // It would recurse on the same range forever; raise a device error instead (the workers see ctl->error and leave).
+        if (lane_id() == 0) atomicCAS(&P.ctl->error, 0u, (uint32_t)BVHGPU_ERR_INTERNAL);
+        leaves = 0;
+        return 0;
+    }
     if (lane_id() == 0) {
         typename Tr::Node nd;
         nd.parent = parent; nd.child_l = cl; nd.child_r = cr; nd.shape = t.count;
@@ -1429,14 +1436,19 @@ int treelet_begin(bvhgpu_ctx* ctx, Tree<T>* tree, uint32_t* sorted_ids, TreeletS
     S->params = P; S->q = P->q; S->qseq = P->qseq; S->qmask = P->qmask; S->ctl = P->ctl;
     return BVHGPU_OK;
 }
-template <class T> __global__ void treelet_start_kernel(BuildCtl* ctl) { if (threadIdx.x == 0) ctl->t_start = global_timer_ns(); }
+template <class T> __global__ void treelet_start_kernel(BuildCtl* ctl, const BuildStatus* status) {
+    if (threadIdx.x == 0) {
+        ctl->t_start = global_timer_ns();
+        if (status->nan_found) ctl->error = (uint32_t)BVHGPU_ERR_NAN;     // NaN shapes: build nothing (the reference panics), the workers leave at once
+    }
+}
 
 template <class T>
 int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
     cudaStream_t st = ctx->stream;
     BuildParams<T>* P = static_cast<BuildParams<T>*>(S->params);
     const uint32_t n = tree->n;
-    treelet_start_kernel<T><<<1, 32, 0, st>>>(P->ctl);
+    treelet_start_kernel<T><<<1, 32, 0, st>>>(P->ctl, P->status);
     int occ = 1;
     BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, build_kernel<T>, WARPS_PER_CTA * 32, 0));
     if (occ < 1) occ = 1;
@@ -1470,6 +1482,7 @@ __global__ void __launch_bounds__(256) rebuild_push_kernel(BuildParams<T> P, con
                                                            const T* __restrict__ cb) {
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t nr = *n_roots;
+    if (P.status->nan_found) return;                                   // (cannot happen through the C ABI: new AABBs are checked before the tree is touched)
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nr; i += warps) {
         const uint32_t r = roots[i];
         const typename Traits<T>::Node& nd = P.nodes[r];
@@ -1485,8 +1498,11 @@ __global__ void __launch_bounds__(256) rebuild_push_kernel(BuildParams<T> P, con
         if (t.count > (uint32_t)TILE) { if (!try_create_gang(P, t)) create_big(P, t); } else push_seg(P, t);
     }
 }
-template <class T> __global__ void rebuild_start_kernel(BuildCtl* ctl, uint32_t n) {
-    if (threadIdx.x == 0) { ctl->t_start = global_timer_ns(); ctl->leaves_done = n; }
+template <class T> __global__ void rebuild_start_kernel(BuildCtl* ctl, uint32_t n, const BuildStatus* status) {
+    if (threadIdx.x == 0) {
+        ctl->t_start = global_timer_ns(); ctl->leaves_done = n;
+        if (status->nan_found) ctl->error = (uint32_t)BVHGPU_ERR_NAN;
+    }
 }
 
 template <class T>
@@ -1524,7 +1540,7 @@ int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, co
     BVH_TRY(dalloc_t(ctx, &P.small, P.small_max ? (size_t)n / 2 + 1 : 1));
     BVH_CUDA_TRY(cudaMemsetAsync(P.qseq, 0, sizeof(uint32_t) * qcap, st));
     BVH_CUDA_TRY(cudaMemsetAsync(P.ctl, 0, sizeof(BuildCtl), st));
-    rebuild_start_kernel<T><<<1, 32, 0, st>>>(P.ctl, n);
+    rebuild_start_kernel<T><<<1, 32, 0, st>>>(P.ctl, n, P.status);
     const int pblocks = (int)std::min<uint64_t>(((uint64_t)n + 63) / 64, (uint64_t)ctx->sm_count * 4);
     rebuild_push_kernel<T><<<pblocks, 256, 0, st>>>(P, d_roots, d_n_roots, cb);
     if (P.gang_budget) {

@@ -5,6 +5,8 @@
 #include <vector>
 #include <new>
 #include <algorithm>
+#include <cctype>
+#include <sched.h>
 
 namespace bvhb200 {
 
@@ -30,17 +32,24 @@ void dfree(bvhgpu_ctx* ctx, void* p) {
 }
 
 // Resolve the deferred device status of a build (synchronises the stream once).
+// A failure is STICKY: the node arrays of a tree whose build / refit / optimize failed are uninitialised or half rewritten,
+// so every later entry point on that tree reports the same status again (the reference panicked at this point and the
+// Bvh never existed); only bvhgpu_tree_free_* is meaningful afterwards.
 template <class T> int resolve_status(Tree<T>* tree) {
+    if (tree->failed_status != BVHGPU_OK) { set_error("%s", tree->failed_message.c_str()); return tree->failed_status; }
     if (!tree->status_pending) return BVHGPU_OK;
     bvhgpu_ctx* ctx = tree->ctx;
     BuildStatus h;
     BVH_CUDA_TRY(cudaMemcpyAsync(&h, tree->d_status, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     tree->status_pending = false;
-    if (h.nan_found) { set_error("build: NaN coordinate in an input AABB (the reference panics here, src/bvh/bvh_node.rs:214-217)"); return BVHGPU_ERR_NAN; }
-    if (h.error == BVHGPU_ERR_TIMEOUT) { set_error("build: device watchdog fired (tickets=%u leaves=%u/%u)", h.tickets, h.leaves_done, tree->n); return BVHGPU_ERR_TIMEOUT; }
-    if (h.error) { set_error("build: device reported status %u (tickets=%u leaves=%u/%u)", h.error, h.tickets, h.leaves_done, tree->n); return (int)h.error; }
-    return BVHGPU_OK;
+    char msg[512];
+    int rc = BVHGPU_OK;
+    if (h.nan_found) { snprintf(msg, sizeof msg, "build: NaN coordinate in an input AABB (the reference panics here, src/bvh/bvh_node.rs:214-217); the tree is unusable"); rc = BVHGPU_ERR_NAN; }
+    else if (h.error == BVHGPU_ERR_TIMEOUT) { snprintf(msg, sizeof msg, "build: device watchdog fired (tickets=%u leaves=%u/%u); the tree is unusable", h.tickets, h.leaves_done, tree->n); rc = BVHGPU_ERR_TIMEOUT; }
+    else if (h.error) { snprintf(msg, sizeof msg, "build: device reported status %u (tickets=%u leaves=%u/%u); the tree is unusable", h.error, h.tickets, h.leaves_done, tree->n); rc = (int)h.error; }
+    if (rc != BVHGPU_OK) { tree->failed_status = rc; tree->failed_message = msg; set_error("%s", msg); }
+    return rc;
 }
 
 template int resolve_status<float>(Tree<float>*);
@@ -150,6 +159,8 @@ static int from_nodes_impl(bvhgpu_ctx* ctx, const typename Traits<T>::Node* node
         if (e != cudaSuccess) { set_error("tree_from_nodes: %s", cudaGetErrorString(e)); return fail(BVHGPU_ERR_CUDA); }
         dfree(ctx, staged);
         staged = nullptr;
+        tree->status_pending = true;                              // the NaN flag of convert_aabbs
+        if ((rc = resolve_status(tree)) != BVHGPU_OK) return fail(rc);
     }
     *out = tree;
     return BVHGPU_OK;
@@ -200,7 +211,7 @@ template <class T> static int ensure_result_buffers(Tree<T>* tree, size_t nrays,
 }
 
 template <class T>
-static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>::Ray* rays, size_t nrays,
+static int traverse_host_impl(Tree<T>* tree, int mode, const void* rays, uint32_t fmt, size_t nrays,
                               uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total) {
     if (!tree || (nrays && !rays) || !offsets) { set_error("traverse: null argument"); return BVHGPU_ERR_INVALID; }
     bvhgpu_ctx* ctx = tree->ctx;
@@ -209,7 +220,7 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     if (nrays == 0 || tree->n == 0) {                            // nothing to pipeline
         size_t tot0 = 0;
         BVH_TRY(ensure_result_buffers(tree, nrays, 1024));
-        BVH_TRY(traverse_device<T>(tree, mode, nullptr, nullptr, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot0));
+        BVH_TRY(traverse_device<T>(tree, mode, nullptr, fmt, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot0));
         BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
         BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         if (total) *total = 0;
@@ -221,7 +232,7 @@ static int traverse_host_impl(Tree<T>* tree, int mode, const typename Traits<T>:
     for (int attempt = 0; attempt < 2; ++attempt) {
         rc = ensure_result_buffers(tree, nrays, want);
         if (rc != BVHGPU_OK) break;
-        rc = traverse_host_pipelined<T>(tree, mode, rays, nrays, offsets, hits, cap, &tot);
+        rc = traverse_host_pipelined<T>(tree, mode, rays, fmt, nrays, offsets, hits, cap, &tot);
         if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && tot > tree->hits_cap && attempt == 0) { want = tot; continue; }   // grow once and redo
         break;
     }
@@ -362,27 +373,52 @@ template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t c
     return BVHGPU_OK;
 }
 
+// New shape AABBs for refit / optimize: converted into a TEMPORARY device array and checked for NaN before the tree is touched,
+// so a rejected update (BVHGPU_ERR_NAN) leaves the tree exactly as it was.  dev_input: `aabbs` is a device pointer.
 template <class T>
-static int refit_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n) {
+static int stage_new_aabbs(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n, bool dev_input, const char* who) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    Scratch scratch(ctx);
+    typename Traits<T>::Aabb* staged = nullptr;
+    const typename Traits<T>::Aabb* d_in = aabbs;
+    if (!dev_input) {
+        BVH_TRY(scratch.get(&staged, n));
+        BVH_CUDA_TRY(cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream));
+        d_in = staged;
+    }
+    typename Traits<T>::DAabb* fresh = nullptr;
+    uint32_t* flag = nullptr;
+    BVH_TRY(dalloc_t(ctx, &fresh, n));
+    int rc = scratch.get(&flag, 1);
+    if (rc == BVHGPU_OK && cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream) != cudaSuccess) rc = BVHGPU_ERR_CUDA;
+    if (rc == BVHGPU_OK) rc = convert_aabbs<T>(ctx, d_in, (uint32_t)n, fresh, flag);
+    uint32_t* h = ctx->h_pinned + 200;
+    if (rc == BVHGPU_OK && (cudaMemcpyAsync(h, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                            cudaStreamSynchronize(ctx->stream) != cudaSuccess)) { set_error("%s: CUDA error while staging the AABBs", who); rc = BVHGPU_ERR_CUDA; }
+    if (rc == BVHGPU_OK && *h) { set_error("%s: NaN coordinate in an input AABB; the tree was left unchanged", who); rc = BVHGPU_ERR_NAN; }
+    if (rc != BVHGPU_OK) { dfree(ctx, fresh); return rc; }
+    dfree(ctx, tree->d_aabb);
+    tree->d_aabb = fresh;
+    return BVHGPU_OK;
+}
+
+template <class T>
+static int refit_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n, bool dev_input) {
     if (!tree || (n && !aabbs)) { set_error("refit: null argument"); return BVHGPU_ERR_INVALID; }
     if (n != tree->n) { set_error("refit: %zu AABBs for a tree over %u shapes", n, tree->n); return BVHGPU_ERR_INVALID; }
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
     if (n == 0) return BVHGPU_OK;
-    typename Traits<T>::Aabb* staged = nullptr;
-    BVH_TRY(dalloc_t(ctx, &staged, n));
-    BVH_CUDA_TRY(cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream));
+    BVH_TRY(stage_new_aabbs<T>(tree, aabbs, n, dev_input, "refit"));
     BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
-    BVH_TRY(convert_aabbs<T>(ctx, staged, (uint32_t)n, tree->d_aabb, &tree->d_status->nan_found));
-    dfree(ctx, staged);
     BVH_TRY(refit(tree));
     tree->status_pending = true;
-    return resolve_status(tree);
+    return dev_input ? (int)BVHGPU_OK : resolve_status(tree);
 }
 
 template <class T>
-static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n, double max_growth, size_t* rebuilt) {
+static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, size_t n, double max_growth, size_t* rebuilt, bool dev_input) {
     if (!tree || (n && !aabbs)) { set_error("optimize: null argument"); return BVHGPU_ERR_INVALID; }
     if (n != tree->n) { set_error("optimize: %zu AABBs for a tree over %u shapes", n, tree->n); return BVHGPU_ERR_INVALID; }
     if (!(max_growth >= 1.0)) { set_error("optimize: max_growth = %g, must be >= 1", max_growth); return BVHGPU_ERR_INVALID; }
@@ -391,14 +427,11 @@ static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, s
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
     if (n == 0) return BVHGPU_OK;
-    typename Traits<T>::Aabb* staged = nullptr;
-    BVH_TRY(dalloc_t(ctx, &staged, n));
-    BVH_CUDA_TRY(cudaMemcpyAsync(staged, aabbs, n * sizeof(*aabbs), cudaMemcpyHostToDevice, ctx->stream));
+    BVH_TRY(stage_new_aabbs<T>(tree, aabbs, n, dev_input, "optimize"));
     BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
-    BVH_TRY(convert_aabbs<T>(ctx, staged, (uint32_t)n, tree->d_aabb, &tree->d_status->nan_found));
-    dfree(ctx, staged);
     BVH_TRY(optimize(tree, max_growth));
     tree->status_pending = true;
+    if (dev_input && !rebuilt) return BVHGPU_OK;                        // asynchronous: errors surface at the next call on the tree
     BuildStatus h;
     BVH_CUDA_TRY(cudaMemcpyAsync(&h, tree->d_status, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     BVH_TRY(resolve_status(tree));                                      // synchronises
@@ -444,6 +477,16 @@ BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    BVH_CUDA_TRY(cudaMalloc((void**)&ctx->d_async_err, 64));
+    BVH_CUDA_TRY(cudaMemset(ctx->d_async_err, 0, 64));
+    {   // NUMA node of the device (bvhgpu_host_alloc): /sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node
+        char bus[32] = {0}, path[128];
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+            for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+            snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+            if (FILE* f = fopen(path, "r")) { int nn = -1; if (fscanf(f, "%d", &nn) == 1) ctx->numa_node = nn; fclose(f); }
+        }
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long thr = ~0ull;                       // keep freed blocks cached: alloc/free pairs stay cheap
@@ -464,6 +507,8 @@ BVH_EXPORT void bvhgpu_destroy(bvhgpu_ctx* ctx) {
     if (ctx->ev_total) cudaEventDestroy(ctx->ev_total);
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_async_err) cudaFree(ctx->d_async_err);
+    for (int i = 0; i < 5; ++i) if (ctx->ev_e2e[i]) cudaEventDestroy(ctx->ev_e2e[i]);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_walk[i]) cudaEventDestroy(ctx->ev_walk[i]); if (ctx->ev_build[i]) cudaEventDestroy(ctx->ev_build[i]); }
     delete ctx;
 }
@@ -480,7 +525,15 @@ BVH_EXPORT int bvhgpu_reset_stream(bvhgpu_ctx* ctx) {
 BVH_EXPORT int bvhgpu_synchronize(bvhgpu_ctx* ctx) {
     if (!ctx) { set_error("synchronize: null ctx"); return BVHGPU_ERR_INVALID; }
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint32_t* h = ctx->h_pinned + 204;
+    BVH_CUDA_TRY(cudaMemcpyAsync(h, ctx->d_async_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (*h) {                                                     // raised by an asynchronous multi-GPU step; reported once
+        const int rc = (int)*h;
+        cudaMemsetAsync(ctx->d_async_err, 0, sizeof(uint32_t), ctx->stream);
+        set_error("sharded traversal: a peer did not answer within the exchange time-out (status %d); the step's result is invalid", rc);
+        return rc;
+    }
     return BVHGPU_OK;
 }
 BVH_EXPORT uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -492,6 +545,8 @@ BVH_EXPORT int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t valu
     if (!strcmp(name, "build_gang")) { ctx->build_gang = value; return BVHGPU_OK; }
     if (!strcmp(name, "build_subtree")) { ctx->build_subtree = value; return BVHGPU_OK; }
     if (!strcmp(name, "traverse_persistent")) { ctx->traverse_persistent = value; return BVHGPU_OK; }
+    if (!strcmp(name, "traverse_stream")) { ctx->traverse_stream = value; return BVHGPU_OK; }
+    if (!strcmp(name, "traverse_top")) { ctx->traverse_top = value; return BVHGPU_OK; }
     set_error("set_option: unknown option '%s'", name);
     return BVHGPU_ERR_INVALID;
 }
@@ -558,6 +613,56 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
     return BVHGPU_OK;
 }
 
+BVH_EXPORT int bvhgpu_memcpy_h2d_async(bvhgpu_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
+    if (!ctx || (bytes && (!host_src || !dev_dst))) { set_error("memcpy_h2d_async: null argument"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (bytes) BVH_CUDA_TRY(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return BVHGPU_OK;
+}
+
+// Pinned host memory on the device's NUMA node: the calling thread is moved onto that node's CPUs while the pages are
+// allocated and first touched (first-touch placement; needs no privilege, unlike mbind), then moved back.
+BVH_EXPORT int bvhgpu_host_alloc(bvhgpu_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) { set_error("host_alloc: null argument"); return BVHGPU_ERR_INVALID; }
+    *out = nullptr;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    cpu_set_t old_set, node_set;
+    bool moved = false;
+    if (ctx->numa_node >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+        char path[128];
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", ctx->numa_node);
+        CPU_ZERO(&node_set);
+        int ncpu = 0;
+        if (FILE* f = fopen(path, "r")) {                         // "0-31,64-95"
+            int a, b;
+            char sep;
+            while (fscanf(f, "%d", &a) == 1) {
+                b = a;
+                int c = fgetc(f);
+                if (c == '-') { if (fscanf(f, "%d", &b) != 1) break; c = fgetc(f); }
+                for (int k = a; k <= b && k < CPU_SETSIZE; ++k) if (CPU_ISSET(k, &old_set)) { CPU_SET(k, &node_set); ++ncpu; }
+                if (c != ',') break;
+                (void)sep;
+            }
+            fclose(f);
+        }
+        if (ncpu > 0 && sched_setaffinity(0, sizeof node_set, &node_set) == 0) moved = true;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable);
+    if (e == cudaSuccess) memset(p, 0, bytes ? bytes : 16);
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (e != cudaSuccess) { set_error("host_alloc: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return BVHGPU_ERR_CUDA; }
+    *out = p;
+    return BVHGPU_OK;
+}
+BVH_EXPORT int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p) {
+    if (!ctx) { set_error("host_free: null ctx"); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (p) BVH_CUDA_TRY(cudaFreeHost(p));
+    return BVHGPU_OK;
+}
+
 #define DEFINE_API(T, SUF, TREE, AABB, RAY, NODE, FLAT)                                                                   \
     BVH_EXPORT int bvhgpu_build_##SUF(bvhgpu_ctx* ctx, const AABB* aabbs, size_t n, int mode, TREE** out) {              \
         return build_impl<T, TREE>(ctx, aabbs, n, mode, true, out);                                                       \
@@ -585,14 +690,24 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_##SUF(TREE* tree, int mode, const RAY* rays, size_t nrays, uint32_t* offsets,          \
                                          uint32_t* hits, size_t cap, size_t* total) {                                     \
-        return traverse_host_impl<T>(tree, mode, rays, nrays, offsets, hits, cap, total);                                 \
+        return traverse_host_impl<T>(tree, mode, rays, BVHGPU_RAYS_FULL, nrays, offsets, hits, cap, total);               \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_od_##SUF(TREE* tree, int mode, const T* origin_dir, size_t nrays, uint32_t* offsets,   \
+                                            uint32_t* hits, size_t cap, size_t* total) {                                  \
+        return traverse_host_impl<T>(tree, mode, origin_dir, BVHGPU_RAYS_OD, nrays, offsets, hits, cap, total);           \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_fetch_##SUF(TREE* tree, uint32_t* hits, size_t cap) { return fetch_impl<T>(tree, hits, cap); } \
     BVH_EXPORT int bvhgpu_traverse_dev_##SUF(TREE* tree, int mode, const void* dev_rays, size_t nrays, void* dev_offsets, \
                                              void* dev_hits, size_t cap, size_t* total) {                                 \
         if (!tree || !dev_offsets || (nrays && !dev_rays)) { set_error("traverse_dev: null argument"); return BVHGPU_ERR_INVALID; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
-        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+        return traverse_device<T>(tree, mode, dev_rays, BVHGPU_RAYS_FULL, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_traverse_od_dev_##SUF(TREE* tree, int mode, const void* dev_origin_dir, size_t nrays, void* dev_offsets, \
+                                                void* dev_hits, size_t cap, size_t* total) {                              \
+        if (!tree || !dev_offsets || (nrays && !dev_origin_dir)) { set_error("traverse_od_dev: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return traverse_device<T>(tree, mode, dev_origin_dir, BVHGPU_RAYS_OD, nrays, (uint32_t*)dev_offsets, (uint32_t*)dev_hits, cap, total); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_sharded_dev_##SUF(TREE* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard) { \
         if (!tree || !shard || (nrays && !dev_rays)) { set_error("traverse_sharded: null argument"); return BVHGPU_ERR_INVALID; } \
@@ -600,7 +715,8 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
             set_error("traverse_sharded: bad rank/world %d/%d", shard->rank, shard->world); return BVHGPU_ERR_INVALID; }     \
         if (nrays == 0 || tree->n == 0) { set_error("traverse_sharded: every rank needs a non-empty shard and tree"); return BVHGPU_ERR_UNSUPPORTED; } \
         BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
-        return traverse_device<T>(tree, mode, (const RAY*)dev_rays, nullptr, nrays, nullptr, nullptr, shard->cap, nullptr, shard); \
+        if (!shard->offsets) { set_error("traverse_sharded: shard->offsets is null"); return BVHGPU_ERR_INVALID; }     \
+        return traverse_device<T>(tree, mode, dev_rays, (uint32_t)shard->ray_layout, nrays, nullptr, nullptr, shard->cap, nullptr, shard); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_query_##SUF(TREE* tree, int mode, int kind, const T* queries, size_t n, uint32_t* offsets, uint32_t* hits, \
                                       size_t cap, size_t* total) {                                                       \
@@ -639,9 +755,13 @@ BVH_EXPORT int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* de
         BVH_TRY(resolve_status<T>(tree));                                                                                 \
         return sah_cost<T>(tree, out2);                                                                                   \
     }                                                                                                                     \
-    BVH_EXPORT int bvhgpu_refit_##SUF(TREE* tree, const AABB* aabbs, size_t n) { return refit_impl<T>(tree, aabbs, n); } \
+    BVH_EXPORT int bvhgpu_refit_##SUF(TREE* tree, const AABB* aabbs, size_t n) { return refit_impl<T>(tree, aabbs, n, false); } \
+    BVH_EXPORT int bvhgpu_refit_dev_##SUF(TREE* tree, const void* dev_aabbs, size_t n) { return refit_impl<T>(tree, (const AABB*)dev_aabbs, n, true); } \
     BVH_EXPORT int bvhgpu_optimize_##SUF(TREE* tree, const AABB* aabbs, size_t n, double max_growth, size_t* rebuilt) { \
-        return optimize_impl<T>(tree, aabbs, n, max_growth, rebuilt);                                                  \
+        return optimize_impl<T>(tree, aabbs, n, max_growth, rebuilt, false);                                           \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_optimize_dev_##SUF(TREE* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt) { \
+        return optimize_impl<T>(tree, (const AABB*)dev_aabbs, n, max_growth, rebuilt, true);                            \
     }
 
 DEFINE_API(float, f32x3, bvhgpu_tree3f, bvh_aabb3f, bvh_ray3f, bvh_node3f, bvh_flat3f)

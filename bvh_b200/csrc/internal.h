@@ -59,6 +59,13 @@ struct bvhgpu_ctx {
     cudaEvent_t ev_chunk[16] = {}, ev_emit[16] = {};
     cudaEvent_t ev_e2e[5] = {};    // profile: start, walk end, last H2D done, last emit, last D2H
     bool have_e2e = false;
+    // host-pointer traversal, streaming form (rays consumed by a running kernel while they arrive): only when a kernel launch
+    // does not block the host and no tool serialises / replays launches.  -1 = not probed yet, 0 = never stream, 1 = ok.
+    int stream_ok = -1;
+    int64_t traverse_stream = -1;  // option "traverse_stream": -1 auto (probe), 0 never, 1 force
+    int64_t traverse_top = -1;     // option "traverse_top": shared-memory top-of-tree walk: -1 auto, 0 off, 1 on
+    uint32_t* d_async_err = nullptr;   // sticky device-side error word of asynchronous calls (sharded exchange): surfaced by bvhgpu_synchronize
+    int numa_node = -1;            // NUMA node of the device (sysfs), -1 unknown
 };
 #define BVH_MAX_CHUNKS 16u
 
@@ -82,6 +89,8 @@ template <class T> struct Tree {
     BuildStatus* d_status = nullptr;
     BuildStatus* h_status = nullptr;          // pinned
     bool status_pending = false;
+    int failed_status = 0;                    // sticky: first failure of build / refit / optimize (BVHGPU_OK = healthy)
+    std::string failed_message;
     // retained result of the last traversal
     uint32_t* d_offsets = nullptr; size_t offsets_cap = 0;
     uint32_t* d_hits = nullptr;    size_t hits_cap = 0;
@@ -96,6 +105,23 @@ template <class T> int resolve_status(Tree<T>* tree);
 int dalloc(bvhgpu_ctx* ctx, void** p, size_t bytes);
 void dfree(bvhgpu_ctx* ctx, void* p);
 template <class P> inline int dalloc_t(bvhgpu_ctx* ctx, P** p, size_t count) { return dalloc(ctx, (void**)p, count * sizeof(P)); }
+// Scratch that is released (stream-ordered) when the scope ends, on every return path.
+struct Scratch {
+    bvhgpu_ctx* ctx;
+    void* ptrs[16];
+    int n = 0;
+    explicit Scratch(bvhgpu_ctx* c) : ctx(c) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { for (int i = 0; i < n; ++i) dfree(ctx, ptrs[i]); }
+    template <class P> int get(P** p, size_t count) {
+        *p = nullptr;
+        if (n >= 16) { set_error("internal: scratch table full"); return BVHGPU_ERR_INTERNAL; }
+        const int rc = dalloc(ctx, (void**)p, count * sizeof(P));
+        if (rc == BVHGPU_OK) ptrs[n++] = (void*)*p;
+        return rc;
+    }
+};
 
 // ---- build_sah.cu ----
 // in_aabbs: device pointer to n AABBs in the C-ABI layout (24 B / 48 B).  Fills tree->d_aabb, d_nodes,
@@ -128,13 +154,13 @@ template <class T> int refit(Tree<T>* tree);                     // recompute ch
 template <class T> int optimize(Tree<T>* tree, double max_growth);   // refit + exact rebuild of the degraded subtrees
 
 // ---- traverse.cu ----
-// d_rays: rays on the device, or nullptr with h_rays = rays in host memory (chunked, overlapped H2D).
+// d_rays: rays on the device; fmt: BVHGPU_RAYS_FULL (9 scalars: the C-ABI Ray) or BVHGPU_RAYS_OD (6 scalars: origin, direction).
 // shard != nullptr: multi-GPU step, results go to every rank's peer-mapped global CSR (d_offsets / d_hits unused).
-template <class T> int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays,
+template <class T> int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt,
                                        size_t nrays, uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total,
                                        const bvhgpu_shard* shard = nullptr);
-// Host rays in, host CSR out; H2D / walk+scan+emit / D2H pipelined over chunks.  Needs tree->d_offsets / d_hits sized by the caller.
-template <class T> int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::Ray* h_rays, size_t nrays,
+// Host rays in, host CSR out; H2D / walk+scan+emit / D2H overlapped.  Needs tree->d_offsets / d_hits sized by the caller.
+template <class T> int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_t fmt, size_t nrays,
                                                uint32_t* h_offsets, uint32_t* h_hits, size_t h_cap, size_t* total);
 // hits sorted by entry (ascending) / exit (descending) distance, with the distances; device pointers
 template <class T> int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays, size_t nrays, int ascending,

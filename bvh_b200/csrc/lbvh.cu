@@ -162,10 +162,12 @@ __global__ void __launch_bounds__(256) lbvh_emit_kernel(uint32_t n, const uint32
                                                         const uint32_t* __restrict__ L, const T* __restrict__ boxes,
                                                         typename Traits<T>::Node* __restrict__ nodes, uint32_t* __restrict__ node_index,
                                                         uint32_t* __restrict__ node_start,
-                                                        bool treelets, QSlot<T>* q, uint32_t* qseq, uint32_t qmask, BuildCtl* ctl) {
+                                                        bool treelets, QSlot<T>* q, uint32_t* qseq, uint32_t qmask, BuildCtl* ctl,
+                                                        const BuildStatus* __restrict__ status) {
     using Tr = Traits<T>;
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= 2 * n - 1) return;
+    if (status->nan_found) return;          // NaN shapes: no nodes, no treelet tasks -- the build reports BVHGPU_ERR_NAN (the reference panics)
     const bool leaf = v >= n - 1;
     const uint32_t f = leaf ? v - (n - 1) : first[v];
     const uint32_t idx = 2 * f + L[v];
@@ -274,7 +276,7 @@ int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32
     TreeletSession<T> S;
     if (treelets) BVH_TRY(treelet_begin<T>(ctx, tree, vals2, &S));
     lbvh_emit_kernel<T><<<gt, 256, 0, st>>>(n, vals2, left, right, first, count, parent, vi, boxes, tree->d_nodes, tree->d_node_index, tree->d_node_start,
-                                            treelets, S.q, S.qseq, S.qmask, S.ctl);
+                                            treelets, S.q, S.qseq, S.qmask, S.ctl, tree->d_status);
     ctx->launches += 14;
     BVH_CUDA_TRY(cudaGetLastError());
     if (treelets) BVH_TRY(treelet_finish<T>(ctx, tree, &S));

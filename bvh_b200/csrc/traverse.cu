@@ -12,14 +12,23 @@
 // them; an exclusive scan turns counts into offsets; the emit kernel copies the slots into place and
 // re-walks only rays with more than K hits.  K = 0 degenerates to the classic count / scan / fill.
 #include "internal.h"
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
 
 namespace bvhb200 {
 
 // Per-ray hit slots of the single-pass scheme: "traverse_slots" option, or (-1, default) as many as a 1 GB
 // scratch budget allows, between 4 and 64 -- rays with more hits than slots are walked a second time by the emit pass.
+// The budget is additionally capped at a quarter of the free device memory (a 1 GB scratch request must not be what runs
+// a nearly full device out of memory); below 4 slots' worth the path degrades to fewer slots, down to the two-pass scheme.
 static inline uint32_t pick_slots(const bvhgpu_ctx* ctx, uint32_t nrays) {
     if (ctx->traverse_slots >= 0) return (uint32_t)std::min<int64_t>(ctx->traverse_slots, 64);
-    uint64_t k = (1ull << 28) / std::max<uint32_t>(nrays, 1u);
+    uint64_t budget_words = 1ull << 28;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget_words = std::min<uint64_t>(budget_words, (uint64_t)free_b / 16);
+    const uint64_t k = budget_words / std::max<uint32_t>(nrays, 1u);
+    if (k < 4) return (uint32_t)k;                   // 0..3 slots: memory is tight
     uint32_t p = 4;
     while (p * 2 <= k && p < 64) p *= 2;
     return p;
@@ -101,10 +110,24 @@ __device__ __forceinline__ uint32_t walk(const typename Traits<T>::TNode* __rest
     return visits;
 }
 
-template <class T> __device__ __forceinline__ void load_ray(const typename Traits<T>::Ray* __restrict__ rays, size_t r, T o[3], T inv[3]) {
-    const T* p = reinterpret_cast<const T*>(rays + r);
+// Ray batches come in two layouts.  RAYS_FULL: the 9-scalar Ray of the C ABI {origin, direction, inv_direction}.
+// RAYS_OD: 6 scalars {origin, direction} with the direction as Ray stores it (already normalised by Ray::new); the
+// inverse direction is recomputed here with the same IEEE division Ray::new performs (src/ray/ray_impl.rs:76-78), so
+// both layouts give bit-identical traversals while the compact one moves a third fewer bytes across PCIe.
+// L2 = true: the batch is still arriving by DMA while the kernel runs (streaming host path): bypass the non-coherent path.
+template <class T> struct RaySrc { const T* base; uint32_t fmt; };
+constexpr uint32_t RAYS_FULL = 0, RAYS_OD = 1;
+template <class T, bool L2>
+__device__ __forceinline__ void load_ray(const RaySrc<T>& src, size_t r, T o[3], T inv[3]) {
+    if (src.fmt == RAYS_FULL) {
+        const T* p = src.base + 9 * r;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { o[k] = __ldg(p + k); inv[k] = __ldg(p + 6 + k); }
+        for (int k = 0; k < 3; ++k) { o[k] = L2 ? __ldcg(p + k) : __ldg(p + k); inv[k] = L2 ? __ldcg(p + 6 + k) : __ldg(p + 6 + k); }
+    } else {
+        const T* p = src.base + 6 * r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { o[k] = L2 ? __ldcg(p + k) : __ldg(p + k); inv[k] = div_rn(T(1), L2 ? __ldcg(p + 3 + k) : __ldg(p + 3 + k)); }
+    }
 }
 
 // Coherence probe: neighbouring rays of a coherent batch (camera rays) point the same way, and then the static
@@ -115,16 +138,17 @@ template <class T> __device__ __forceinline__ void load_ray(const typename Trait
 // 32 consecutive rays on coherent batches -- 1.91 ms vs 1.46 ms for the static kernel on 4 M Sponza camera rays: the
 // static mapping also keeps neighbouring warps of a CTA on neighbouring pixels, which is what feeds the L1.)
 template <class T>
-__global__ void __launch_bounds__(256) coherence_probe_kernel(const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays, uint32_t* flag) {
+__global__ void __launch_bounds__(256) coherence_probe_kernel(RaySrc<T> rays, uint32_t nrays, uint32_t* flag) {
     __shared__ float acc[8];
     float sum = 0.f;
     const uint32_t samples = 1024, stride = nrays > 2 * samples ? nrays / samples : 1;
+    const uint32_t rstride = rays.fmt == RAYS_FULL ? 9u : 6u;       // the direction sits at scalar 3 in both layouts
     uint32_t n = 0;
     for (uint32_t k = threadIdx.x; k < samples; k += 256) {
         const uint32_t i = k * stride;
         if (i + 1 >= nrays) break;
-        const T* a = reinterpret_cast<const T*>(rays + i) + 3;
-        const T* b = reinterpret_cast<const T*>(rays + i + 1) + 3;
+        const T* a = rays.base + (size_t)rstride * i + 3;
+        const T* b = rays.base + (size_t)rstride * (i + 1) + 3;
         sum += (float)(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
         ++n;
     }
@@ -143,7 +167,7 @@ __global__ void __launch_bounds__(256) coherence_probe_kernel(const typename Tra
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                                          const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                         const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
+                                                         RaySrc<T> rays, uint32_t nrays,
                                                          uint32_t first, uint32_t count,
                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
                                                          unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T
     uint32_t visits = 0;
     if (r < first + count) {
         T o[3], inv[3];
-        load_ray<T>(rays, r, o, inv);
+        load_ray<T, false>(rays, r, o, inv);
         uint32_t cnt = 0;
         visits = walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
             if (cnt < K) slots[(size_t)cnt * nrays + r] = shape;
@@ -167,16 +191,20 @@ __global__ void __launch_bounds__(256) walk_count_kernel(const typename Traits<T
 // Pass 1, persistent form.  A fixed grid of warps pulls rays from a global ticket counter; a lane that finishes
 // its ray is refilled as soon as REFILL lanes of its warp are idle, so warps stay populated although rays take
 // 10..400 visits (the one-ray-per-thread kernel above averages 12 of 32 active lanes on random rays).
-// STREAM: the rays are still arriving from the host (chunked H2D on the copy stream); `ready` counts the rays
-// whose bytes are resident (bumped by a 4-byte DMA after every chunk), lanes wait for their ray to arrive, and
-// ray loads bypass the non-coherent path.  Copy and walk overlap without any per-chunk kernel tail.
+// STREAM: the rays are still arriving from the host (chunked H2D on the copy stream, enqueued BEFORE this kernel is
+// launched); `ready` counts the rays whose bytes are resident (bumped by a 4-byte DMA after every chunk), lanes wait
+// for their ray to arrive, and ray loads bypass the non-coherent path.  Copy and walk overlap without any per-chunk
+// kernel tail.  The wait carries a %globaltimer watchdog: if the copies never come (failed DMA, a tool that replays
+// the kernel against a restored `ready` word) the kernel raises BVHGPU_ERR_TIMEOUT in *err and drains instead of
+// spinning forever.
 template <class T, bool FLAT, bool STREAM>
 __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                                               const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                              const typename Traits<T>::Ray* rays, uint32_t nrays,
+                                                              RaySrc<T> rays, uint32_t nrays,
                                                               uint32_t* __restrict__ ticket, const uint32_t* ready,
                                                               uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
-                                                              unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
+                                                              unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if,
+                                                              uint32_t* err, unsigned long long timeout_ns) {
     if (gate && *gate != run_if) return;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
     constexpr int REFILL = 8;
@@ -194,22 +222,28 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
             base = __shfl_sync(FULL, base, 0);
             if (base >= nrays) exhausted = true;
             const uint32_t mine = base + __popc(need & lt);
-            const bool take = r == NONE && mine < nrays;
+            bool take = r == NONE && mine < nrays;
             if (STREAM) {
                 const uint32_t want = __reduce_max_sync(FULL, take ? mine + 1 : 0u);
                 if (want) {
-                    uint32_t ns = 100;
-                    while (*(volatile const uint32_t*)ready < want) { __nanosleep(ns); if (ns < 2000) ns <<= 1; }
+                    uint32_t ok = 1;
+                    if (lane == 0) {
+                        uint32_t ns = 100;
+                        const unsigned long long t0 = global_timer_ns();
+                        while (*(volatile const uint32_t*)ready < want) {
+                            if (*(volatile const uint32_t*)err != 0u) { ok = 0; break; }          // another warp gave up already
+                            if (global_timer_ns() - t0 > timeout_ns) { ok = 0; atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+                            __nanosleep(ns);
+                            if (ns < 2000) ns <<= 1;
+                        }
+                    }
+                    ok = __shfl_sync(FULL, ok, 0);
                     __threadfence();
+                    if (!ok) { exhausted = true; take = false; }
                 }
             }
             if (take) {
-                const T* p = reinterpret_cast<const T*>(rays + mine);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (STREAM) { o[k] = __ldcg(p + k); inv[k] = __ldcg(p + 6 + k); }
-                    else        { o[k] = __ldg(p + k);  inv[k] = __ldg(p + 6 + k); }
-                }
+                load_ray<T, STREAM>(rays, mine, o, inv);
                 r = mine; i = 0; cnt = 0;
             }
         }
@@ -245,18 +279,20 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
     if (lane == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
 }
 
-// Exclusive scan of counts, phase A: per-block local exclusive offsets + block totals.
+// Exclusive scan of counts, phase A: per-block local exclusive offsets + block totals (+ the largest count, if asked for).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ counts, uint32_t n,
-                                                                  uint32_t* __restrict__ local, unsigned long long* __restrict__ blocksum) {
+                                                                  uint32_t* __restrict__ local, unsigned long long* __restrict__ blocksum,
+                                                                  uint32_t* __restrict__ maxcount) {
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], s = 0;
+    uint32_t v[SCAN_ITEMS], s = 0, m = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0u; s += v[k]; }
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0u; s += v[k]; m = v[k] > m ? v[k] : m; }
     uint32_t incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
     if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    if (maxcount) { m = __reduce_max_sync(0xffffffffu, m); if (lane_id() == 0 && m) atomicMax(maxcount, m); }
     __syncthreads();
     uint32_t woff = 0;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
@@ -291,21 +327,27 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
     if (threadIdx.x == 0) *total = carry_s;
 }
 
-// Destinations of the emit pass.  Single GPU: one destination (the caller's buffers), bases 0.  Sharded: every
-// rank's peer-mapped global CSR; this rank's rays start at ray_base, its hits at *hit_base (known after the
-// totals exchange).
+// Destinations of the emit pass.  Single GPU: one destination (the caller's buffers), bases 0.  Sharded: the hit lists go
+// to every rank's peer-mapped global hit buffer at *hit_base + the local offset (known after the totals exchange); the
+// offsets are NOT shipped -- every rank rebuilds them from the narrow per-ray counts it received (gscan kernels).
 struct EmitDst {
     int world;
-    uint32_t* offsets[BVHGPU_MAX_PEERS];
+    uint32_t* offsets;                       // single GPU: the caller's offsets; sharded: nullptr
     uint32_t* hits[BVHGPU_MAX_PEERS];
-    unsigned long long ray_base;
     const unsigned long long* hit_base;      // nullptr = 0
-    const unsigned long long* grand_total;   // nullptr = local total
-    unsigned long long nrays_global;
-    int self;                                // destination that receives the grand total (local copy)
+    const uint32_t* err;                     // sharded: sticky error word; a failed exchange skips the emit
+    unsigned long long nrays_out;            // single GPU: index of the closing offsets entry
 };
 
-// Totals exchange over peer memory: mailbox layout (u64 words): tot[parity][src][2] = {seq, total}, done[parity][src].
+// ---- exchange over peer memory (multi-GPU ray sharding) -------------------------------------------------------------------
+// Mailbox (u64 words; BVHGPU_MAILBOX_BYTES per rank, zero-initialised):
+//   [ (par*8 + src)*4 + {0,1,2,3} ]  = {seq, hit total, count width in bytes, largest count} published by rank `src`
+//   [ 64 + par*8 + src ]             = seq of the step whose hit stores of rank `src` have landed ("done")
+//   [ 128 + (seq % 1024)*4 + {0..3} ] = trace of this rank: {seq, %globaltimer at the start of the totals wait, ns waited for
+//                                       the peers' totals, ns waited for the peers' done flags}   (diagnostics, bench.py)
+// Count staging (4*nrays_global + 144 bytes per rank): segment of source rank s at byte seg_off(s); rank s stores its per-ray
+// hit counts there in ITS narrowest width (1, 2 or 4 bytes, from its largest count) -- 1 byte per ray on ordinary batches
+// instead of the 4-byte offsets the first version of this exchange replicated to every rank.
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -314,49 +356,147 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-struct PeerBoxes { int rank, world; unsigned long long* box[BVHGPU_MAX_PEERS]; unsigned long long seq; };
+constexpr int MB_TOT = 0, MB_DONE = 64, MB_TRACE = 128, MB_TRACE_LEN = 1024;
+struct PeerBoxes {
+    int rank, world;
+    unsigned long long* box[BVHGPU_MAX_PEERS];
+    unsigned char* stage[BVHGPU_MAX_PEERS];            // count staging of every rank
+    unsigned long long seq;
+    unsigned long long rays_before[BVHGPU_MAX_PEERS + 1];   // prefix sums of the shard sizes
+};
+__host__ __device__ __forceinline__ unsigned long long seg_off(const PeerBoxes& pb, int s) {
+    return ((4ull * pb.rays_before[s] + 15ull) & ~15ull) + 16ull * (unsigned long long)s;
+}
 
-__global__ void xchg_totals_kernel(PeerBoxes pb, const unsigned long long* __restrict__ local_total,
-                                   unsigned long long* __restrict__ xinfo /* {hit_base, grand_total} */, uint32_t* err, unsigned long long timeout_ns) {
-    const int lane = threadIdx.x;
-    const unsigned long long par = pb.seq & 1ull;
-    const unsigned long long mine = *local_total;
-    if (lane < pb.world) {                                   // publish {total, seq} into peer `lane`'s mailbox, slot [par][rank]
-        unsigned long long* slot = pb.box[lane] + (par * BVHGPU_MAX_PEERS + pb.rank) * 2;
-        slot[1] = mine;
+// Every rank pushes its narrowed counts into all ranks' staging (coalesced 16-byte P2P stores), then the last block to finish
+// publishes {total, width, maxcount, seq} into all mailboxes: a peer that sees the seq also sees the counts.
+__global__ void __launch_bounds__(256) xchg_post_kernel(PeerBoxes pb, const uint32_t* __restrict__ counts, uint32_t R,
+                                                        const unsigned long long* __restrict__ local_total, const uint32_t* __restrict__ maxcount,
+                                                        uint32_t* __restrict__ blocks_done) {
+    const uint32_t mc = *maxcount;
+    const uint32_t width = mc <= 0xFFu ? 1u : (mc <= 0xFFFFu ? 2u : 4u);
+    unsigned long long rb_mine = 0;
+#pragma unroll
+    for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k == pb.rank) rb_mine = pb.rays_before[k];
+    const unsigned long long seg = ((4ull * rb_mine + 15ull) & ~15ull) + 16ull * (unsigned long long)pb.rank;
+    const uint32_t per = 16u / width;                                  // rays per 16-byte packet
+    const uint32_t npk = (R + per - 1) / per;
+    for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const uint32_t r0 = pk * per;
+        for (uint32_t k = 0; k < per; ++k) {
+            const uint32_t c = r0 + k < R ? counts[r0 + k] : 0u;
+            const uint32_t bit = k * width * 8u;
+            w[bit >> 5] |= c << (bit & 31u);
+        }
+        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+        for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) *reinterpret_cast<uint4*>(pb.stage[d] + seg + 16ull * pk) = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < (unsigned)pb.world) {
+        const unsigned long long par = pb.seq & 1ull;
+        unsigned long long* slot = pb.box[threadIdx.x] + MB_TOT + (par * BVHGPU_MAX_PEERS + pb.rank) * 4;
+        slot[1] = *local_total; slot[2] = width; slot[3] = mc;
         __threadfence_system();
         st_release_sys(slot, pb.seq);
     }
-    unsigned long long tot = 0;
-    if (lane < pb.world) {                                   // wait for peer `lane`'s total in my own mailbox
-        const unsigned long long* slot = pb.box[pb.rank] + (par * BVHGPU_MAX_PEERS + lane) * 2;
-        const unsigned long long t0 = global_timer_ns();
+    if (threadIdx.x == 0) *blocks_done = 0u;
+}
+
+// xinfo (u64 words): [0] hit base of this rank, [1] grand total, [2+s] count width of rank s.
+__global__ void xchg_wait_kernel(PeerBoxes pb, unsigned long long* __restrict__ xinfo, uint32_t* err, unsigned long long timeout_ns) {
+    const int lane = threadIdx.x;
+    const unsigned long long par = pb.seq & 1ull;
+    unsigned long long tot = 0, width = 1, waited = 0;
+    const unsigned long long t0 = global_timer_ns();
+    if (lane < pb.world) {                                   // wait for peer `lane`'s post in my own mailbox
+        const unsigned long long* slot = pb.box[pb.rank] + MB_TOT + (par * BVHGPU_MAX_PEERS + lane) * 4;
         while (ld_acquire_sys(slot) != pb.seq) {
             if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
-            __nanosleep(200);
+            __nanosleep(100);
         }
-        tot = slot[1];
+        tot = slot[1]; width = slot[2];
+        waited = global_timer_ns() - t0;
     }
-    unsigned long long base = 0, grand = 0;
+    unsigned long long base = 0, grand = 0, wmax = 0;
     for (int r = 0; r < pb.world; ++r) {
-        const unsigned long long v = __shfl_sync(0xffffffffu, tot, r);
+        const unsigned long long v = __shfl_sync(0xffffffffu, tot, r), w = __shfl_sync(0xffffffffu, waited, r);
         if (r < pb.rank) base += v;
         grand += v;
+        wmax = w > wmax ? w : wmax;
     }
-    if (lane == 0) { xinfo[0] = base; xinfo[1] = grand; }
+    if (lane < pb.world) xinfo[2 + lane] = width;
+    if (lane == 0) {
+        xinfo[0] = base; xinfo[1] = grand;
+        unsigned long long* tr = pb.box[pb.rank] + MB_TRACE + (pb.seq % MB_TRACE_LEN) * 4;
+        tr[0] = pb.seq; tr[1] = t0; tr[2] = wmax; tr[3] = 0;
+    }
 }
 
 __global__ void xchg_done_kernel(PeerBoxes pb, uint32_t* err, unsigned long long timeout_ns) {
     const int lane = threadIdx.x;
     const unsigned long long par = pb.seq & 1ull;
     __threadfence_system();                                   // my emit stores (previous kernel) are ordered before the flag
-    if (lane < pb.world) st_release_sys(pb.box[lane] + 4 * BVHGPU_MAX_PEERS + par * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
+    if (lane < pb.world) st_release_sys(pb.box[lane] + MB_DONE + par * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
+    unsigned long long waited = 0;
     if (lane < pb.world) {
-        const unsigned long long* slot = pb.box[pb.rank] + 4 * BVHGPU_MAX_PEERS + par * BVHGPU_MAX_PEERS + lane;
+        const unsigned long long* slot = pb.box[pb.rank] + MB_DONE + par * BVHGPU_MAX_PEERS + lane;
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(slot) != pb.seq) {
             if (global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
-            __nanosleep(200);
+            __nanosleep(100);
+        }
+        waited = global_timer_ns() - t0;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, waited, o); waited = w > waited ? w : waited; }
+    if (lane == 0) pb.box[pb.rank][MB_TRACE + (pb.seq % MB_TRACE_LEN) * 4 + 3] = waited;
+}
+
+// Global offsets from the staged counts: the same two-level scan as the local one, over all nrays_global rays.
+__device__ __forceinline__ uint32_t staged_count(const PeerBoxes& pb, const unsigned char* __restrict__ stage,
+                                                 const unsigned long long* __restrict__ xinfo, unsigned long long g) {
+    int s = 0;
+    unsigned long long rb = 0;
+#pragma unroll
+    for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k < pb.world && g >= pb.rays_before[k]) { s = k; rb = pb.rays_before[k]; }
+    const unsigned long long i = g - rb;
+    const unsigned char* p = stage + (((4ull * rb + 15ull) & ~15ull) + 16ull * (unsigned long long)s);
+    const unsigned long long w = xinfo[2 + s];
+    return w == 1 ? (uint32_t)__ldcg(p + i) : (w == 2 ? (uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p) + i) : __ldcg(reinterpret_cast<const uint32_t*>(p) + i));
+}
+template <bool WRITE>
+__global__ void __launch_bounds__(SCAN_THREADS) gscan_kernel(PeerBoxes pb, const unsigned char* __restrict__ stage, const unsigned long long* __restrict__ xinfo,
+                                                             unsigned long long n, unsigned long long* __restrict__ blocksum,
+                                                             uint32_t* __restrict__ offsets, const uint32_t* __restrict__ err) {
+    if (*err) return;
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? staged_count(pb, stage, xinfo, base + k) : 0u; s += v[k]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+    if (!WRITE) {
+        if (threadIdx.x == SCAN_THREADS - 1) blocksum[blockIdx.x] = (unsigned long long)(woff + incl);
+    } else {
+        unsigned long long run = blocksum[blockIdx.x] + woff + incl - s;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) offsets[base + k] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run; run += v[k]; }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) {
+            const unsigned long long t = xinfo[1];
+            offsets[n] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
         }
     }
 }
@@ -365,60 +505,69 @@ __global__ void xchg_done_kernel(PeerBoxes pb, uint32_t* err, unsigned long long
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                                    const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                   const typename Traits<T>::Ray* __restrict__ rays, uint32_t nrays,
+                                                   RaySrc<T> rays, uint32_t nrays,
                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
                                                    const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
                                                    const unsigned long long* __restrict__ total,
                                                    EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count) {
+    if (dst.err && *dst.err) return;
     const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long hbase = dst.hit_base ? *dst.hit_base : 0ull;
-    if (r == first) {                         // (chunked host path: the last chunk's write is the final total)
-        const unsigned long long t = dst.grand_total ? *dst.grand_total : *total;
-        dst.offsets[dst.self][dst.nrays_global] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
+    if (r == first && dst.offsets) {          // (chunked host path: the last chunk's write is the final total)
+        const unsigned long long t = *total;
+        dst.offsets[dst.nrays_out] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
     }
     if (r >= first + count) return;
     const unsigned long long off = hbase + blocksum[r / SCAN_TILE] + local[r];
-    const uint32_t off32 = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
-    for (int d = 0; d < dst.world; ++d) dst.offsets[d][dst.ray_base + r] = off32;
+    if (dst.offsets) dst.offsets[r] = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
     const uint32_t c = counts[r];
     if (c == 0 || dst.hits[0] == nullptr) return;
     if (c <= K) {
         for (uint32_t k = 0; k < c; ++k) {
             if (off + k < cap) {
                 const uint32_t h = slots[(size_t)k * nrays + r];
-                for (int d = 0; d < dst.world; ++d) dst.hits[d][off + k] = h;
+#pragma unroll
+                for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < dst.world) dst.hits[d][off + k] = h;
             }
         }
     } else {
         T o[3], inv[3];
-        load_ray<T>(rays, r, o, inv);
+        load_ray<T, false>(rays, r, o, inv);
         unsigned long long w = off;
         walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
-            if (w < cap) for (int d = 0; d < dst.world; ++d) dst.hits[d][w] = shape;
+            if (w < cap) {
+#pragma unroll
+                for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < dst.world) dst.hits[d][w] = shape;
+            }
             ++w;
         });
     }
 }
 
 // Launch pass 1 over rays [first, first+count): persistent refill kernel (default) or one ray per thread.
-// sums layout (u64 words): [nblk] total, [nblk+1] visits, [nblk+2..3] exchange info, [nblk+4] error, [nblk+5] ticket, [nblk+6] ready.
+// sums layout (u64 words): [nblk] total, [nblk+1] visits, [nblk+2 .. nblk+11] exchange info, [nblk+12] error, [nblk+13] ticket,
+// [nblk+14] ready, [nblk+15] probe verdict, [nblk+16] largest count, [nblk+17] block counter of the exchange post.
+constexpr uint32_t SUMS_TAIL = 20;
+constexpr uint32_t S_TOTAL = 0, S_VISITS = 1, S_XINFO = 2, S_ERR = 12, S_TICKET = 13, S_READY = 14, S_GATE = 15, S_MAXC = 16, S_BLKDONE = 17;
+constexpr unsigned long long STREAM_TIMEOUT_NS = 4ull * 1000ull * 1000ull * 1000ull;
 template <class T>
-static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray* rays, uint32_t R, uint32_t first, uint32_t count,
+static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, uint32_t first, uint32_t count,
                         uint32_t* counts, uint32_t* slots, uint32_t K, unsigned long long* sums, uint32_t nblk, bool stream_mode) {
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
+    unsigned long long* tail = sums + nblk;
     // traverse_persistent: 0 = one ray per thread, 1 = persistent refill, 2 (default) = probe decides on the device
     const int64_t pmode = stream_mode ? 1 : ctx->traverse_persistent;
     uint32_t* gate = nullptr;
     if (pmode >= 2) {
-        gate = reinterpret_cast<uint32_t*>(sums + nblk + 7);
+        gate = reinterpret_cast<uint32_t*>(tail + S_GATE);
         coherence_probe_kernel<T><<<1, 256, 0, st>>>(rays, R, gate);
         ctx->launches++;
     }
     if (pmode == 0 || pmode >= 2) {
         const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, sums + nblk + 1, gate, 1u);
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
         ctx->launches++;
         if (pmode == 0) return BVHGPU_OK;
     }
@@ -429,27 +578,28 @@ static int launch_pass1(Tree<T>* tree, bool flat, const typename Traits<T>::Ray*
         ctx->walk_grid = ctx->sm_count * (occ < 1 ? 1 : occ);
     }
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->walk_grid, ((uint64_t)R + 255) / 256);
-    uint32_t* ticket = reinterpret_cast<uint32_t*>(sums + nblk + 5);
-    const uint32_t* ready = reinterpret_cast<const uint32_t*>(sums + nblk + 6);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
+    const uint32_t* ready = reinterpret_cast<const uint32_t*>(tail + S_READY);
+    uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);
     if (stream_mode) {
-        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, nullptr, 0u);
-        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, nullptr, 0u);
+        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
+        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
     } else {
-        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, gate, 0u);
-        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, sums + nblk + 1, gate, 0u);
+        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
+        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
     }
     ctx->launches++;
     return BVHGPU_OK;
 }
 
 template <class T>
-int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_rays, const typename Traits<T>::Ray* h_rays, size_t nrays,
+int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, size_t nrays,
                     uint32_t* d_offsets, uint32_t* d_hits, size_t cap, size_t* total, const bvhgpu_shard* shard) {
-    using Ray = typename Traits<T>::Ray;
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
     if (nrays > 0x7FFFFFFFull) { set_error("traverse: nrays %zu exceeds 2^31-1", nrays); return BVHGPU_ERR_INVALID; }
     if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("traverse: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
+    if (fmt != RAYS_FULL && fmt != RAYS_OD) { set_error("traverse: bad ray layout %u", fmt); return BVHGPU_ERR_INVALID; }
     tree->last_nrays = nrays;
     if (nrays == 0) {
         if (d_offsets) BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t), st));
@@ -457,7 +607,6 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         tree->last_total = 0;
         return BVHGPU_OK;
     }
-    if (h_rays) { set_error("internal: host rays go through traverse_host_pipelined"); return BVHGPU_ERR_INTERNAL; }
     if (tree->n == 0) {                                          // empty Bvh: no hits (bvh_impl.rs:109-112)
         BVH_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * (nrays + 1), st));
         if (total) *total = 0;
@@ -466,51 +615,73 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
     }
     BVH_TRY(resolve_status(tree));                               // never walk a tree whose build failed
     if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const RaySrc<T> rays{reinterpret_cast<const T*>(d_rays), fmt};
     const uint32_t R = (uint32_t)nrays;
     const uint32_t K = pick_slots(ctx, R);
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    Scratch scratch(ctx);
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
-    unsigned long long* sums = nullptr;       // [nblk] block offsets, [nblk] total, [nblk+1] visits
-    BVH_TRY(dalloc_t(ctx, &counts, R));
-    BVH_TRY(dalloc_t(ctx, &local, R));
-    if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 8));      // see launch_pass1 for the layout of the tail words
-    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 8 * sizeof(unsigned long long), st));
+    unsigned long long* sums = nullptr;       // [nblk] block offsets, then the tail words (see launch_pass1)
+    BVH_TRY(scratch.get(&counts, R));
+    BVH_TRY(scratch.get(&local, R));
+    if (K) BVH_TRY(scratch.get(&slots, (size_t)K * R));
+    BVH_TRY(scratch.get(&sums, (size_t)nblk + SUMS_TAIL));
+    unsigned long long* tail = sums + nblk;
+    BVH_CUDA_TRY(cudaMemsetAsync(tail, 0, SUMS_TAIL * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     {
         if (ctx->profile) cudaEventRecord(ctx->ev_walk[0], st);
-        BVH_TRY(launch_pass1<T>(tree, flat, d_rays, R, 0, R, counts, slots, K, sums, nblk, false));
+        BVH_TRY(launch_pass1<T>(tree, flat, rays, R, 0, R, counts, slots, K, sums, nblk, false));
         if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
     }
     const int grid = (R + 255) / 256;
-    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
-    scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, shard ? reinterpret_cast<uint32_t*>(tail + S_MAXC) : nullptr);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, tail + S_TOTAL);
+    ctx->launches += 2;
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
     if (total) {                                                  // the total is known before the hit lists are written
-        BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        BVH_CUDA_TRY(cudaMemcpyAsync(h, tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     }
     EmitDst dst{};
     PeerBoxes pb{};
     const unsigned long long xchg_timeout = 10ull * 1000ull * 1000ull * 1000ull;
     if (shard) {
-        dst.world = shard->world; dst.self = shard->rank; dst.ray_base = shard->rays_before; dst.nrays_global = shard->nrays_global;
-        dst.hit_base = sums + nblk + 2; dst.grand_total = sums + nblk + 3;
-        pb.rank = shard->rank; pb.world = shard->world; pb.seq = shard->seq;
-        for (int d = 0; d < shard->world; ++d) {
-            dst.offsets[d] = (uint32_t*)shard->peer_offsets[d]; dst.hits[d] = (uint32_t*)shard->peer_hits[d];
+        const int W = shard->world;
+        dst.world = W; dst.offsets = nullptr; dst.hit_base = tail + S_XINFO; dst.err = ctx->d_async_err;
+        pb.rank = shard->rank; pb.world = W; pb.seq = shard->seq;
+        pb.rays_before[0] = 0;
+        for (int d = 0; d < W; ++d) {
+            dst.hits[d] = (uint32_t*)shard->peer_hits[d];
             pb.box[d] = (unsigned long long*)shard->peer_mailbox[d];
+            pb.stage[d] = (unsigned char*)shard->peer_counts[d];
+            pb.rays_before[d + 1] = pb.rays_before[d] + shard->shard_rays[d];
         }
+        for (int d = W; d < BVHGPU_MAX_PEERS; ++d) pb.rays_before[d + 1] = pb.rays_before[W];
+        const unsigned long long NG = pb.rays_before[W];
+        if (shard->shard_rays[shard->rank] != nrays) { set_error("traverse_sharded: shard_rays[rank] = %zu but nrays = %zu", shard->shard_rays[shard->rank], nrays); return BVHGPU_ERR_INVALID; }
+        if (NG > 0x7FFFFFFFull) { set_error("traverse_sharded: %llu rays in total exceed 2^31-1", NG); return BVHGPU_ERR_INVALID; }
         cap = shard->cap;
-        xchg_totals_kernel<<<1, 32, 0, st>>>(pb, sums + nblk, sums + nblk + 2, (uint32_t*)(sums + nblk + 4), xchg_timeout);
-        ctx->launches++;
+        const int pgrid = (int)std::min<uint32_t>(2u * (uint32_t)ctx->sm_count, (R / 16 + 255) / 256 + 1);
+        xchg_post_kernel<<<pgrid, 256, 0, st>>>(pb, counts, R, tail + S_TOTAL, reinterpret_cast<const uint32_t*>(tail + S_MAXC), reinterpret_cast<uint32_t*>(tail + S_BLKDONE));
+        xchg_wait_kernel<<<1, 32, 0, st>>>(pb, tail + S_XINFO, ctx->d_async_err, xchg_timeout);
+        // global offsets from everybody's counts (local work), before this rank reports "done": a peer that has seen all
+        // done flags may start its next step and overwrite the staging
+        const uint32_t gblk = (uint32_t)((NG + SCAN_TILE - 1) / SCAN_TILE);
+        unsigned long long* gsums = nullptr;
+        BVH_TRY(scratch.get(&gsums, (size_t)gblk + 1));
+        BVH_CUDA_TRY(cudaMemsetAsync(gsums + gblk, 0, sizeof(unsigned long long), st));
+        gscan_kernel<false><<<gblk, SCAN_THREADS, 0, st>>>(pb, pb.stage[pb.rank], tail + S_XINFO, NG, gsums, nullptr, ctx->d_async_err);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(gsums, gblk, gsums + gblk);
+        gscan_kernel<true><<<gblk, SCAN_THREADS, 0, st>>>(pb, pb.stage[pb.rank], tail + S_XINFO, NG, gsums, (uint32_t*)shard->offsets, ctx->d_async_err);
+        ctx->launches += 5;
     } else {
-        dst.world = 1; dst.self = 0; dst.offsets[0] = d_offsets; dst.hits[0] = d_hits; dst.ray_base = 0; dst.nrays_global = R;
+        dst.world = 1; dst.offsets = d_offsets; dst.hits[0] = d_hits; dst.nrays_out = R;
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap, 0u, R);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_rays, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)cap, 0u, R);
-    if (shard) { xchg_done_kernel<<<1, 32, 0, st>>>(pb, (uint32_t*)(sums + nblk + 4), xchg_timeout); ctx->launches++; }
-    ctx->launches += 3;
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R);
+    ctx->launches++;
+    if (shard) { xchg_done_kernel<<<1, 32, 0, st>>>(pb, ctx->d_async_err, xchg_timeout); ctx->launches++; }
     BVH_CUDA_TRY(cudaGetLastError());
     int rc = BVHGPU_OK;
     if (total) {
@@ -521,85 +692,162 @@ int traverse_device(Tree<T>* tree, int mode, const typename Traits<T>::Ray* d_ra
         if (h[0] > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", h[0]); rc = BVHGPU_ERR_CAPACITY; }
         else if (d_hits && h[0] > cap) { set_error("traverse: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
     }
-    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums);
     return rc;
 }
 
-// Host-pointer entry point, fully pipelined: the batch is cut into chunks; chunk c's H2D copy (copy stream) overlaps
-// the walk / scan / emit of chunk c-1 (compute stream), and chunk c-1's offsets travel back (D2H stream) while chunk c
-// is walked.  The per-chunk scans chain through a running total on the device, so every chunk's offsets are final as
-// soon as its emit kernel has run.  Results are retained in tree->d_offsets / d_hits (bvhgpu_traverse_fetch_*).
+// ---- may the host path stream rays into a running kernel? ------------------------------------------------------------------
+// The streaming form needs (a) kernel launches that return to the host while the kernel runs and (b) nobody replaying or
+// serialising kernels.  Neither holds under CUDA_LAUNCH_BLOCKING=1, cuda-gdb, compute-sanitizer or Nsight Compute (which
+// replays a kernel several times against restored memory: the DMA-bumped `ready` word would be rolled back).  Those are
+// recognised from the environment / the injected libraries; in addition a one-off probe checks property (a) directly: a
+// kernel that waits (bounded) for a flag which only a LATER-enqueued copy on another stream sets.
+__global__ void overlap_probe_kernel(const volatile uint32_t* flag, uint32_t* saw, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_timer_ns();
+    uint32_t ok = 0;
+    for (;;) {
+        if (*flag) { ok = 1; break; }
+        if (global_timer_ns() - t0 > timeout_ns) break;
+        __nanosleep(200);
+    }
+    *saw = ok;
+}
+static bool tooling_detected() {
+    const char* lb = getenv("CUDA_LAUNCH_BLOCKING");
+    if (lb && lb[0] && strcmp(lb, "0") != 0) return true;
+    static const char* vars[] = {"CUDA_INJECTION64_PATH", "CUDA_INJECTION32_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NVTX_INJECTION64_PATH",
+                                 "CUDBG_USE_LEGACY_DEBUGGER", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NSIGHT_CUDA_DEBUGGER", "CUDA_DEBUGGER_SOFTWARE_PREEMPTION"};
+    for (const char* v : vars) { const char* e = getenv(v); if (e && e[0]) return true; }
+    FILE* f = fopen("/proc/self/maps", "r");
+    if (f) {
+        char line[1024];
+        bool found = false;
+        while (!found && fgets(line, sizeof line, f))
+            if (strstr(line, "nsight") || strstr(line, "libcuda-injection") || strstr(line, "libsanitizer-collection") || strstr(line, "libInterceptorInjection") || strstr(line, "libTreeLauncher"))
+                found = true;
+        fclose(f);
+        if (found) return true;
+    }
+    return false;
+}
+static int stream_capable(bvhgpu_ctx* ctx) {
+    if (ctx->traverse_stream == 0) return 0;
+    if (ctx->traverse_stream == 1) return 1;
+    if (tooling_detected()) return 0;                           // re-checked every call: cheap, and a tool can attach later
+    if (ctx->stream_ok >= 0) return ctx->stream_ok;
+    ctx->stream_ok = 0;
+    uint32_t* d = nullptr;
+    if (dalloc_t(ctx, &d, 2) != BVHGPU_OK) return 0;
+    uint32_t* h = ctx->h_pinned + 128;
+    bool ok = cudaMemsetAsync(d, 0, 2 * sizeof(uint32_t), ctx->stream) == cudaSuccess;
+    ok = ok && cudaEventRecord(ctx->ev_order, ctx->stream) == cudaSuccess && cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0) == cudaSuccess;
+    if (ok) {
+        overlap_probe_kernel<<<1, 1, 0, ctx->stream>>>(d, d + 1, 20ull * 1000ull * 1000ull);      // gives up after 20 ms
+        h[0] = 1u;
+        ok = cudaMemcpyAsync(d, h, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(h + 1, d + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+        ok = (cudaStreamSynchronize(ctx->copy_stream) == cudaSuccess) && ok;
+        ok = (cudaStreamSynchronize(ctx->stream) == cudaSuccess) && ok;
+        ctx->launches++;
+        if (ok && h[1] == 1u) ctx->stream_ok = 1;
+    }
+    dfree(ctx, d);
+    return ctx->stream_ok;
+}
+
+// Host-pointer entry point.  Large batches on an undisturbed device are STREAMED: the batch is copied in chunks on the copy
+// stream, each followed by a 4-byte DMA that bumps a device-side `ready` counter, and ONE persistent walk kernel -- launched
+// AFTER all copies are enqueued, so it never depends on work the host has yet to submit -- consumes the rays as they arrive.
+// Small batches, and any process in which launches are serialised or replayed (see stream_capable), take the plain form:
+// one copy, then the same kernels as the device-pointer path.  The emit pass runs in slices whose offsets travel back on the
+// D2H stream while the next slice is emitted.  Results are retained in tree->d_offsets / d_hits (bvhgpu_traverse_fetch_*).
 template <class T>
-int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::Ray* h_rays, size_t nrays,
+int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_t fmt, size_t nrays,
                             uint32_t* h_offsets, uint32_t* h_hits, size_t h_cap, size_t* total) {
-    using Ray = typename Traits<T>::Ray;
     bvhgpu_ctx* ctx = tree->ctx;
     cudaStream_t st = ctx->stream;
     const uint32_t R = (uint32_t)nrays;
     BVH_TRY(resolve_status(tree));
+    if (fmt != RAYS_FULL && fmt != RAYS_OD) { set_error("traverse: bad ray layout %u", fmt); return BVHGPU_ERR_INVALID; }
     if (!tree->d_tnodes) BVH_TRY(build_traversal_records(tree));
+    const size_t ray_bytes = (fmt == RAYS_FULL ? 9 : 6) * sizeof(T);
     const uint32_t K = pick_slots(ctx, R);
     const uint32_t nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
+    Scratch scratch(ctx);
     uint32_t *counts = nullptr, *slots = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;
-    Ray* staged = nullptr;
-    BVH_TRY(dalloc_t(ctx, &counts, R));
-    BVH_TRY(dalloc_t(ctx, &local, R));
-    if (K) BVH_TRY(dalloc_t(ctx, &slots, (size_t)K * R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 8));
-    BVH_TRY(dalloc_t(ctx, &staged, R));
-    BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 8 * sizeof(unsigned long long), st));
-    BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));
-    BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
-    BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_order, 0));
+    unsigned char* staged = nullptr;
+    BVH_TRY(scratch.get(&counts, R));
+    BVH_TRY(scratch.get(&local, R));
+    if (K) BVH_TRY(scratch.get(&slots, (size_t)K * R));
+    BVH_TRY(scratch.get(&sums, (size_t)nblk + SUMS_TAIL));
+    BVH_TRY(scratch.get(&staged, ray_bytes * R));
+    unsigned long long* tail = sums + nblk;
+    BVH_CUDA_TRY(cudaMemsetAsync(tail, 0, SUMS_TAIL * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
+    const RaySrc<T> rays{reinterpret_cast<const T*>(staged), fmt};
     EmitDst dst{};
-    dst.world = 1; dst.self = 0; dst.offsets[0] = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.ray_base = 0; dst.nrays_global = R;
-    // ONE persistent walk kernel consumes the rays as they arrive: the batch is copied in small chunks on the copy
-    // stream, each followed by a 4-byte DMA that bumps the device-side `ready` counter the kernel's lanes wait on.
+    dst.world = 1; dst.offsets = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.nrays_out = R;
+    const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 32768));
+    const bool streaming = nchunks > 1 && stream_capable(ctx) == 1;
+    BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));             // the scratch (and its zeroed tail) exists from here on
+    BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_order, 0));
     if (ctx->profile) cudaEventRecord(ctx->ev_e2e[0], st);
-    BVH_TRY(launch_pass1<T>(tree, flat, staged, R, 0, R, counts, slots, K, sums, nblk, true));
-    if (ctx->profile) cudaEventRecord(ctx->ev_e2e[1], st);
-    {
-        const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 32768));
+    if (streaming) {
+        BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
         uint32_t* h_ready = ctx->h_pinned + 64;                  // pinned: one value per chunk, alive until the final sync
-        uint32_t* d_ready = reinterpret_cast<uint32_t*>(sums + nblk + 6);
+        uint32_t* d_ready = reinterpret_cast<uint32_t*>(tail + S_READY);
         for (uint32_t c = 0; c < nchunks; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
-            BVH_CUDA_TRY(cudaMemcpyAsync(staged + lo, h_rays + lo, sizeof(Ray) * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream));
+            cudaError_t e = cudaMemcpyAsync(staged + ray_bytes * lo, (const unsigned char*)h_rays + ray_bytes * lo, ray_bytes * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream);
             h_ready[c] = hi;
-            BVH_CUDA_TRY(cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e != cudaSuccess) {                               // nothing waits on `ready` yet (the kernel is launched below): just report
+                set_error("traverse: H2D copy of chunk %u failed: %s", c, cudaGetErrorString(e));
+                cudaStreamSynchronize(ctx->copy_stream);
+                return BVHGPU_ERR_CUDA;
+            }
         }
         if (ctx->profile) cudaEventRecord(ctx->ev_e2e[2], ctx->copy_stream);
+        const int rc1 = launch_pass1<T>(tree, flat, rays, R, 0, R, counts, slots, K, sums, nblk, true);
+        if (rc1 != BVHGPU_OK) { cudaStreamSynchronize(ctx->copy_stream); return rc1; }      // the copies still target the scratch
+        if (ctx->profile) cudaEventRecord(ctx->ev_e2e[1], st);
+    } else {
+        BVH_CUDA_TRY(cudaMemcpyAsync(staged, h_rays, ray_bytes * R, cudaMemcpyHostToDevice, st));
+        if (ctx->profile) cudaEventRecord(ctx->ev_e2e[2], st);
+        BVH_TRY(launch_pass1<T>(tree, flat, rays, R, 0, R, counts, slots, K, sums, nblk, false));
+        if (ctx->profile) cudaEventRecord(ctx->ev_e2e[1], st);
     }
     {
-        const int grid = (R + 255) / 256;
-        scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
+        scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, nullptr);
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, tail + S_TOTAL);
         // emit + D2H of the offsets in 4 slices so that the copy back overlaps the rest of the emit
         const uint32_t nsl = R >= 400000 ? 4 : 1;
         for (uint32_t c = 0; c < nsl; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nsl), hi = (uint32_t)((uint64_t)R * (c + 1) / nsl), cnt = hi - lo;
             const int g = (cnt + 255) / 256;
-            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
-            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, staged, R, counts, slots, K, local, sums, sums + nblk, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt);
             BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
             BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
             const uint32_t ncopy = cnt + (c + 1 == nsl ? 1u : 0u);
             BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
-        (void)grid;
         if (ctx->profile) { cudaEventRecord(ctx->ev_e2e[3], st); cudaEventRecord(ctx->ev_e2e[4], ctx->d2h_stream); ctx->have_e2e = true; }
         ctx->launches += 2 + nsl;
     }
     BVH_CUDA_TRY(cudaGetLastError());
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
-    BVH_CUDA_TRY(cudaMemcpyAsync(h, sums + nblk, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BVH_CUDA_TRY(cudaMemcpyAsync(h, tail, (S_ERR + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     BVH_CUDA_TRY(cudaStreamSynchronize(st));
-    dfree(ctx, counts); dfree(ctx, local); if (slots) dfree(ctx, slots); dfree(ctx, sums); dfree(ctx, staged);
-    const unsigned long long tot = h[0];
-    tree->last_total = (size_t)tot; tree->last_visits = h[1]; tree->last_nrays = nrays;
+    const unsigned long long tot = h[S_TOTAL];
+    tree->last_total = (size_t)tot; tree->last_visits = h[S_VISITS]; tree->last_nrays = nrays;
     if (total) *total = (size_t)tot;
+    if ((uint32_t)h[S_ERR] != 0u) {
+        cudaStreamSynchronize(ctx->d2h_stream);
+        if (streaming) ctx->stream_ok = 0;                        // whatever starved the kernel: do not stream again on this context
+        set_error("traverse: the streamed rays did not arrive within %.1f s (device watchdog); the result is invalid", (double)STREAM_TIMEOUT_NS * 1e-9);
+        return BVHGPU_ERR_TIMEOUT;
+    }
     int rc = BVHGPU_OK;
     if (tot > 0xFFFFFFFFull) { set_error("traverse: %llu hits overflow the u32 CSR offsets", tot); rc = BVHGPU_ERR_CAPACITY; }
     else if (tot > tree->hits_cap) { set_error("traverse: %llu hits exceed the retained buffer (%zu)", tot, tree->hits_cap); rc = BVHGPU_ERR_CAPACITY; }
@@ -609,8 +857,8 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const typename Traits<T>::R
     BVH_CUDA_TRY(cudaStreamSynchronize(ctx->d2h_stream));
     return rc;
 }
-template int traverse_host_pipelined<float>(Tree<float>*, int, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
-template int traverse_host_pipelined<double>(Tree<double>*, int, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_host_pipelined<float>(Tree<float>*, int, const void*, uint32_t, size_t, uint32_t*, uint32_t*, size_t, size_t*);
+template int traverse_host_pipelined<double>(Tree<double>*, int, const void*, uint32_t, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 
 // ---- the other IntersectsAabb implementors: Aabb, Point, Ball (src/aabb/intersection.rs:35-45, src/ball.rs:85-106) ----
 // Same stackless walk, another predicate.  Query records: Aabb {min,max} (6 T), Point (3 T), Ball {center, radius} (4 T).
@@ -736,7 +984,7 @@ static int query_launch(Tree<T>* tree, bool flat, const T* d_queries, uint32_t n
     const int grid = (nq + 255) / 256;
     if (flat) query_kernel<T, KIND, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     else      query_kernel<T, KIND, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, nq, local, sums);
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, nq, local, sums, nullptr);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
     if (flat) query_kernel<T, KIND, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
     else      query_kernel<T, KIND, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
@@ -976,7 +1224,7 @@ __global__ void __launch_bounds__(256) ordered_kernel(const typename Traits<T>::
     if (FILL && r == 0) { const unsigned long long t = *total; offsets[nrays] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t; }
     if (r >= nrays) return;
     T o[3], inv[3];
-    load_ray<T>(rays, r, o, inv);
+    load_ray<T, false>(RaySrc<T>{reinterpret_cast<const T*>(rays), RAYS_FULL}, r, o, inv);
     unsigned long long base = 0, w = 0;
     if (FILL) { base = blocksum[r / SCAN_TILE] + local[r]; offsets[r] = base > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)base; w = base; }
     uint32_t cnt = 0, i = 0;
@@ -1026,7 +1274,7 @@ int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays
     BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
     const int grid = (R + 255) / 256;
     ordered_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, d_rays, R, ascending, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums);
+    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, nullptr);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
     ordered_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, d_rays, R, ascending, counts, local, sums, sums + nblk, d_offsets, d_hits, d_dists, (unsigned long long)cap);
     ctx->launches += 4;
@@ -1073,8 +1321,8 @@ int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t
     return BVHGPU_OK;
 }
 
-template int traverse_device<float>(Tree<float>*, int, const bvh_ray3f*, const bvh_ray3f*, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
-template int traverse_device<double>(Tree<double>*, int, const bvh_ray3d*, const bvh_ray3d*, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
+template int traverse_device<float>(Tree<float>*, int, const void*, uint32_t, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
+template int traverse_device<double>(Tree<double>*, int, const void*, uint32_t, size_t, uint32_t*, uint32_t*, size_t, size_t*, const bvhgpu_shard*);
 template int rays_new_device<float>(bvhgpu_ctx*, const float*, const float*, size_t, bvh_ray3f*);
 template int rays_new_device<double>(bvhgpu_ctx*, const double*, const double*, size_t, bvh_ray3d*);
 

@@ -66,13 +66,14 @@ def allgather_csr(offsets: torch.Tensor, hits: torch.Tensor, total: int | None =
 
 
 class ShardedTraversal:
-    """The multi-GPU step with the exchange fused into the traversal (bvhgpu_traverse_sharded_dev_*): every rank
-    holds a peer-mapped copy of the global CSR; after its walk a rank publishes its hit total into all peers'
-    mailboxes over NVLink and its emit kernel stores its rebased offsets / hit lists straight into every rank's
-    buffers (P2P stores).  No NCCL call and no host synchronisation on the data path; torch.distributed is used
-    once, at construction, to swap the CUDA IPC handles."""
+    """The multi-GPU step with the exchange fused into the traversal (bvhgpu_traverse_sharded_dev_*): every rank ends the step
+    with its own copy of the global CSR.  After its walk a rank pushes its per-ray hit COUNTS (1 byte per ray unless a ray has
+    more than 255 hits) into all peers' staging buffers and publishes its hit total in their mailboxes; every rank rebuilds the
+    global offsets with a local scan; the emit kernel stores the hit lists straight into every rank's hit buffer (P2P stores over
+    NVLink).  No NCCL call and no host synchronisation on the data path; torch.distributed is used once, at construction, to
+    swap the CUDA IPC handles."""
 
-    def __init__(self, bvh, nrays_local: int, cap: int, group=None):
+    def __init__(self, bvh, nrays_local: int, cap: int, group=None, ray_layout: int = 0):
         import ctypes as C
 
         import numpy as np
@@ -80,29 +81,35 @@ class ShardedTraversal:
         from . import capi
 
         self.bvh, self.capi, self.C, self.np = bvh, capi, C, np
+        self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > capi.MAX_PEERS:
             raise ValueError(f"at most {capi.MAX_PEERS} ranks")
         sizes = [None] * self.world
         dist.all_gather_object(sizes, int(nrays_local), group=group)
+        if min(sizes) <= 0:
+            raise ValueError("every rank needs a non-empty shard")
         self.n_each = sizes
         self.nrays_global = sum(sizes)
         self.rays_before = sum(sizes[: self.rank])
         self.cap = int(cap)
         L, ctx = capi.lib(), bvh.ctx._h
         self._own, handles = [], []
-        for nbytes in (4 * (self.nrays_global + 1), 4 * self.cap, capi.MAILBOX_BYTES):
+        # peer-mapped: count staging, global hit lists, mailbox; local only: the global offsets
+        for nbytes in (capi.shard_stage_bytes(self.nrays_global), 4 * self.cap, capi.MAILBOX_BYTES, 4 * (self.nrays_global + 1)):
             ptr, h = C.c_void_p(), (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
             capi.check(L.bvhgpu_peer_alloc(ctx, nbytes, C.byref(ptr), h))
             self._own.append(ptr)
             handles.append(bytes(h))
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, handles, group=group)
+        dist.all_gather_object(everyone, handles[:3], group=group)
         self._opened = []
         self.shard = capi.Shard()
         self.shard.rank, self.shard.world = self.rank, self.world
-        self.shard.rays_before, self.shard.nrays_global, self.shard.cap, self.shard.seq = self.rays_before, self.nrays_global, self.cap, 0
+        self.shard.cap, self.shard.seq, self.shard.ray_layout = self.cap, 0, int(ray_layout)
+        self.shard.offsets = self._own[3].value
         for r in range(self.world):
+            self.shard.shard_rays[r] = sizes[r]
             ptrs = []
             for k in range(3):
                 if r == self.rank:
@@ -113,7 +120,7 @@ class ShardedTraversal:
                     capi.check(L.bvhgpu_peer_open(ctx, hb, C.byref(p)))
                     self._opened.append(p)
                     ptrs.append(p.value)
-            self.shard.peer_offsets[r], self.shard.peer_hits[r], self.shard.peer_mailbox[r] = ptrs
+            self.shard.peer_counts[r], self.shard.peer_hits[r], self.shard.peer_mailbox[r] = ptrs
         dist.barrier(group=group)
         self._fn = getattr(L, f"bvhgpu_traverse_sharded_dev_{bvh._d['suffix']}")
 
@@ -123,23 +130,46 @@ class ShardedTraversal:
         self.shard.seq += 1
         self.capi.check(self._fn(self.bvh._h, mode, self.C.c_void_p(rays_ptr), nrays, self.C.byref(self.shard)))
 
-    def fetch(self):
-        """Global CSR as numpy arrays (offsets u32[n_global+1], hits u32[total]); synchronises."""
+    def step_host(self, host_rays_ptr: int, dev_rays_ptr: int, nbytes: int, nrays: int, mode: int = 0):
+        """The step with this rank's shard still in (pinned) host memory: H2D on the context's stream, then step()."""
+        self.capi.check(self.capi.lib().bvhgpu_memcpy_h2d_async(self.bvh.ctx._h, self.C.c_void_p(dev_rays_ptr), self.C.c_void_p(host_rays_ptr), nbytes))
+        self.step(dev_rays_ptr, nrays, mode)
+
+    def fetch(self, offsets_out=None, hits_out=None):
+        """Global CSR as numpy arrays (offsets u32[n_global+1], hits u32[total]); synchronises and raises if a peer timed out
+        (bvhgpu_synchronize), if the u32 offsets overflowed or if the hit lists did not fit `cap`."""
         np, C, L = self.np, self.C, self.capi.lib()
-        off = np.empty(self.nrays_global + 1, dtype=np.uint32)
-        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, off.ctypes.data_as(C.c_void_p), self._own[0], off.nbytes))
-        total = int(off[-1])
-        hits = np.empty(min(total, self.cap), dtype=np.uint32)
-        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, hits.ctypes.data_as(C.c_void_p), self._own[1], hits.nbytes))
+        self.bvh.ctx.synchronize()
+        off = offsets_out if offsets_out is not None else np.empty(self.nrays_global + 1, dtype=np.uint32)
+        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, off.ctypes.data_as(C.c_void_p), self._own[3], 4 * (self.nrays_global + 1)))
+        total = int(off[self.nrays_global])
+        if total == 0xFFFFFFFF:
+            raise self.capi.BvhGpuError(self.capi.ERR_CAPACITY, "sharded traversal: the hit total overflows the u32 CSR offsets")
+        if total > self.cap:
+            raise self.capi.BvhGpuError(self.capi.ERR_CAPACITY, f"sharded traversal: {total} hits do not fit the global hit buffers (cap {self.cap})")
+        hits = hits_out[:total] if hits_out is not None else np.empty(total, dtype=np.uint32)
+        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, hits.ctypes.data_as(C.c_void_p), self._own[1], 4 * total))
         return off, hits
+
+    def trace(self):
+        """Per-step exchange trace of this rank (diagnostics): dict seq -> (ns waited for the peers' totals, ns waited for their
+        done flags).  Long waits on one rank mean ANOTHER rank was late; the rank that never waits is the straggler."""
+        np, C, L = self.np, self.C, self.capi.lib()
+        box = np.empty(self.capi.MAILBOX_BYTES // 8, dtype=np.uint64)
+        self.capi.check(L.bvhgpu_memcpy_d2h(self.bvh.ctx._h, box.ctypes.data_as(C.c_void_p), self._own[2], box.nbytes))
+        tr = box[self.capi.MB_TRACE_WORD: self.capi.MB_TRACE_WORD + 4 * self.capi.MB_TRACE_LEN].reshape(-1, 4)
+        return {int(r[0]): (int(r[2]), int(r[3])) for r in tr if r[0] != 0}
 
     def close(self):
         L, ctx = self.capi.lib(), self.bvh.ctx._h
-        self.bvh.ctx.synchronize()
-        dist.barrier()
+        try:
+            self.bvh.ctx.synchronize()
+        except self.capi.BvhGpuError:
+            pass
+        dist.barrier(group=self.group)
         for p in self._opened:
             L.bvhgpu_peer_close(ctx, p)
-        dist.barrier()
+        dist.barrier(group=self.group)
         for p in self._own:
             L.bvhgpu_peer_free(ctx, p)
         self._opened, self._own = [], []

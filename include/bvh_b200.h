@@ -80,6 +80,12 @@ typedef enum {
     BVHGPU_TRAVERSE_FLAT = 1    /* FlatBvh::traverse semantics (src/flat_bvh.rs:396-431): reached leaves re-test the shape AABB */
 } bvhgpu_traverse_mode;
 
+/* Ray batch layouts at the boundary.  FULL is the crate's Ray (bvh_ray3f / bvh_ray3d).  OD carries only what Ray::new keeps
+ * besides the reciprocal: 6 scalars per ray {origin[3], direction[3]} with `direction` exactly as Ray stores it (normalised);
+ * the device recomputes inv_direction = 1/direction with the same IEEE division Ray::new performs (src/ray/ray_impl.rs:76-78),
+ * so both layouts give bit-identical results -- OD moves 24 instead of 36 bytes per f32 ray across PCIe. */
+typedef enum { BVHGPU_RAYS_FULL = 0, BVHGPU_RAYS_OD = 1 } bvhgpu_ray_layout;
+
 typedef struct bvhgpu_ctx bvhgpu_ctx;       /* one per device: stream, scratch pool           */
 typedef struct bvhgpu_tree3f bvhgpu_tree3f; /* device-resident Bvh<f32,3> (+ FlatBvh, shape AABBs) */
 typedef struct bvhgpu_tree3d bvhgpu_tree3d; /* device-resident Bvh<f64,3>                      */
@@ -93,7 +99,13 @@ const char* bvhgpu_version(void);
  * stream and is honoured as such).  bvhgpu_reset_stream returns to the context's own stream. */
 int bvhgpu_set_stream(bvhgpu_ctx* ctx, void* cuda_stream);
 int bvhgpu_reset_stream(bvhgpu_ctx* ctx);
+/* Waits for the context's stream.  Also the point where errors of asynchronous multi-GPU steps surface: a peer that never
+ * answered (BVHGPU_ERR_TIMEOUT) is reported here, once, and the step's result must not be used. */
 int bvhgpu_synchronize(bvhgpu_ctx* ctx);
+/* Pinned host memory for ray / result staging, placed on the NUMA node the device hangs off (sysfs numa_node of the
+ * PCI function) -- on a two-socket host a buffer pinned on the far socket moves at a fraction of the PCIe rate. */
+int bvhgpu_host_alloc(bvhgpu_ctx* ctx, size_t bytes, void** out);
+int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
 /* Tunables: "traverse_slots" (per-ray hit slots of the single-pass path, 0 = two-pass count/fill, -1 = auto),
@@ -102,6 +114,8 @@ uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
  * "build_subtree" (exact builder: build ranges of <= 32 shapes in registers, one warp per subtree; -1 auto, 0 never, 1 always),
  * "build_gang" (exact builder: co-resident warp gangs walk the top levels behind device-wide barriers; -1 auto by size, 0 never, 1 always),
  * -- every combination produces the same bits; the switches exist for measurement (tools/build_sweep.py) --
+ * "traverse_stream" (host-pointer traversal: consume the rays in a running kernel while the copy is still in flight;
+ *   -1 auto = only when launches are asynchronous and no profiler / debugger / sanitizer is attached, 0 never, 1 force),
  * "profile" (1: bracket the dominant kernels with CUDA events, read back with bvhgpu_get_metric). */
 int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value);
 /* Measurements of the last profiled call on this context: "walk_ms" (traversal walk kernel),
@@ -157,31 +171,47 @@ int bvhgpu_traverse_f64x3(bvhgpu_tree3d* tree, int mode, const bvh_ray3d* rays, 
                           uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
 int bvhgpu_traverse_fetch_f32x3(bvhgpu_tree3f* tree, uint32_t* hits, size_t cap);
 int bvhgpu_traverse_fetch_f64x3(bvhgpu_tree3d* tree, uint32_t* hits, size_t cap);
+/* The same with the compact ray layout BVHGPU_RAYS_OD: `origin_dir` holds 6 scalars per ray. */
+int bvhgpu_traverse_od_f32x3(bvhgpu_tree3f* tree, int mode, const float* origin_dir, size_t nrays,
+                             uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_traverse_od_f64x3(bvhgpu_tree3d* tree, int mode, const double* origin_dir, size_t nrays,
+                             uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
 /* Device-resident variant: rays / offsets / hits are device pointers.  `total` may be NULL
  * (no host synchronisation); hits beyond `cap` are dropped and reported through *total. */
 int bvhgpu_traverse_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_rays, size_t nrays,
                               void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
 int bvhgpu_traverse_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_rays, size_t nrays,
                               void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+int bvhgpu_traverse_od_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_origin_dir, size_t nrays,
+                                 void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
+int bvhgpu_traverse_od_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_origin_dir, size_t nrays,
+                                 void* dev_offsets, void* dev_hits, size_t cap, size_t* total);
 /* ---- multi-GPU ray sharding with the exchange fused into the traversal (no NCCL on the data path) -------------
- * Every rank owns a contiguous shard of the ray batch and a replica of the tree.  The global CSR lives in
- * peer-mapped buffers (one copy per rank, allocated with bvhgpu_peer_alloc and opened on the other ranks through
- * CUDA IPC): after its local walk a rank publishes its hit total to all peers' mailboxes over NVLink, waits for
- * theirs, and its emit kernel then stores its rebased offsets and hit lists DIRECTLY into every rank's global
- * buffers (P2P stores) -- the all-gather of hit lists north_star asks for, overlapped tile by tile with the emit.
- * `seq` must increase by one per call on all ranks.  Mailbox size: BVHGPU_MAILBOX_BYTES. */
+ * Every rank owns a contiguous shard of the ray batch and a replica of the tree.  Every rank ends the step with its own
+ * copy of the GLOBAL CSR in original ray order -- the all-gather of hit lists north_star asks for -- built over peer
+ * memory (buffers allocated with bvhgpu_peer_alloc and opened on the other ranks through CUDA IPC):
+ *   1. after its local walk a rank stores its per-ray hit COUNTS, narrowed to 1 / 2 / 4 bytes by its largest count, into
+ *      every rank's count staging (16-byte P2P stores over NVLink) and then publishes {hit total, width} in all mailboxes;
+ *   2. it waits for the peers' posts, which fixes its hit base; every rank rebuilds the global u32 offsets from the
+ *      staged counts with a local scan (so 1 byte per ray crosses NVLink instead of 4);
+ *   3. its emit kernel stores its hit lists DIRECTLY into every rank's global hit buffer (P2P stores, tile by tile);
+ *   4. done flags: when the stream reaches the end of the step, this rank's copy of the global CSR is complete.
+ * `seq` must increase by one per call on all ranks.  No host synchronisation; failures (a peer that never answers)
+ * are reported by bvhgpu_synchronize.  Mailbox layout (trace words for diagnostics included): traverse.cu. */
 #define BVHGPU_MAX_PEERS 8
-#define BVHGPU_MAILBOX_BYTES 1024
+#define BVHGPU_MAILBOX_BYTES 65536
 #define BVHGPU_IPC_HANDLE_BYTES 64
+#define BVHGPU_SHARD_STAGE_BYTES(nrays_global) (4 * (size_t)(nrays_global) + 16 * BVHGPU_MAX_PEERS + 32)
 typedef struct {
     int rank, world;
-    void* peer_offsets[BVHGPU_MAX_PEERS];   /* u32[nrays_global + 1] on every rank (index = rank)          */
-    void* peer_hits[BVHGPU_MAX_PEERS];      /* u32[cap] on every rank                                      */
-    void* peer_mailbox[BVHGPU_MAX_PEERS];   /* BVHGPU_MAILBOX_BYTES on every rank, zero-initialised         */
-    uint64_t seq;                           /* 1, 2, 3, ... identical on all ranks for the same step        */
-    size_t rays_before;                     /* global index of this rank's first ray                        */
-    size_t nrays_global;
-    size_t cap;                             /* capacity of the global hit buffers                           */
+    void* peer_counts[BVHGPU_MAX_PEERS];    /* BVHGPU_SHARD_STAGE_BYTES(nrays_global) on every rank (index = rank)   */
+    void* peer_hits[BVHGPU_MAX_PEERS];      /* u32[cap] on every rank: the global hit lists                          */
+    void* peer_mailbox[BVHGPU_MAX_PEERS];   /* BVHGPU_MAILBOX_BYTES on every rank, zero-initialised                  */
+    void* offsets;                          /* LOCAL device memory, u32[nrays_global + 1]: the global CSR offsets     */
+    uint64_t seq;                           /* 1, 2, 3, ... identical on all ranks for the same step                 */
+    size_t shard_rays[BVHGPU_MAX_PEERS];    /* rays of every rank's shard (shard_rays[rank] == nrays of the call)     */
+    size_t cap;                             /* capacity of the global hit buffers                                    */
+    int ray_layout;                         /* bvhgpu_ray_layout of dev_rays                                         */
 } bvhgpu_shard;
 int bvhgpu_traverse_sharded_dev_f32x3(bvhgpu_tree3f* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard);
 int bvhgpu_traverse_sharded_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_rays, size_t nrays, const bvhgpu_shard* shard);
@@ -192,6 +222,8 @@ int bvhgpu_peer_close(bvhgpu_ctx* ctx, void* dev_ptr);
 int bvhgpu_peer_free(bvhgpu_ctx* ctx, void* dev_ptr);
 /* Synchronous device -> host copy on the context's stream (lets a binding read peer-allocated buffers). */
 int bvhgpu_memcpy_d2h(bvhgpu_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+/* Asynchronous host -> device copy on the context's stream (host memory should be pinned: bvhgpu_host_alloc). */
+int bvhgpu_memcpy_h2d_async(bvhgpu_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
 
 /* Counters of the last traversal on this tree: [0] node records visited, [1] hits. */
 int bvhgpu_traverse_stats_f32x3(bvhgpu_tree3f* tree, uint64_t* out2);
@@ -255,6 +287,10 @@ int bvhgpu_sah_cost_f64x3(bvhgpu_tree3d* tree, double* out2);
  * Bvh::update_shapes, src/bvh/optimization.rs:304-351 fix_aabbs_ascending).  Topology is kept. */
 int bvhgpu_refit_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n);
 int bvhgpu_refit_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n);
+/* The AABBs are already on the device (C-ABI layout): nothing is uploaded.  A NaN in the new AABBs is rejected
+ * (BVHGPU_ERR_NAN) before the tree is touched, in every refit / optimize / update variant. */
+int bvhgpu_refit_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_aabbs, size_t n);
+int bvhgpu_refit_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_aabbs, size_t n);
 
 /* ---- optimize: replaces Bvh::update_shapes after shapes moved (src/bvh/optimization.rs:290-302) ----
  * The reference removes and re-inserts every changed shape sequentially (remove_shape :208-288, add_shape :70-206).
@@ -268,6 +304,8 @@ int bvhgpu_refit_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n);
  * (assert_consistent, assert_tight), on hit sets, and on SAH cost against the oracle's update_shapes. */
 int bvhgpu_optimize_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n, double max_growth, size_t* rebuilt);
 int bvhgpu_optimize_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n, double max_growth, size_t* rebuilt);
+int bvhgpu_optimize_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt);
+int bvhgpu_optimize_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt);
 
 #ifdef __cplusplus
 }

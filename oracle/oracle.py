@@ -144,7 +144,9 @@ class TraverseResult:
 
 
 def traverse(tree: np.ndarray, shapes: np.ndarray, rays: np.ndarray, mode: int = MODE_FLAT, prec: str = "f32",
-             threads: int = 1) -> TraverseResult:
+             threads: int = 1, count_stats: bool = True) -> TraverseResult:
+    """threads > 1: persistent pinned worker pool, rays handed out in chunks (dynamic).  count_stats=False keeps the visit
+    counters out of the hot loop (the timed CPU legs of bench.py); `.seconds` is the wall time of the parallel section."""
     d = _DT[prec]
     tdt = d["flat"] if mode == MODE_FLAT else d["node"]
     tree = np.ascontiguousarray(tree, dtype=tdt)
@@ -152,12 +154,13 @@ def traverse(tree: np.ndarray, shapes: np.ndarray, rays: np.ndarray, mode: int =
     rays = np.ascontiguousarray(rays, dtype=d["ray"])
     nrays = len(rays)
     offsets = np.zeros(nrays + 1, dtype=np.uint64)
-    stats = np.zeros(5, dtype=np.uint64)
+    stats = np.zeros(6, dtype=np.uint64)
     ovf = C.c_int(0)
     cap = max(4 * nrays, 1024)
     fn = getattr(lib(), f"orc_traverse_batch_{prec}")
     while True:
         hits = np.empty(cap, dtype=np.uint32)
+        stats[5] = 0 if count_stats else 1
         total = fn(C.c_int(mode), _p(tree), C.c_uint32(len(tree)), _p(shapes), _p(rays), C.c_uint64(nrays),
                    _p(offsets), _p(hits), C.c_uint64(cap), _p(stats), C.c_uint32(threads), C.byref(ovf))
         if total <= cap:

@@ -6,65 +6,143 @@
 #include "bvh_oracle.hpp"
 #include <cstring>
 #include <chrono>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <pthread.h>
+#include <sched.h>
 
 using namespace orc;
 
 namespace {
+
+// ---- persistent worker pool for the timed CPU legs (bench.py --impl reference / cpu_baseline) ------------------------------
+// Threads are created once, pinned round-robin to the CPUs the process may use, and woken per batch; rays are handed out in
+// chunks from an atomic counter (dynamic scheduling: the batch's expensive rays are not evenly spread).  Creating ~100 fresh
+// threads per call and splitting the batch statically made the measured CPU rate swing by 3-4x between otherwise equal hosts.
+class Pool {
+  public:
+    static Pool& get() { static Pool p; return p; }
+    unsigned size() const { return (unsigned)workers_.size(); }
+    // runs fn(worker) on workers [0, nthreads) and returns when all are done
+    void run(unsigned nthreads, const std::function<void(unsigned)>& fn) {
+        nthreads = std::max(1u, std::min(nthreads, size()));
+        std::unique_lock<std::mutex> lk(m_);
+        fn_ = &fn; active_ = nthreads; pending_ = nthreads; ++gen_;
+        cv_.notify_all();
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+  private:
+    Pool() {
+        std::vector<int> cpus;
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0)
+            for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) cpus.push_back(c);
+        unsigned n = std::max(1u, std::thread::hardware_concurrency());
+        if (!cpus.empty()) n = std::min<unsigned>(n, (unsigned)cpus.size());
+        for (unsigned t = 0; t < n; ++t) {
+            workers_.emplace_back([this, t] { loop(t); });
+            if (!cpus.empty()) {
+                cpu_set_t one;
+                CPU_ZERO(&one);
+                CPU_SET(cpus[t % cpus.size()], &one);
+                pthread_setaffinity_np(workers_.back().native_handle(), sizeof one, &one);
+            }
+        }
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    void loop(unsigned t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(unsigned)>* fn = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                if (t < active_) fn = fn_;
+            }
+            if (fn) {
+                (*fn)(t);
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned)>* fn_ = nullptr;
+    unsigned active_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
 
 template <class T>
 uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3<T>* shapes,
                         const Ray3<T>* rays, uint64_t nrays, uint64_t* offsets, uint32_t* hits, uint64_t cap,
                         uint64_t* stats, unsigned threads, int* overflow32) {
     // mode 0: Bvh::traverse (recursive)   1: FlatBvh::traverse   2: BvhTraverseIterator
+    // stats == nullptr: no visit counters in the hot loop (the timed legs); stats != nullptr: counters + wall time in stats[4].
     if (threads < 1) threads = 1;
-    if ((uint64_t)threads > nrays) threads = nrays ? (unsigned)nrays : 1;
-    std::vector<std::vector<uint32_t>> lists(threads);
-    std::vector<std::vector<uint64_t>> counts(threads);
-    std::vector<TraverseStats> tst(threads);
-    std::vector<int> ok(threads, 1);
+    const uint64_t CHUNK = 2048;
+    const uint64_t nchunks = (nrays + CHUNK - 1) / CHUNK;
+    std::vector<std::vector<uint32_t>> lists(nchunks);
+    std::vector<std::vector<uint32_t>> counts(nchunks);
+    std::vector<TraverseStats> tst(std::max(1u, threads));
+    std::vector<int> ok(std::max(1u, threads), 1);
+    std::atomic<uint64_t> next{0};
+    const bool want_stats = stats != nullptr && stats[5] == 0;      // stats[5] != 0 on entry: time only, no counters
     auto work = [&](unsigned t) {
-        const uint64_t lo = nrays * t / threads, hi = nrays * (t + 1) / threads;
-        std::vector<uint32_t> out, mine;
-        std::vector<uint64_t> cnt;
+        std::vector<uint32_t> out;
         TraverseStats ls;                        // thread-local: no false sharing in the hot loop
+        TraverseStats* lsp = want_stats ? &ls : nullptr;
         int lok = 1;
-        cnt.reserve(hi - lo);
-        for (uint64_t r = lo; r < hi; ++r) {
-            out.clear();
-            if (mode == 0) traverse_recursive((const Node<T>*)tree, n_tree, shapes, rays[r], out, &ls);
-            else if (mode == 1) traverse_flat((const FlatNode<T>*)tree, n_tree, shapes, rays[r], out, &ls);
-            else if (!traverse_iterator((const Node<T>*)tree, n_tree, shapes, rays[r], out)) lok = 0;
-            cnt.push_back(out.size());
-            mine.insert(mine.end(), out.begin(), out.end());
+        for (;;) {
+            const uint64_t c = next.fetch_add(1, std::memory_order_relaxed);
+            if (c >= nchunks) break;
+            const uint64_t lo = c * CHUNK, hi = std::min(nrays, lo + CHUNK);
+            std::vector<uint32_t>& mine = lists[c];
+            std::vector<uint32_t>& cnt = counts[c];
+            cnt.reserve(hi - lo);
+            for (uint64_t r = lo; r < hi; ++r) {
+                out.clear();
+                if (mode == 0) traverse_recursive((const Node<T>*)tree, n_tree, shapes, rays[r], out, lsp);
+                else if (mode == 1) traverse_flat((const FlatNode<T>*)tree, n_tree, shapes, rays[r], out, lsp);
+                else if (!traverse_iterator((const Node<T>*)tree, n_tree, shapes, rays[r], out)) lok = 0;
+                cnt.push_back((uint32_t)out.size());
+                mine.insert(mine.end(), out.begin(), out.end());
+            }
         }
-        counts[t].swap(cnt);
-        lists[t].swap(mine);
         tst[t] = ls;
         ok[t] = lok;
     };
     const auto tic = std::chrono::steady_clock::now();
     if (threads == 1) work(0);
-    else {
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < threads; ++t) pool.emplace_back(work, t);
-        for (auto& th : pool) th.join();
-    }
+    else Pool::get().run(threads, work);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count();
     uint64_t total = 0, r = 0;
-    for (unsigned t = 0; t < threads; ++t) {
-        for (uint64_t c : counts[t]) { if (offsets) offsets[r] = total; total += c; ++r; }
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        for (uint32_t k : counts[c]) { if (offsets) offsets[r] = total; total += k; ++r; }
     }
     if (offsets) offsets[nrays] = total;
     if (hits) {
         uint64_t w = 0;
-        for (unsigned t = 0; t < threads; ++t) {
-            for (uint32_t h : lists[t]) { if (w < cap) hits[w] = h; ++w; }
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            for (uint32_t h : lists[c]) { if (w < cap) hits[w] = h; ++w; }
         }
     }
     if (stats) {
         stats[0] = stats[1] = stats[2] = stats[3] = 0;
         for (auto& s : tst) { stats[0] += s.node_visits; stats[1] += s.slab_tests; stats[2] += s.leaf_visits; stats[3] += s.hits; }
-        stats[4] = (uint64_t)(secs * 1e9);          // wall time of the traversal section (thread create .. join), ns
+        stats[4] = (uint64_t)(secs * 1e9);          // wall time of the traversal section (dispatch .. all workers done), ns
     }
     if (overflow32) { *overflow32 = 0; for (int o : ok) if (!o) *overflow32 = 1; }
     return total;
@@ -202,6 +280,7 @@ DEFINE_FOR(double, f64)
 ORC_API uint64_t orc_last_build_ns() { return g_last_build_ns; }
 ORC_API uint64_t orc_splitmix64(uint64_t* seed) { return splitmix64(*seed); }
 ORC_API uint32_t orc_hardware_threads() { return std::thread::hardware_concurrency(); }
+ORC_API uint32_t orc_pool_threads() { return Pool::get().size(); }
 ORC_API uint32_t orc_sizeof(int what) {
     switch (what) {
         case 0: return sizeof(Aabb3<float>);

@@ -1,0 +1,242 @@
+"""GPU tests added in round 2: compact ray layout, tool-safe host traversal, sticky build failures, NaN handling of the
+update entry points, device-resident refit / optimize, the fused multi-GPU exchange on whatever GPUs the box has.
+Run on the B200 box:  python -m pytest tests -m gpu"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.scenes import rays_for, scene
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from bvh_b200 import api as A
+
+    return A
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["boxes21", "cubes1000", "random5000", "huge300"])
+def test_compact_ray_layout_is_bit_identical(api, name, prec):
+    """BVHGPU_RAYS_OD (origin + direction, inv_direction recomputed on the device) == the full Ray layout == the oracle,
+    incl. axis-aligned rays (zero direction components: inv = +-inf, NaN rule of the slab test)."""
+    from bvh_b200 import capi
+
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    rays = rays_for(shapes, 3000, prec, seed=11, axis_aligned=400)
+    for mode, omode in ((capi.TRAVERSE_BVH, O.MODE_RECURSIVE), (capi.TRAVERSE_FLAT, O.MODE_FLAT)):
+        tree = want.nodes if omode == O.MODE_RECURSIVE else O.flatten(want.nodes, prec)
+        r = O.traverse(tree, shapes, rays, omode, prec)
+        for compact in (False, True):
+            off, hits = bvh.traverse_batch(rays, mode=mode, compact=compact)
+            assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits), (mode, compact)
+    bvh.free()
+
+
+def test_compact_layout_device_pointers_and_large_batch(api):
+    """The device-pointer OD entry point and the streamed host path (>= 2 chunks) on 300 k rays."""
+    import torch
+
+    from bvh_b200 import capi
+
+    shapes = O.create_n_cubes(2000)
+    want = O.build(shapes)
+    rays, _ = O.create_rays(300_000)
+    r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, threads=O.hardware_threads())
+    bvh = api.Bvh.build(shapes)
+    for stream_opt in (-1, 0, 1):                       # auto / plain copy-then-walk / forced streaming
+        bvh.ctx.set_option("traverse_stream", stream_opt)
+        for compact in (False, True):
+            off, hits = bvh.traverse_batch(rays, compact=compact)
+            assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits), (stream_opt, compact)
+    bvh.ctx.set_option("traverse_stream", -1)
+    dev = torch.device("cuda", 0)
+    od = np.empty((len(rays), 6), dtype=np.float32)
+    od[:, :3], od[:, 3:] = rays["origin"], rays["direction"]
+    d_od = torch.from_numpy(od.reshape(-1)).to(dev)
+    d_off = torch.empty(len(rays) + 1, dtype=torch.int32, device=dev)
+    d_hits = torch.empty(4 * len(rays), dtype=torch.int32, device=dev)
+    tot = C.c_size_t(0)
+    torch.cuda.synchronize(dev)
+    capi.check(capi.lib().bvhgpu_traverse_od_dev_f32x3(bvh._h, 0, C.c_void_p(d_od.data_ptr()), len(rays), C.c_void_p(d_off.data_ptr()),
+                                                       C.c_void_p(d_hits.data_ptr()), d_hits.numel(), C.byref(tot)))
+    bvh.ctx.synchronize()
+    assert tot.value == len(r.hits)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint32).astype(np.uint64), r.offsets)
+    assert np.array_equal(d_hits[: tot.value].cpu().numpy().view(np.uint32), r.hits)
+    bvh.free()
+
+
+_BLOCKING_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from oracle import oracle as O
+from bvh_b200 import api
+shapes = O.create_n_cubes(2000)
+rays, _ = O.create_rays(300_000)
+bvh = api.Bvh.build(shapes)
+off, hits = bvh.traverse_batch(rays)
+off2, hits2 = bvh.traverse_batch(rays, compact=True)
+want = O.build(shapes)
+r = O.traverse(want.nodes, shapes, rays, O.MODE_RECURSIVE, threads=8)
+ok = np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits) and np.array_equal(off, off2) and np.array_equal(hits, hits2)
+print("BLOCKING_OK" if ok else "BLOCKING_MISMATCH", len(hits))
+"""
+
+
+def test_host_traversal_survives_serialised_launches():
+    """CUDA_LAUNCH_BLOCKING=1 makes every launch wait for the kernel: a walk kernel that waited for copies the host had yet to enqueue
+    would never return (round 1: the driver's ncu pass hung for 900 s).  The host path must take the plain form here and finish."""
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    r = subprocess.run([sys.executable, "-c", _BLOCKING_SCRIPT % ROOT], capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "BLOCKING_OK" in r.stdout
+
+
+def test_host_traversal_under_ncu_lists_the_traversal_kernels():
+    """`ncu python -c smoke()` must finish in seconds and list the walk / scan / emit kernels (what the driver records)."""
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        pytest.skip("ncu not installed")
+    cmd = [ncu, "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "-c", "200", "--csv",
+           sys.executable, "-c", "import sys; sys.path.insert(0, %r); import __graft_entry__ as g; g.smoke()" % ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if "ERR_NVGPUCTRPERM" in r.stdout + r.stderr or "permission" in (r.stdout + r.stderr).lower():
+        pytest.skip("no permission for GPU performance counters on this box")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "smoke ok" in r.stdout
+    for k in ("walk_", "scan_local_kernel", "scan_blocks_kernel", "emit_kernel"):
+        assert k in r.stdout, k
+
+
+def test_failed_build_is_sticky(api):
+    """bvhgpu_build_dev_* defers the status: the first call on the tree reports the NaN, and so does EVERY later call (the node arrays
+    were never written); nothing may walk them."""
+    import torch
+
+    from bvh_b200 import capi
+
+    shapes = scene("random1000").copy()
+    shapes["min"][77][0] = np.nan
+    dev = torch.device("cuda", 0)
+    d = torch.from_numpy(shapes.view(np.uint8).reshape(-1)).to(dev)
+    torch.cuda.synchronize(dev)
+    for mode in (capi.BUILD_EXACT_SAH, capi.BUILD_LBVH, capi.BUILD_LBVH_TREELET):
+        bvh = api.Bvh.build_dev(d.data_ptr(), len(shapes), mode=mode)          # no error yet
+        rays = rays_for(scene("random1000"), 100, seed=3)
+        for attempt in range(3):
+            with pytest.raises(capi.BvhGpuError) as e:
+                bvh.traverse_batch(rays)
+            assert e.value.status == capi.ERR_NAN, (mode, attempt)
+        with pytest.raises(capi.BvhGpuError):
+            bvh.flatten()
+        with pytest.raises(capi.BvhGpuError):
+            bvh.nodes
+        bvh.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["exact", "lbvh", "lbvh_treelet"])
+def test_nan_in_x_is_rejected_by_every_builder(api, mode):
+    from bvh_b200 import capi
+
+    shapes = scene("random3000").copy()
+    shapes["max"][1234][0] = np.nan                      # the split axis of the root of this scene is x
+    with pytest.raises(capi.BvhGpuError) as e:
+        api.Bvh.build(shapes, mode=mode)
+    assert e.value.status == capi.ERR_NAN
+
+
+@pytest.mark.parametrize("what", ["refit", "optimize"])
+def test_nan_update_leaves_the_tree_untouched(api, what):
+    """A NaN in the new AABBs is refused BEFORE anything is overwritten: same nodes, still traversable (the reference would have
+    panicked inside update_shapes with a half-modified Bvh)."""
+    from bvh_b200 import capi
+
+    shapes = scene("cubes1000").copy()
+    bvh = api.Bvh.build(shapes)
+    before = bvh.nodes.copy()
+    bad = shapes.copy()
+    bad["min"][5000][0] = np.nan
+    with pytest.raises(capi.BvhGpuError) as e:
+        bvh.refit(bad) if what == "refit" else bvh.optimize(bad)
+    assert e.value.status == capi.ERR_NAN
+    after = bvh.nodes
+    assert np.array_equal(before.view(np.uint8), after.view(np.uint8))
+    rays = rays_for(shapes, 500, seed=5)
+    r = O.traverse(before, shapes, rays, O.MODE_RECURSIVE)
+    off, hits = bvh.traverse_batch(rays)
+    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits)
+    bvh.free()
+
+
+def test_device_resident_refit_and_optimize(api):
+    """bvhgpu_refit_dev_* / bvhgpu_optimize_dev_*: the new AABBs are already on the device (no upload) -- same result as the host forms."""
+    import torch
+
+    from bvh_b200 import capi
+
+    shapes = scene("cubes1000").copy()
+    rng = np.random.default_rng(21)
+    moved = rng.choice(len(shapes), 600, replace=False)
+    delta = rng.uniform(-3000, 3000, (600, 3)).astype(np.float32)
+    new = shapes.copy()
+    new["min"][moved] += delta
+    new["max"][moved] += delta
+    dev = torch.device("cuda", 0)
+    d_new = torch.from_numpy(new.view(np.uint8).reshape(-1)).to(dev)
+    torch.cuda.synchronize(dev)
+    L = capi.lib()
+    a, b = api.Bvh.build(shapes), api.Bvh.build(shapes)
+    a.refit(new)
+    capi.check(L.bvhgpu_refit_dev_f32x3(b._h, C.c_void_p(d_new.data_ptr()), len(new)))
+    b._nodes = None
+    assert np.array_equal(a.nodes.view(np.uint8), b.nodes.view(np.uint8))
+    a2, b2 = api.Bvh.build(shapes), api.Bvh.build(shapes)
+    ra = a2.optimize(new)
+    rb = C.c_size_t(0)
+    capi.check(L.bvhgpu_optimize_dev_f32x3(b2._h, C.c_void_p(d_new.data_ptr()), len(new), C.c_double(1.5), C.byref(rb)))
+    b2._nodes = None
+    assert ra == rb.value and ra > 0
+    assert np.array_equal(a2.nodes.view(np.uint8), b2.nodes.view(np.uint8))
+    assert O.is_consistent(b2.nodes, new) and O.is_tight(b2.nodes)
+    for t in (a, b, a2, b2):
+        t.free()
+
+
+def test_pinned_numa_local_host_buffers(api):
+    ctx = api.Context.default()
+    arr = ctx.host_alloc(1 << 20, np.uint32)
+    arr[:] = np.arange(len(arr), dtype=np.uint32)
+    assert int(arr[12345]) == 12345
+    ctx.host_free(arr)
+
+
+@pytest.mark.parametrize("nproc", [1, 2])
+def test_fused_multi_gpu_exchange(nproc):
+    """tools/check_sharded.py under torchrun: the fused sharded traversal (counts pushed in 1 / 2 / 4-byte width, offsets rebuilt by
+    the local scan, hit lists stored into every rank's buffer) == the NCCL all-gather path == the oracle, with uneven shards and with
+    rays that have > 65 535 hits on one rank only.  nproc = 1 runs the whole exchange machinery on a single-GPU box."""
+    import torch
+
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs >= {nproc} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+                        "--master-port", str(29533 + nproc), os.path.join(ROOT, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("fused==nccl True  fused==oracle True") == 2 * nproc
