@@ -182,10 +182,10 @@ template <class T> static int flatten_impl(Tree<T>* tree, typename Traits<T>::Fl
     if (!tree) { set_error("flatten: null tree"); return BVHGPU_ERR_INVALID; }
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (out || tree->failed_status != BVHGPU_OK) BVH_TRY(resolve_status(tree));   // never map a node array whose build failed
     BVH_TRY(build_flat(tree));
     if (len) *len = tree->n_flat;
     if (out) {
-        BVH_TRY(resolve_status(tree));
         if (cap < tree->n_flat) { set_error("flatten: capacity %zu < %zu flat nodes", cap, tree->n_flat); return BVHGPU_ERR_CAPACITY; }
         if (tree->n_flat) {
             BVH_CUDA_TRY(cudaMemcpyAsync(out, tree->d_flat, sizeof(*out) * tree->n_flat, cudaMemcpyDeviceToHost, ctx->stream));
@@ -554,6 +554,9 @@ BVH_EXPORT int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t valu
 BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out) {
     if (!ctx || !name || !out) { set_error("get_metric: null argument"); return BVHGPU_ERR_INVALID; }
     cudaEvent_t* ev = nullptr;
+    if (!strncmp(name, "e2e_host_us_", 12) && name[12] >= '0' && name[12] <= '7' && !name[13]) { *out = ctx->host_us[name[12] - '0']; return BVHGPU_OK; }
+    if (!strcmp(name, "host_streamed")) { *out = (double)ctx->last_streamed; return BVHGPU_OK; }
+    if (!strcmp(name, "numa_node")) { *out = (double)ctx->numa_node; return BVHGPU_OK; }
     if (!strcmp(name, "walk_ms") && ctx->have_walk) ev = ctx->ev_walk;
     else if (!strcmp(name, "build_ms") && ctx->have_build) ev = ctx->ev_build;
     if (!ev && ctx->have_e2e && !strncmp(name, "e2e_", 4)) {      // e2e_walk_ms / e2e_h2d_ms / e2e_emit_ms / e2e_d2h_ms: since call start

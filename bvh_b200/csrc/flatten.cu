@@ -13,10 +13,11 @@ namespace bvhb200 {
 template <class T>
 __global__ void __launch_bounds__(256) flat_kernel(const typename Traits<T>::Node* __restrict__ nodes,
                                                    const uint32_t* __restrict__ node_start, uint32_t n_nodes,
-                                                   typename Traits<T>::Flat* __restrict__ flat) {
+                                                   typename Traits<T>::Flat* __restrict__ flat, const BuildStatus* __restrict__ status) {
     using Tr = Traits<T>;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
+    if (status->error | status->nan_found) return;      // the (asynchronous) build failed: the node array is garbage, map nothing
     const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);      // parent, child_l, child_r, shape/count
     const bool leaf = meta.y == BVH_INVALID;
     if (i == 0) {
@@ -53,10 +54,11 @@ __global__ void __launch_bounds__(256) flat_kernel(const typename Traits<T>::Nod
 template <class T>
 __global__ void __launch_bounds__(256) trec_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes,
                                                    const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                   typename Traits<T>::TNode* __restrict__ trec) {
+                                                   typename Traits<T>::TNode* __restrict__ trec, const BuildStatus* __restrict__ status) {
     using Tr = Traits<T>;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
+    if (status->error | status->nan_found) return;
     typename Tr::TNode r;
     if (n_nodes == 1) {                       // root leaf: the shape's own AABB is tested (bvh_node.rs:314)
         T mn[3], mx[3];
@@ -89,7 +91,7 @@ template <class T> int build_traversal_records(Tree<T>* tree) {
     const uint32_t n_trec = tree->n == 1 ? 1u : tree->n_nodes - 1;
     if (!tree->d_tnodes) BVH_TRY(dalloc_t(ctx, &tree->d_tnodes, n_trec));
     tree->n_trec = n_trec;
-    trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->d_aabb, tree->d_tnodes);
+    trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->d_aabb, tree->d_tnodes, tree->d_status);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
     return BVHGPU_OK;
@@ -101,7 +103,7 @@ template <class T> int build_flat(Tree<T>* tree) {
     tree->have_flat = true;
     if (tree->n == 0) return BVHGPU_OK;
     if (!tree->d_flat) BVH_TRY(dalloc_t(ctx, &tree->d_flat, tree->n_flat));
-    flat_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_start, tree->n_nodes, tree->d_flat);
+    flat_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_start, tree->n_nodes, tree->d_flat, tree->d_status);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
     return BVHGPU_OK;

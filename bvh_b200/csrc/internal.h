@@ -62,6 +62,9 @@ struct bvhgpu_ctx {
     // host-pointer traversal, streaming form (rays consumed by a running kernel while they arrive): only when a kernel launch
     // does not block the host and no tool serialises / replays launches.  -1 = not probed yet, 0 = never stream, 1 = ok.
     int stream_ok = -1;
+    double host_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // profile: host-side time stamps of the last host-pointer traversal (us since entry)
+    uint64_t slot_budget_words = 0; // traversal slot scratch budget (a quarter of the memory that was free at first use, in 4-byte words / 4)
+    int last_streamed = -1;        // did the last host-pointer traversal stream (1) or copy-then-walk (0)
     int64_t traverse_stream = -1;  // option "traverse_stream": -1 auto (probe), 0 never, 1 force
     int64_t traverse_top = -1;     // option "traverse_top": shared-memory top-of-tree walk: -1 auto, 0 off, 1 on
     uint32_t* d_async_err = nullptr;   // sticky device-side error word of asynchronous calls (sharded exchange): surfaced by bvhgpu_synchronize

@@ -96,7 +96,7 @@ class ShardedTraversal:
         L, ctx = capi.lib(), bvh.ctx._h
         self._own, handles = [], []
         # peer-mapped: count staging, global hit lists, mailbox; local only: the global offsets
-        for nbytes in (capi.shard_stage_bytes(self.nrays_global), 4 * self.cap, capi.MAILBOX_BYTES, 4 * (self.nrays_global + 1)):
+        for nbytes in (2 * capi.shard_stage_bytes(self.nrays_global), 4 * self.cap, capi.MAILBOX_BYTES, 4 * (self.nrays_global + 1)):
             ptr, h = C.c_void_p(), (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
             capi.check(L.bvhgpu_peer_alloc(ctx, nbytes, C.byref(ptr), h))
             self._own.append(ptr)

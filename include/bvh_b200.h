@@ -194,17 +194,19 @@ int bvhgpu_traverse_od_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_
  *      every rank's count staging (16-byte P2P stores over NVLink) and then publishes {hit total, width} in all mailboxes;
  *   2. it waits for the peers' posts, which fixes its hit base; every rank rebuilds the global u32 offsets from the
  *      staged counts with a local scan (so 1 byte per ray crosses NVLink instead of 4);
- *   3. its emit kernel stores its hit lists DIRECTLY into every rank's global hit buffer (P2P stores, tile by tile);
+ *   3. its emit kernel writes its hit lists into its own copy of the global hit buffer, and a push kernel stores that
+ *      segment into every peer's copy with whole 16-byte P2P stores (4-byte stores scattered by the emit itself reached a
+ *      small fraction of the NVLink rate: measured 12.9 ms per 16 M-ray Sponza step on 4 GPUs);
  *   4. done flags: when the stream reaches the end of the step, this rank's copy of the global CSR is complete.
  * `seq` must increase by one per call on all ranks.  No host synchronisation; failures (a peer that never answers)
  * are reported by bvhgpu_synchronize.  Mailbox layout (trace words for diagnostics included): traverse.cu. */
 #define BVHGPU_MAX_PEERS 8
 #define BVHGPU_MAILBOX_BYTES 65536
 #define BVHGPU_IPC_HANDLE_BYTES 64
-#define BVHGPU_SHARD_STAGE_BYTES(nrays_global) (4 * (size_t)(nrays_global) + 16 * BVHGPU_MAX_PEERS + 32)
+#define BVHGPU_SHARD_STAGE_BYTES(nrays_global) ((4 * (size_t)(nrays_global) + 16 * BVHGPU_MAX_PEERS + 32 + 255) & ~(size_t)255)
 typedef struct {
     int rank, world;
-    void* peer_counts[BVHGPU_MAX_PEERS];    /* BVHGPU_SHARD_STAGE_BYTES(nrays_global) on every rank (index = rank)   */
+    void* peer_counts[BVHGPU_MAX_PEERS];    /* 2 * BVHGPU_SHARD_STAGE_BYTES(nrays_global) on every rank (index = rank): two halves, alternating per step */
     void* peer_hits[BVHGPU_MAX_PEERS];      /* u32[cap] on every rank: the global hit lists                          */
     void* peer_mailbox[BVHGPU_MAX_PEERS];   /* BVHGPU_MAILBOX_BYTES on every rank, zero-initialised                  */
     void* offsets;                          /* LOCAL device memory, u32[nrays_global + 1]: the global CSR offsets     */

@@ -128,17 +128,21 @@ uint64_t traverse_batch(int mode, const void* tree, uint32_t n_tree, const Aabb3
     if (threads == 1) work(0);
     else Pool::get().run(threads, work);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - tic).count();
-    uint64_t total = 0, r = 0;
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        for (uint32_t k : counts[c]) { if (offsets) offsets[r] = total; total += k; ++r; }
-    }
-    if (offsets) offsets[nrays] = total;
-    if (hits) {
-        uint64_t w = 0;
-        for (uint64_t c = 0; c < nchunks; ++c) {
-            for (uint32_t h : lists[c]) { if (w < cap) hits[w] = h; ++w; }
+    // assembly into one CSR: chunk bases serially (a few hundred), then every chunk's offsets / hits in parallel
+    std::vector<uint64_t> base(nchunks + 1, 0);
+    for (uint64_t c = 0; c < nchunks; ++c) base[c + 1] = base[c] + lists[c].size();
+    const uint64_t total = base[nchunks];
+    std::atomic<uint64_t> next2{0};
+    auto assemble = [&](unsigned) {
+        for (;;) {
+            const uint64_t c = next2.fetch_add(1, std::memory_order_relaxed);
+            if (c >= nchunks) break;
+            if (offsets) { uint64_t run = base[c], r = c * CHUNK; for (uint32_t k : counts[c]) { offsets[r++] = run; run += k; } }
+            if (hits) { uint64_t w = base[c]; for (uint32_t h : lists[c]) { if (w < cap) hits[w] = h; ++w; } }
         }
-    }
+    };
+    if (threads == 1) assemble(0); else Pool::get().run(threads, assemble);
+    if (offsets) offsets[nrays] = total;
     if (stats) {
         stats[0] = stats[1] = stats[2] = stats[3] = 0;
         for (auto& s : tst) { stats[0] += s.node_visits; stats[1] += s.slab_tests; stats[2] += s.leaf_visits; stats[3] += s.hits; }
