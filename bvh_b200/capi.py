@@ -23,7 +23,7 @@ MB_TRACE_WORD, MB_TRACE_LEN = 128, 1024          # mailbox trace ring (u64 words
 
 def shard_stage_bytes(nrays_global: int) -> int:
     """BVHGPU_SHARD_STAGE_BYTES"""
-    return (4 * nrays_global + 16 * MAX_PEERS + 32 + 255) & ~255
+    return (8200 * (nrays_global // 2048 + 2 * MAX_PEERS) + 255) & ~255
 
 
 class Shard(C.Structure):

@@ -353,33 +353,26 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
     if (threadIdx.x == 0) *total = carry_s;
 }
 
-// Destinations of the emit pass.  Single GPU: one destination (the caller's buffers), bases 0.  Sharded: the hit lists go
-// to every rank's peer-mapped global hit buffer at *hit_base + the local offset (known after the totals exchange); the
-// offsets are NOT shipped -- every rank rebuilds them from the narrow per-ray counts it received (gscan kernels).
-struct EmitDst {
-    int world;
-    uint32_t* offsets;                       // single GPU: the caller's offsets; sharded: nullptr
-    uint32_t* hits[BVHGPU_MAX_PEERS];
-    const unsigned long long* hit_base;      // nullptr = 0
-    const uint32_t* err;                     // sharded: sticky error word; a failed exchange skips the emit
-    unsigned long long nrays_out;            // single GPU: index of the closing offsets entry
-};
-
 // ---- exchange over peer memory (multi-GPU ray sharding) -------------------------------------------------------------------
+// Every rank ends the step with its own copy of the GLOBAL CSR (offsets u32[NG+1], hit lists) in original ray order.
 // Mailbox (u64 words; BVHGPU_MAILBOX_BYTES per rank, zero-initialised):
-//   [ (par*8 + src)*4 + {0,1,2,3} ]  = {seq, hit total, count width in bytes, largest count} published by rank `src`
+//   [ (par*8 + src)*4 + {0,1} ]      = {seq, hit total} published by rank `src`
 //   [ 64 + par*8 + src ]             = seq of the step whose hit lists of rank `src` have landed ("done")
-//   [ 128 + (seq % 1024)*4 + {0..3} ] = trace of this rank: {seq, %globaltimer at the start of the totals wait, ns waited for
-//                                       the peers' totals, ns waited for the peers' done flags}   (diagnostics, bench.py)
-// Count staging (2 x BVHGPU_SHARD_STAGE_BYTES per rank, the halves alternate with the parity of seq): segment of source rank s
-// at byte seg_off(s); rank s stores its per-ray hit counts there in ITS narrowest width (1, 2 or 4 bytes, from its largest
-// count) -- 1 byte per ray on ordinary batches instead of the 4-byte offsets the first version replicated to every rank.
-// Step = 4 kernels after the local walk + scan_local:
-//   xchg_post   block 0 scans the block sums (local total), all blocks push the narrowed counts, the last one publishes the total
-//   gscan<0>    every block waits for all peers' posts (spinning on LOCAL memory), then sums its tile of the staged counts
-//   emit        hit lists into the LOCAL copy of the global hit buffer at hit_base + local offset
-//   xchg_push   bulk copy of this rank's hit segment into every peer's buffer (16-byte P2P stores); last block: done flags out
-//   gscan<1>    global u32 offsets (tile base = sum of the tile sums before it); block 0 finally waits for the peers' done flags
+//   [ 128 + (seq % 1024)*4 + {0..3} ] = trace of this rank: {seq, %globaltimer when the peers' posts were all in, ns waited for
+//                                       the posts, ns waited for the done flags}   (diagnostics, bench.py)
+// Staging (2 x BVHGPU_SHARD_STAGE_BYTES per rank, the halves alternate with the parity of seq).  Rays are handled in TILES of
+// SCAN_TILE = 2048 (per source rank, counted from its first ray); a tile of source s with tile index t has the global tile
+// number g = tiles_before[s] + t.
+//   counts of tile g : 8192 bytes at 8192*g -- the per-ray hit counts in the tile's own width (1, 2 or 4 bytes, from the tile's
+//                      largest count): 1 byte per ray crosses NVLink on ordinary batches, not a 4-byte offset
+//   table entry g    : u64 at table_off + 8*g = exclusive hit offset of the tile inside its source's list | width << 56
+// The step is the SAME number of kernels as on one GPU (after the walk: scan_post, emit, + goffsets):
+//   scan_post  per tile: local scan, counts pushed to all ranks; the last block scans the tile sums, pushes the tile table and
+//              publishes the total (a peer that sees the seq also sees counts and table)
+//   emit       every block first waits for all posts (LOCAL polling) -> hit base; hit lists into the local copy of the global
+//              hit buffer, then the block copies its contiguous piece to every peer (16-byte P2P stores); last block: done flags
+//   goffsets   per tile of every source: offsets = hit base of the source + tile offset + prefix of the staged counts;
+//              block 0 ends the step by waiting for the peers' done flags
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -389,187 +382,213 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 constexpr int MB_TOT = 0, MB_DONE = 64, MB_TRACE = 128, MB_TRACE_LEN = 1024;
+constexpr unsigned long long TILE_BYTES = 4ull * SCAN_TILE;
+constexpr unsigned long long OFF_MASK = (1ull << 56) - 1ull;
 struct PeerBoxes {
-    int rank, world;
+    int rank, world;                                   // world == 0: single GPU, nothing below is used
     unsigned long long* box[BVHGPU_MAX_PEERS];
-    unsigned char* stage[BVHGPU_MAX_PEERS];            // count staging of every rank (the half of this step's parity)
+    unsigned char* stage[BVHGPU_MAX_PEERS];            // staging of every rank (the half of this step's parity)
     uint32_t* hits[BVHGPU_MAX_PEERS];                  // global hit buffer of every rank
     unsigned long long seq;
-    unsigned long long rays_before[BVHGPU_MAX_PEERS + 1];   // prefix sums of the shard sizes
+    unsigned long long rays_before[BVHGPU_MAX_PEERS + 1];    // prefix sums of the shard sizes
+    unsigned long long tiles_before[BVHGPU_MAX_PEERS + 1];   // prefix sums of ceil(shard size / SCAN_TILE)
+    unsigned long long table_off;                            // byte offset of the tile table inside a staging half
+    uint32_t* err;                                           // sticky error word of the context
+    unsigned long long timeout_ns;
 };
-// xinfo (u64 words): [0] hit base of this rank, [1] grand total, [2+s] count width of rank s.
-__device__ __forceinline__ unsigned long long seg_of(const PeerBoxes& pb, int s_static, unsigned long long rb) {
-    return ((4ull * rb + 15ull) & ~15ull) + 16ull * (unsigned long long)s_static;
-}
 
-// Block 0 first turns the block sums of scan_local into exclusive block offsets + the local total (what scan_blocks_kernel does
-// on one GPU).  All blocks push the narrowed counts into all ranks' staging (coalesced 16-byte P2P stores); the last block to
-// finish publishes {total, width, maxcount, seq} into all mailboxes: a peer that sees the seq also sees the counts.
-__global__ void __launch_bounds__(256) xchg_post_kernel(PeerBoxes pb, const uint32_t* __restrict__ counts, uint32_t R,
-                                                        unsigned long long* __restrict__ blocksum, uint32_t nblk,
-                                                        unsigned long long* __restrict__ local_total, const uint32_t* __restrict__ maxcount,
-                                                        uint32_t* __restrict__ blocks_done) {
-    if (blockIdx.x == 0) {                                            // exclusive scan of nblk block sums by one block
-        __shared__ unsigned long long wsum[8];
-        __shared__ unsigned long long carry_s;
-        if (threadIdx.x == 0) carry_s = 0ull;
-        __syncthreads();
-        for (uint32_t b0 = 0; b0 < nblk; b0 += 256) {
-            const uint32_t bb = b0 + threadIdx.x;
-            const unsigned long long v = bb < nblk ? blocksum[bb] : 0ull;
-            unsigned long long incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
-            if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            unsigned long long woff = 0;
-            for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
-            const unsigned long long carry = carry_s;
-            if (bb < nblk) blocksum[bb] = carry + woff + incl - v;
-            __syncthreads();
-            if (threadIdx.x == 255) carry_s = carry + woff + incl;
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) *local_total = carry_s;
-    }
-    const uint32_t mc = *maxcount;
-    const uint32_t width = mc <= 0xFFu ? 1u : (mc <= 0xFFFFu ? 2u : 4u);
-    unsigned long long rb_mine = 0;
-#pragma unroll
-    for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k == pb.rank) rb_mine = pb.rays_before[k];
-    const unsigned long long seg = ((4ull * rb_mine + 15ull) & ~15ull) + 16ull * (unsigned long long)pb.rank;
-    const uint32_t per = 16u / width;                                  // rays per 16-byte packet
-    const uint32_t npk = (R + per - 1) / per;
-    for (uint32_t pk = blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += gridDim.x * blockDim.x) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        const uint32_t r0 = pk * per;
-        for (uint32_t k = 0; k < per; ++k) {
-            const uint32_t c = r0 + k < R ? counts[r0 + k] : 0u;
-            const uint32_t bit = k * width * 8u;
-            w[bit >> 5] |= c << (bit & 31u);
-        }
-        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-#pragma unroll
-        for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) *reinterpret_cast<uint4*>(pb.stage[d] + seg + 16ull * pk) = v;
-    }
-    // the block's P2P stores -> barrier -> ONE system-scope fence (cumulative over what the barrier ordered) -> arrival counter;
-    // a fence.sys per thread made this kernel 3x longer than its stores
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) { __threadfence_system(); last = atomicAdd(blocks_done, 1u) == gridDim.x - 1; }
-    __syncthreads();
-    if (!last) return;
-    if (threadIdx.x == 0) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < (unsigned)pb.world) {
-        const unsigned long long par = pb.seq & 1ull;
-        unsigned long long* slot = pb.box[threadIdx.x] + MB_TOT + (par * BVHGPU_MAX_PEERS + pb.rank) * 4;
-        slot[1] = __ldcg(local_total); slot[2] = width; slot[3] = mc;
-        __threadfence_system();
-        st_release_sys(slot, pb.seq);
-    }
-    if (threadIdx.x == 0) *blocks_done = 0u;
-}
-
-// Wait (one warp of the calling block) until every peer has posted step pb.seq; returns this rank's hit base / the grand total /
-// the widths through shared memory of the caller.  Spins on LOCAL memory (the mailbox of this rank).
-struct XInfo { unsigned long long base, grand, width[BVHGPU_MAX_PEERS], waited; };
-__device__ __forceinline__ void wait_posts(const PeerBoxes& pb, XInfo* xs, uint32_t* err, unsigned long long timeout_ns) {
-    const int lane = threadIdx.x;                                      // called by threads 0..31
+// Wait (threads 0..31 of the calling block) until every peer has posted step pb.seq; hit bases of all sources + the grand total.
+struct XInfo { unsigned long long base[BVHGPU_MAX_PEERS], grand, waited; };
+__device__ __forceinline__ void wait_posts(const PeerBoxes& pb, XInfo* xs) {
+    const int lane = threadIdx.x;
     const unsigned long long par = pb.seq & 1ull;
-    unsigned long long tot = 0, width = 1, waited = 0;
-    const unsigned long long t0 = global_timer_ns();
+    unsigned long long tot = 0, waited = 0;
     if (lane < pb.world) {
         const unsigned long long* slot = pb.box[pb.rank] + MB_TOT + (par * BVHGPU_MAX_PEERS + lane) * 4;
+        const unsigned long long t0 = global_timer_ns();
         uint32_t spins = 0;
         while (ld_acquire_sys(slot) != pb.seq) {
-            if (((++spins) & 63u) == 0u && global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+            if (((++spins) & 63u) == 0u && global_timer_ns() - t0 > pb.timeout_ns) { atomicExch(pb.err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
             __nanosleep(100);
         }
-        tot = slot[1]; width = slot[2];
+        tot = slot[1];
         waited = global_timer_ns() - t0;
     }
-    unsigned long long base = 0, grand = 0, wmax = 0;
+    unsigned long long run = 0, wmax = 0, mine = 0;
     for (int r = 0; r < pb.world; ++r) {
         const unsigned long long v = __shfl_sync(0xffffffffu, tot, r), w = __shfl_sync(0xffffffffu, waited, r);
-        if (r < pb.rank) base += v;
-        grand += v;
+        if (lane == r) mine = run;
+        run += v;
         wmax = w > wmax ? w : wmax;
     }
-    if (lane < BVHGPU_MAX_PEERS) xs->width[lane] = width;
-    if (lane == 0) { xs->base = base; xs->grand = grand; xs->waited = wmax; }
+    if (lane < BVHGPU_MAX_PEERS) xs->base[lane] = mine;
+    if (lane == 0) { xs->grand = run; xs->waited = wmax; }
 }
 
-// Global offsets from the staged counts.  WRITE = false: wait for the posts, tile sums (+ block 0 leaves xinfo for the kernels
-// behind it).  WRITE = true: tile base = sum of the tile sums before the tile (a block-wide reduction: they are all final),
-// offsets out; block 0 ends the step by waiting for the peers' done flags.
-__device__ __forceinline__ uint32_t staged_count(const PeerBoxes& pb, const unsigned char* __restrict__ stage,
-                                                 const unsigned long long* width, unsigned long long g) {
-    int s = 0;
-    unsigned long long rb = 0;
-#pragma unroll
-    for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k < pb.world && g >= pb.rays_before[k]) { s = k; rb = pb.rays_before[k]; }
-    const unsigned long long i = g - rb;
-    const unsigned char* p = stage + (((4ull * rb + 15ull) & ~15ull) + 16ull * (unsigned long long)s);
-    const unsigned long long w = width[s];
-    return w == 1 ? (uint32_t)__ldcg(p + i) : (w == 2 ? (uint32_t)__ldcg(reinterpret_cast<const unsigned short*>(p) + i) : __ldcg(reinterpret_cast<const uint32_t*>(p) + i));
-}
-template <bool WRITE>
-__global__ void __launch_bounds__(SCAN_THREADS) gscan_kernel(PeerBoxes pb, const unsigned char* __restrict__ stage, unsigned long long* __restrict__ xinfo,
-                                                             unsigned long long n, unsigned long long* __restrict__ blocksum,
-                                                             uint32_t* __restrict__ offsets, uint32_t* err, unsigned long long timeout_ns) {
+// One warp waits for the posts and leaves {hit base of every source, grand total, ns waited} in xinfo[0..9] for the two kernels
+// behind it (polling the mailbox from every block of those kernels cost 30 us per step, measured).
+__global__ void xchg_wait_kernel(PeerBoxes pb, unsigned long long* __restrict__ xinfo) {
     __shared__ XInfo xs;
-    __shared__ uint32_t wsum[SCAN_THREADS / 32];
-    __shared__ unsigned long long red[SCAN_THREADS / 32];
-    if (!WRITE) {
-        if (threadIdx.x < 32) wait_posts(pb, &xs, err, timeout_ns);
-        __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            xinfo[0] = xs.base; xinfo[1] = xs.grand;
+    wait_posts(pb, &xs);
+    __syncwarp();
+    if (threadIdx.x < BVHGPU_MAX_PEERS) xinfo[threadIdx.x] = xs.base[threadIdx.x];
+    if (threadIdx.x == 0) { xinfo[8] = xs.grand; xinfo[9] = xs.waited; }
+}
+
+// Exclusive scan of the per-ray counts: per-tile local offsets + (last block) exclusive tile offsets and the total -- one kernel
+// (the last block to arrive scans the tile sums).  SHARDED: the tile's counts, then the tile table and the total, go to all ranks.
+template <bool SHARDED>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_post_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ local,
+                                                                 unsigned long long* __restrict__ blocksum, unsigned long long* __restrict__ total,
+                                                                 uint32_t* __restrict__ arrival, PeerBoxes pb) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32], wmax[SCAN_THREADS / 32];
+    __shared__ unsigned long long wsum64[SCAN_THREADS / 32];
+    __shared__ unsigned long long carry_s;
+    __shared__ bool last;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0, m = 0;
 #pragma unroll
-            for (int k = 0; k < BVHGPU_MAX_PEERS; ++k) xinfo[2 + k] = xs.width[k];
-            unsigned long long* tr = pb.box[pb.rank] + MB_TRACE + (pb.seq % MB_TRACE_LEN) * 4;
-            tr[0] = pb.seq; tr[1] = global_timer_ns(); tr[2] = xs.waited; tr[3] = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? counts[base + k] : 0u; s += v[k]; m = v[k] > m ? v[k] : m; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    if (lane_id() == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    uint32_t woff = 0, tsum = 0, tmax = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) { if (w < (int)(threadIdx.x >> 5)) woff += wsum[w]; tsum += wsum[w]; tmax = wmax[w] > tmax ? wmax[w] : tmax; }
+    uint32_t run = woff + incl - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) local[base + k] = run; run += v[k]; }
+    const unsigned long long width = tmax <= 0xFFu ? 1ull : (tmax <= 0xFFFFu ? 2ull : 4ull);
+    if (SHARDED) {
+        unsigned long long tb_mine = 0;
+#pragma unroll
+        for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k == pb.rank) tb_mine = pb.tiles_before[k];
+        const unsigned long long at = TILE_BYTES * (tb_mine + blockIdx.x) + (unsigned long long)threadIdx.x * SCAN_ITEMS * width;
+        if (width == 1) {
+            const uint2 q = make_uint2(v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24, v[4] | v[5] << 8 | v[6] << 16 | v[7] << 24);
+#pragma unroll
+            for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) *reinterpret_cast<uint2*>(pb.stage[d] + at) = q;
+        } else if (width == 2) {
+            const uint4 q = make_uint4(v[0] | v[1] << 16, v[2] | v[3] << 16, v[4] | v[5] << 16, v[6] | v[7] << 16);
+#pragma unroll
+            for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) *reinterpret_cast<uint4*>(pb.stage[d] + at) = q;
+        } else {
+            const uint4 q0 = make_uint4(v[0], v[1], v[2], v[3]), q1 = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) { *reinterpret_cast<uint4*>(pb.stage[d] + at) = q0; *reinterpret_cast<uint4*>(pb.stage[d] + at + 16) = q1; }
         }
-    } else {
-        if (threadIdx.x < BVHGPU_MAX_PEERS) xs.width[threadIdx.x] = xinfo[2 + threadIdx.x];
-        if (threadIdx.x == 0) xs.grand = xinfo[1];
+    }
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = (unsigned long long)tsum | (width << 56);
+    // the block's stores -> barrier -> ONE fence (cumulative over what the barrier ordered) -> arrival counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (SHARDED && pb.world > 1) __threadfence_system(); else __threadfence();
+        last = atomicAdd(arrival, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) { __threadfence(); carry_s = 0ull; }
+    __syncthreads();
+    unsigned long long tb_mine = 0;
+    if (SHARDED) {
+#pragma unroll
+        for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k == pb.rank) tb_mine = pb.tiles_before[k];
+    }
+    for (uint32_t b0 = 0; b0 < gridDim.x; b0 += SCAN_THREADS) {           // exclusive scan of the tile sums by this (last) block
+        const uint32_t bb = b0 + threadIdx.x;
+        const unsigned long long e = bb < gridDim.x ? __ldcg(blocksum + bb) : 0ull;
+        const unsigned long long val = e & OFF_MASK;
+        unsigned long long in64 = val;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, in64, o); if ((int)lane_id() >= o) in64 += t; }
+        if (lane_id() == 31) wsum64[threadIdx.x >> 5] = in64;
+        __syncthreads();
+        unsigned long long wo = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wo += wsum64[w];
+        const unsigned long long carry = carry_s;
+        const unsigned long long excl = carry + wo + in64 - val;
+        if (bb < gridDim.x) {
+            blocksum[bb] = excl;
+            if (SHARDED) {
+                const unsigned long long entry = (excl & OFF_MASK) | (e & ~OFF_MASK);
+#pragma unroll
+                for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world) *reinterpret_cast<unsigned long long*>(pb.stage[d] + pb.table_off + 8ull * (tb_mine + bb)) = entry;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + wo + in64;
         __syncthreads();
     }
-    __shared__ uint32_t failed;                                          // block-uniform (the branch below contains barriers)
-    if (threadIdx.x == 0) failed = *(volatile uint32_t*)err;
+    if (threadIdx.x == 0) { *total = carry_s; *arrival = 0u; }
+    if (SHARDED) {
+        if (threadIdx.x == 0) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < (unsigned)pb.world) {
+            unsigned long long* slot = pb.box[threadIdx.x] + MB_TOT + ((pb.seq & 1ull) * BVHGPU_MAX_PEERS + pb.rank) * 4;
+            slot[1] = carry_s;
+            __threadfence_system();
+            st_release_sys(slot, pb.seq);
+        }
+    }
+}
+
+// Global offsets: one block per tile of every source rank.
+__global__ void __launch_bounds__(SCAN_THREADS) goffsets_kernel(PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t wsum[SCAN_THREADS / 32];
+    __shared__ uint32_t failed;
+    if (threadIdx.x == 0) failed = *(volatile uint32_t*)pb.err;
     __syncthreads();
+    const unsigned long long g = blockIdx.x;
     if (failed == 0u) {
-        const unsigned long long base = (unsigned long long)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-        uint32_t v[SCAN_ITEMS], s = 0;
+        int sg = 0;
+        unsigned long long tb = 0, rb = 0, re = pb.rays_before[1];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? staged_count(pb, stage, xs.width, base + k) : 0u; s += v[k]; }
+        for (int k = 1; k < BVHGPU_MAX_PEERS; ++k) if (k < pb.world && g >= pb.tiles_before[k]) { sg = k; tb = pb.tiles_before[k]; rb = pb.rays_before[k]; re = pb.rays_before[k + 1]; }
+        const unsigned long long hb = xinfo[sg];
+        const unsigned char* stage = nullptr;
+#pragma unroll
+        for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d == pb.rank) stage = pb.stage[d];
+        const unsigned long long entry = __ldcg(reinterpret_cast<const unsigned long long*>(stage + pb.table_off + 8ull * g));
+        const unsigned long long width = entry >> 56;
+        const unsigned char* p = stage + TILE_BYTES * g + (unsigned long long)threadIdx.x * SCAN_ITEMS * width;
+        uint32_t v[SCAN_ITEMS], s = 0;
+        static_assert(SCAN_ITEMS == 8, "8 counts per thread");
+        if (width == 1) {
+            const uint2 q = __ldcg(reinterpret_cast<const uint2*>(p));
+            v[0] = q.x & 0xFFu; v[1] = (q.x >> 8) & 0xFFu; v[2] = (q.x >> 16) & 0xFFu; v[3] = q.x >> 24; v[4] = q.y & 0xFFu; v[5] = (q.y >> 8) & 0xFFu; v[6] = (q.y >> 16) & 0xFFu; v[7] = q.y >> 24;
+        } else if (width == 2) {
+            const uint4 q = __ldcg(reinterpret_cast<const uint4*>(p));
+            v[0] = q.x & 0xFFFFu; v[1] = q.x >> 16; v[2] = q.y & 0xFFFFu; v[3] = q.y >> 16; v[4] = q.z & 0xFFFFu; v[5] = q.z >> 16; v[6] = q.w & 0xFFFFu; v[7] = q.w >> 16;
+        } else {
+            const uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(p)), q1 = __ldcg(reinterpret_cast<const uint4*>(p) + 1);
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
         uint32_t incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
         if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
-        unsigned long long before = 0;
-        if (WRITE) {                                                    // sum of the tile sums in front of this tile
-            for (uint32_t b = threadIdx.x; b < blockIdx.x; b += SCAN_THREADS) before += blocksum[b];
-            for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
-            if (lane_id() == 0) red[threadIdx.x >> 5] = before;
-        }
         __syncthreads();
         uint32_t woff = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
-        if (!WRITE) {
-            if (threadIdx.x == SCAN_THREADS - 1) blocksum[blockIdx.x] = (unsigned long long)(woff + incl);
-        } else {
-            unsigned long long run = 0;
+        unsigned long long run = hb + (entry & OFF_MASK) + woff + incl - s;
+        const unsigned long long j0 = rb + (g - tb) * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-            for (int w = 0; w < SCAN_THREADS / 32; ++w) run += red[w];
-            run += woff + incl - s;
+        for (int k = 0; k < SCAN_ITEMS; ++k) { if (j0 + k < re) offsets[j0 + k] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run; run += v[k]; }
+        if (g == gridDim.x - 1 && threadIdx.x == 0) {
+            unsigned long long ng = 0;
 #pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) offsets[base + k] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run; run += v[k]; }
-            if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) offsets[n] = xs.grand > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)xs.grand;
+            for (int k = 1; k <= BVHGPU_MAX_PEERS; ++k) if (k == pb.world) ng = pb.rays_before[k];
+            const unsigned long long grand = xinfo[8];
+            offsets[ng] = grand > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)grand;
         }
     }
-    if (WRITE && blockIdx.x == 0 && threadIdx.x < 32) {                 // the step ends when every peer's hit lists have landed here
+    if (blockIdx.x == 0 && threadIdx.x < 32) {                 // the step ends when every peer's hit lists have landed here
         const int lane = threadIdx.x;
         const unsigned long long par = pb.seq & 1ull;
         unsigned long long waited = 0;
@@ -578,65 +597,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) gscan_kernel(PeerBoxes pb, const
             const unsigned long long t0 = global_timer_ns();
             uint32_t spins = 0;
             while (ld_acquire_sys(slot) != pb.seq) {
-                if (((++spins) & 63u) == 0u && global_timer_ns() - t0 > timeout_ns) { atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+                if (((++spins) & 63u) == 0u && global_timer_ns() - t0 > pb.timeout_ns) { atomicExch(pb.err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
                 __nanosleep(100);
             }
             waited = global_timer_ns() - t0;
         }
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, waited, o); waited = w > waited ? w : waited; }
-        if (lane == 0) pb.box[pb.rank][MB_TRACE + (pb.seq % MB_TRACE_LEN) * 4 + 3] = waited;
-    }
-}
-
-// The all-gather proper: this rank's hit segment [base, base + total) of its LOCAL copy of the global hit buffer goes to the same
-// place in every peer's copy, as whole 16-byte stores (scalar at the unaligned ends).  The last block to finish fences and raises
-// this rank's done flag in every mailbox.
-__global__ void __launch_bounds__(256) xchg_push_kernel(PeerBoxes pb, const unsigned long long* __restrict__ xinfo, const unsigned long long* __restrict__ local_total,
-                                                        unsigned long long cap, uint32_t* __restrict__ blocks_done, const uint32_t* __restrict__ err) {
-    if (*err == 0u && pb.world > 1) {
-        const unsigned long long begin = xinfo[0];
-        unsigned long long end = begin + *local_total;
-        if (end > cap) end = cap;
-        uint32_t* src = nullptr;
-#pragma unroll
-        for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d == pb.rank) src = pb.hits[d];
-        const unsigned long long q0 = (begin + 3ull) & ~3ull, q1 = end & ~3ull;       // whole quads inside the segment
-        if (begin < end) {
-            if (q0 < q1) {
-                const unsigned long long nq = (q1 - q0) >> 2;
-                for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (unsigned long long)gridDim.x * blockDim.x) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(src + q0 + 4ull * q);
-#pragma unroll
-                    for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world && d != pb.rank) *reinterpret_cast<uint4*>(pb.hits[d] + q0 + 4ull * q) = v;
-                }
-            }
-            if (blockIdx.x == 0 && threadIdx.x < 8) {                   // up to 3 words in front of q0 and 3 behind q1; or a short segment (< 7 words) as a whole
-                unsigned long long w;
-                bool ok;
-                if (q0 < q1) { w = threadIdx.x < 4 ? begin + threadIdx.x : q1 + (threadIdx.x - 4); ok = threadIdx.x < 4 ? w < q0 : w < end; }
-                else         { w = begin + threadIdx.x; ok = w < end; }
-                if (ok) {
-                    const uint32_t v = src[w];
-#pragma unroll
-                    for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world && d != pb.rank) pb.hits[d][w] = v;
-                }
-            }
+        if (lane == 0) {
+            unsigned long long* tr = pb.box[pb.rank] + MB_TRACE + (pb.seq % MB_TRACE_LEN) * 4;
+            tr[0] = pb.seq; tr[1] = global_timer_ns(); tr[2] = xinfo[9]; tr[3] = waited;
         }
     }
-    // the block's P2P stores -> barrier -> ONE system-scope fence (cumulative over what the barrier ordered) -> arrival counter;
-    // a fence.sys per thread made this kernel 3x longer than its stores
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) { __threadfence_system(); last = atomicAdd(blocks_done, 1u) == gridDim.x - 1; }
-    __syncthreads();
-    if (!last) return;
-    if (threadIdx.x == 0) __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < (unsigned)pb.world) st_release_sys(pb.box[threadIdx.x] + MB_DONE + (pb.seq & 1ull) * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
-    if (threadIdx.x == 0) *blocks_done = 0u;
 }
 
-// Pass 2: final offsets + hit lists.  Rays with <= K hits copy their slots, the rest walk again.
+// Destination of the emit pass.  Single GPU: the caller's buffers.  Sharded (pb.world > 0): the local copy of the global hit buffer
+// at hit base + local offset; the offsets are not written here (goffsets_kernel rebuilds them on every rank).
+struct EmitDst {
+    uint32_t* offsets;                       // single GPU: the caller's offsets; sharded: nullptr
+    uint32_t* hits;
+    unsigned long long nrays_out;            // single GPU: index of the closing offsets entry
+};
+
+// Pass 2: final offsets + hit lists.  Rays with <= K hits copy their slots, the rest walk again.  Sharded: the block then ships
+// its piece of the hit lists -- contiguous, because the block's rays are -- to every peer.
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
                                                    const typename Traits<T>::DAabb* __restrict__ aabb,
@@ -644,39 +627,85 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
                                                    const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
                                                    const unsigned long long* __restrict__ total,
-                                                   EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count) {
-    if (dst.err && *dst.err) return;
-    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long hbase = dst.hit_base ? *dst.hit_base : 0ull;
-    if (r == first && dst.offsets) {          // (chunked host path: the last chunk's write is the final total)
-        const unsigned long long t = *total;
-        dst.offsets[dst.nrays_out] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
+                                                   EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count,
+                                                   PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ arrival) {
+    __shared__ unsigned long long rng[2];
+    __shared__ uint32_t failed;
+    __shared__ bool last;
+    const bool sharded = pb.world > 0;
+    unsigned long long hbase = 0;
+    if (sharded) {
+        if (threadIdx.x == 0) failed = *(volatile uint32_t*)pb.err;
+        __syncthreads();
+        hbase = xinfo[pb.rank];
     }
-    if (r >= first + count) return;
-    const unsigned long long off = hbase + blocksum[r / SCAN_TILE] + local[r];
-    if (dst.offsets) dst.offsets[r] = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
-    const uint32_t c = counts[r];
-    if (c == 0 || dst.hits[0] == nullptr) return;
-    if (c <= K) {
-        for (uint32_t k = 0; k < c; ++k) {
-            if (off + k < cap) {
-                const uint32_t h = slots[(size_t)k * nrays + r];
-#pragma unroll
-                for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < dst.world) dst.hits[d][off + k] = h;
+    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (!sharded || failed == 0u) {
+        if (r == first && dst.offsets) {          // (sliced host path: the last slice's write is the final total)
+            const unsigned long long t = *total;
+            dst.offsets[dst.nrays_out] = t > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)t;
+        }
+        if (r < first + count) {
+            const unsigned long long off = hbase + blocksum[r / SCAN_TILE] + local[r];
+            if (dst.offsets) dst.offsets[r] = off > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)off;
+            const uint32_t c = counts[r];
+            if (c != 0 && dst.hits != nullptr) {
+                if (c <= K) {
+                    for (uint32_t k = 0; k < c; ++k) if (off + k < cap) dst.hits[off + k] = slots[(size_t)k * nrays + r];
+                } else {
+                    T o[3], inv[3];
+                    load_ray<T, false>(rays, r, o, inv);
+                    unsigned long long w = off;
+                    walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) { if (w < cap) dst.hits[w] = shape; ++w; });
+                }
             }
         }
-    } else {
-        T o[3], inv[3];
-        load_ray<T, false>(rays, r, o, inv);
-        unsigned long long w = off;
-        walk<T, FLAT>(trec, n_rec, aabb, o, inv, [&](uint32_t shape) {
-            if (w < cap) {
-#pragma unroll
-                for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < dst.world) dst.hits[d][w] = shape;
-            }
-            ++w;
-        });
     }
+    if (!sharded) return;
+    bool pushed = false;
+    if (failed == 0u && pb.world > 1) {
+        if (threadIdx.x == 0) {
+            const uint32_t r0 = first + blockIdx.x * blockDim.x;
+            const uint32_t r1 = min(r0 + blockDim.x, first + count) - 1u;
+            rng[0] = hbase + blocksum[r0 / SCAN_TILE] + local[r0];
+            rng[1] = hbase + blocksum[r1 / SCAN_TILE] + local[r1] + counts[r1];
+        }
+        __syncthreads();                                              // also: the block's own hit stores are visible to the block
+        const unsigned long long begin = rng[0], end = rng[1] < cap ? rng[1] : cap;
+        if (begin < end) {
+            pushed = true;
+            const uint32_t* src = dst.hits;
+            const unsigned long long q0 = (begin + 3ull) & ~3ull, q1 = end & ~3ull;
+            if (q0 < q1) {
+                for (unsigned long long q = (q0 >> 2) + threadIdx.x; q < (q1 >> 2); q += blockDim.x) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + q);
+#pragma unroll
+                    for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world && d != pb.rank) reinterpret_cast<uint4*>(pb.hits[d])[q] = v;
+                }
+            }
+            if (threadIdx.x < 8) {                                     // up to 3 words in front of q0 and 3 behind q1; or a short piece (< 7 words) as a whole
+                unsigned long long w;
+                bool ok;
+                if (q0 < q1) { w = threadIdx.x < 4 ? begin + threadIdx.x : q1 + (threadIdx.x - 4); ok = threadIdx.x < 4 ? w < q0 : w < end; }
+                else         { w = begin + threadIdx.x; ok = w < end; }
+                if (ok) {
+                    const uint32_t v = __ldcg(src + w);
+#pragma unroll
+                    for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) if (d < pb.world && d != pb.rank) pb.hits[d][w] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (pushed) __threadfence_system();                           // only a block that stored to peers has something to order
+        last = atomicAdd(arrival, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) { __threadfence_system(); *arrival = 0u; }
+    __syncthreads();
+    if (threadIdx.x < (unsigned)pb.world) st_release_sys(pb.box[threadIdx.x] + MB_DONE + (pb.seq & 1ull) * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
 }
 
 // Launch pass 1 over rays [first, first+count): persistent refill kernel (default) or one ray per thread.
@@ -770,22 +799,23 @@ int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, s
         if (ctx->profile) { cudaEventRecord(ctx->ev_walk[1], st); ctx->have_walk = true; }
     }
     const int grid = (R + 255) / 256;
-    scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, shard ? reinterpret_cast<uint32_t*>(tail + S_MAXC) : nullptr);
-    ctx->launches++;
     EmitDst dst{};
-    PeerBoxes pb{};
-    const unsigned long long xchg_timeout = 10ull * 1000ull * 1000ull * 1000ull;
-    uint32_t gblk = 0;
-    unsigned long long NG = 0;
-    unsigned long long* gsums = nullptr;
+    PeerBoxes pb{};                                                   // world == 0: single GPU
+    uint32_t* arrival = reinterpret_cast<uint32_t*>(tail + S_BLKDONE);
     if (shard) {
         const int W = shard->world;
         pb.rank = shard->rank; pb.world = W; pb.seq = shard->seq;
-        pb.rays_before[0] = 0;
-        for (int d = 0; d < W; ++d) pb.rays_before[d + 1] = pb.rays_before[d] + shard->shard_rays[d];
-        for (int d = W; d < BVHGPU_MAX_PEERS; ++d) pb.rays_before[d + 1] = pb.rays_before[W];
-        NG = pb.rays_before[W];
+        pb.err = ctx->d_async_err; pb.timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+        pb.rays_before[0] = 0; pb.tiles_before[0] = 0;
+        for (int d = 0; d < BVHGPU_MAX_PEERS; ++d) {
+            const unsigned long long nd = d < W ? (unsigned long long)shard->shard_rays[d] : 0ull;
+            pb.rays_before[d + 1] = pb.rays_before[d] + nd;
+            pb.tiles_before[d + 1] = pb.tiles_before[d] + (nd + SCAN_TILE - 1) / SCAN_TILE;
+        }
+        const unsigned long long NG = pb.rays_before[W], NT = pb.tiles_before[W];
+        pb.table_off = TILE_BYTES * NT;
         const size_t half = BVHGPU_SHARD_STAGE_BYTES(NG);                // the staging alternates between two halves (parity of seq)
+        if (pb.table_off + 8ull * NT > half) { set_error("internal: staging layout exceeds BVHGPU_SHARD_STAGE_BYTES"); return BVHGPU_ERR_INTERNAL; }
         for (int d = 0; d < W; ++d) {
             pb.box[d] = (unsigned long long*)shard->peer_mailbox[d];
             pb.stage[d] = (unsigned char*)shard->peer_counts[d] + (shard->seq & 1ull) * half;
@@ -794,31 +824,26 @@ int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, s
         if (shard->shard_rays[shard->rank] != nrays) { set_error("traverse_sharded: shard_rays[rank] = %zu but nrays = %zu", shard->shard_rays[shard->rank], nrays); return BVHGPU_ERR_INVALID; }
         if (NG > 0x7FFFFFFFull) { set_error("traverse_sharded: %llu rays in total exceed 2^31-1", NG); return BVHGPU_ERR_INVALID; }
         cap = shard->cap;
-        dst.world = 1; dst.offsets = nullptr; dst.hits[0] = pb.hits[pb.rank]; dst.hit_base = tail + S_XINFO; dst.err = ctx->d_async_err;
-        gblk = (uint32_t)((NG + SCAN_TILE - 1) / SCAN_TILE);
-        BVH_TRY(scratch.get(&gsums, (size_t)gblk + 1));
-        const int pgrid = (int)std::min<uint32_t>(2u * (uint32_t)ctx->sm_count, (R / 16 + 255) / 256 + 1);
-        xchg_post_kernel<<<pgrid, 256, 0, st>>>(pb, counts, R, sums, nblk, tail + S_TOTAL, reinterpret_cast<const uint32_t*>(tail + S_MAXC), reinterpret_cast<uint32_t*>(tail + S_BLKDONE));
-        gscan_kernel<false><<<gblk, SCAN_THREADS, 0, st>>>(pb, pb.stage[pb.rank], tail + S_XINFO, NG, gsums, nullptr, ctx->d_async_err, xchg_timeout);
-        ctx->launches += 2;
-    } else {
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, tail + S_TOTAL);
+        dst.offsets = nullptr; dst.hits = pb.hits[pb.rank];
+        scan_post_kernel<true><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb);
+        xchg_wait_kernel<<<1, 32, 0, st>>>(pb, tail + S_XINFO);
         ctx->launches++;
-        dst.world = 1; dst.offsets = d_offsets; dst.hits[0] = d_hits; dst.nrays_out = R;
+    } else {
+        dst.offsets = d_offsets; dst.hits = d_hits; dst.nrays_out = R;
+        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb);
     }
+    ctx->launches++;
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
     if (total) {                                                  // the total is known before the hit lists are written
         BVH_CUDA_TRY(cudaMemcpyAsync(h, tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R);
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
     ctx->launches++;
     if (shard) {
-        const int xgrid = ctx->sm_count;
-        xchg_push_kernel<<<xgrid, 256, 0, st>>>(pb, tail + S_XINFO, tail + S_TOTAL, (unsigned long long)cap, reinterpret_cast<uint32_t*>(tail + S_BLKDONE), ctx->d_async_err);
-        gscan_kernel<true><<<gblk, SCAN_THREADS, 0, st>>>(pb, pb.stage[pb.rank], tail + S_XINFO, NG, gsums, (uint32_t*)shard->offsets, ctx->d_async_err, xchg_timeout);
-        ctx->launches += 2;
+        goffsets_kernel<<<(unsigned)pb.tiles_before[pb.world], SCAN_THREADS, 0, st>>>(pb, tail + S_XINFO, (uint32_t*)shard->offsets);
+        ctx->launches++;
     }
     BVH_CUDA_TRY(cudaGetLastError());
     int rc = BVHGPU_OK;
@@ -899,6 +924,23 @@ static int stream_capable(bvhgpu_ctx* ctx) {
     return ctx->stream_ok;
 }
 
+// cuStreamWriteValue32 (driver API, resolved through the runtime: no libcuda link dependency): the arrival counter is bumped by a
+// stream memory operation behind every chunk copy instead of a 4-byte DMA (each tiny copy cost ~10 us of copy-engine latency:
+// 16 of them stretched a 0.44 ms transfer to 0.63 ms).  Falls back to the 4-byte copy where the entry point is missing.
+typedef int (*WriteValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static WriteValue32Fn stream_write_value32() {
+    static WriteValue32Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (WriteValue32Fn)p;
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 // Host-pointer entry point.  Large batches on an undisturbed device are STREAMED: the batch is copied in chunks on the copy
 // stream, each followed by a 4-byte DMA that bumps a device-side `ready` counter, and ONE persistent walk kernel -- launched
 // AFTER all copies are enqueued, so it never depends on work the host has yet to submit -- consumes the rays as they arrive.
@@ -933,8 +975,10 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     const RaySrc<T> rays{reinterpret_cast<const T*>(staged), fmt};
     EmitDst dst{};
-    dst.world = 1; dst.offsets = tree->d_offsets; dst.hits[0] = tree->d_hits; dst.nrays_out = R;
-    const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 32768));
+    dst.offsets = tree->d_offsets; dst.hits = tree->d_hits; dst.nrays_out = R;
+    const PeerBoxes nopeers{};
+    uint32_t* arrival = reinterpret_cast<uint32_t*>(tail + S_BLKDONE);
+    const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 120000));     // ~8 chunks per million rays
     const bool streaming = nchunks > 1 && stream_capable(ctx) == 1;
     ctx->last_streamed = streaming ? 1 : 0;
     stamp(0);                                                     // scratch allocated
@@ -949,7 +993,11 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
             cudaError_t e = cudaMemcpyAsync(staged + ray_bytes * lo, (const unsigned char*)h_rays + ray_bytes * lo, ray_bytes * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream);
             h_ready[c] = hi;
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) {
+                WriteValue32Fn wv = stream_write_value32();
+                if (!wv || wv(ctx->copy_stream, (unsigned long long)(uintptr_t)d_ready, hi, 0u) != 0)
+                    e = cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+            }
             if (e != cudaSuccess) {                               // nothing waits on `ready` yet (the kernel is launched below): just report
                 set_error("traverse: H2D copy of chunk %u failed: %s", c, cudaGetErrorString(e));
                 cudaStreamSynchronize(ctx->copy_stream);
@@ -969,22 +1017,21 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
     }
     stamp(2);                                                     // walk launched
     {
-        scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, nullptr);
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, tail + S_TOTAL);
+        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, nopeers);
         // emit + D2H of the offsets in 4 slices so that the copy back overlaps the rest of the emit
         const uint32_t nsl = R >= 400000 ? 4 : 1;
         for (uint32_t c = 0; c < nsl; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nsl), hi = (uint32_t)((uint64_t)R * (c + 1) / nsl), cnt = hi - lo;
             const int g = (cnt + 255) / 256;
-            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt);
-            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt);
+            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
+            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
             BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
             BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
             const uint32_t ncopy = cnt + (c + 1 == nsl ? 1u : 0u);
             BVH_CUDA_TRY(cudaMemcpyAsync(h_offsets + lo, tree->d_offsets + lo, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
         if (ctx->profile) { cudaEventRecord(ctx->ev_e2e[3], st); cudaEventRecord(ctx->ev_e2e[4], ctx->d2h_stream); ctx->have_e2e = true; }
-        ctx->launches += 2 + nsl;
+        ctx->launches += 1 + nsl;
     }
     BVH_CUDA_TRY(cudaGetLastError());
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);

@@ -190,20 +190,22 @@ int bvhgpu_traverse_od_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_
  * Every rank owns a contiguous shard of the ray batch and a replica of the tree.  Every rank ends the step with its own
  * copy of the GLOBAL CSR in original ray order -- the all-gather of hit lists north_star asks for -- built over peer
  * memory (buffers allocated with bvhgpu_peer_alloc and opened on the other ranks through CUDA IPC):
- *   1. after its local walk a rank stores its per-ray hit COUNTS, narrowed to 1 / 2 / 4 bytes by its largest count, into
- *      every rank's count staging (16-byte P2P stores over NVLink) and then publishes {hit total, width} in all mailboxes;
- *   2. it waits for the peers' posts, which fixes its hit base; every rank rebuilds the global u32 offsets from the
- *      staged counts with a local scan (so 1 byte per ray crosses NVLink instead of 4);
- *   3. its emit kernel writes its hit lists into its own copy of the global hit buffer, and a push kernel stores that
- *      segment into every peer's copy with whole 16-byte P2P stores (4-byte stores scattered by the emit itself reached a
- *      small fraction of the NVLink rate: measured 12.9 ms per 16 M-ray Sponza step on 4 GPUs);
- *   4. done flags: when the stream reaches the end of the step, this rank's copy of the global CSR is complete.
+ *   1. the scan kernel behind the local walk stores every 2048-ray tile's hit COUNTS, narrowed to 1 / 2 / 4 bytes by the
+ *      tile's largest count, into every rank's staging (8/16-byte P2P stores over NVLink); its last block adds the table of
+ *      tile offsets and publishes the rank's hit total in all mailboxes;
+ *   2. the emit kernel waits for the peers' posts (which fixes its hit base), writes its hit lists into its own copy of
+ *      the global hit buffer, and every block ships its contiguous piece to all peers with whole 16-byte P2P stores
+ *      (4-byte stores scattered straight from the emit loop reached a small fraction of the NVLink rate: 12.9 ms per
+ *      16 M-ray Sponza step on 4 GPUs against 2.7 ms this way on 8); the last block raises the done flags;
+ *   3. one more kernel rebuilds the global u32 offsets on every rank from the staged counts (1 byte per ray crossed
+ *      NVLink instead of 4) and ends the step by waiting for the peers' done flags: when the stream reaches the end of the
+ *      step, this rank's copy of the global CSR is complete.  Same number of kernels as a single-GPU step plus one.
  * `seq` must increase by one per call on all ranks.  No host synchronisation; failures (a peer that never answers)
  * are reported by bvhgpu_synchronize.  Mailbox layout (trace words for diagnostics included): traverse.cu. */
 #define BVHGPU_MAX_PEERS 8
 #define BVHGPU_MAILBOX_BYTES 65536
 #define BVHGPU_IPC_HANDLE_BYTES 64
-#define BVHGPU_SHARD_STAGE_BYTES(nrays_global) ((4 * (size_t)(nrays_global) + 16 * BVHGPU_MAX_PEERS + 32 + 255) & ~(size_t)255)
+#define BVHGPU_SHARD_STAGE_BYTES(nrays_global) ((8200 * ((size_t)(nrays_global) / 2048 + 2 * BVHGPU_MAX_PEERS) + 255) & ~(size_t)255)
 typedef struct {
     int rank, world;
     void* peer_counts[BVHGPU_MAX_PEERS];    /* 2 * BVHGPU_SHARD_STAGE_BYTES(nrays_global) on every rank (index = rank): two halves, alternating per step */

@@ -121,7 +121,7 @@ def test_host_traversal_under_ncu_lists_the_traversal_kernels():
         pytest.skip("no permission for GPU performance counters on this box")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "smoke ok" in r.stdout
-    for k in ("walk_", "scan_local_kernel", "scan_blocks_kernel", "emit_kernel"):
+    for k in ("walk_", "scan_post_kernel", "emit_kernel"):
         assert k in r.stdout, k
 
 
