@@ -273,6 +273,22 @@ class Bvh:
             capi.check(st)
             return offsets, hits[: total.value], dists[: total.value]
 
+    def set_triangles(self, triangles):
+        """Triangle vertices of the shapes (n, 3, 3) or (n, 9): enables closest_hit(..., triangles=True).  Triangle i must lie inside shape i's AABB."""
+        t = np.ascontiguousarray(triangles, dtype=self._d["scalar"]).reshape(-1, 9)
+        capi.check(getattr(capi.lib(), f"bvhgpu_tree_set_triangles_{self._d['suffix']}")(self._h, _ptr(t), len(t)))
+
+    def closest_hit(self, rays: np.ndarray, triangles: bool = False):
+        """Per ray: (shape index or U32_MAX, distance or inf, uv (n, 2)).  triangles=False: the shape whose AABB is entered first (exact);
+        triangles=True: Ray::intersects_triangle minimum over the triangles set with set_triangles (front-to-back, distance-pruned)."""
+        rays = np.ascontiguousarray(rays, dtype=self._d["ray"])
+        n = len(rays)
+        shape = np.zeros(n, dtype=np.uint32)
+        dist = np.zeros(n, dtype=self._d["scalar"])
+        uv = np.zeros((n, 2), dtype=self._d["scalar"])
+        capi.check(getattr(capi.lib(), f"bvhgpu_closest_hit_{self._d['suffix']}")(self._h, _ptr(rays), n, 1 if triangles else 0, _ptr(shape), _ptr(dist), _ptr(uv)))
+        return shape, dist, uv
+
     def query_batch(self, kind: int, queries, mode: int = capi.TRAVERSE_BVH):
         """Bvh::traverse with Aabb / Point / Ball queries (IntersectsAabb implementors other than Ray).
         queries: (n, 6) {min,max} for capi.QUERY_AABB, (n, 3) for QUERY_POINT, (n, 4) {center, radius} for QUERY_BALL."""

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 SO = os.path.join(HERE, "libbvh_b200.so")
-SOURCES = ["capi.cu", "build_sah.cu", "flatten.cu", "traverse.cu", "lbvh.cu"]
+SOURCES = ["capi.cu", "build_sah.cu", "flatten.cu", "traverse.cu", "lbvh.cu", "closest.cu"]
 HEADERS = ["common.cuh", "internal.h", "build_types.cuh", os.path.join("..", "..", "include", "bvh_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> 
         r = subprocess.run(cmd, capture_output=True, text=True)
         return cmd, r
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(6, len(jobs))) as ex:
             for cmd, r in ex.map(run, jobs):
                 if verbose or ptxas_v or r.returncode != 0:
                     sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

@@ -95,6 +95,10 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_flatten_{s}").argtypes = [vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_fetch_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_tree_set_triangles_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_tree_set_triangles_dev_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_closest_hit_{s}").argtypes = [vp, vp, sz, i32, vp, vp, vp]
+        getattr(L, f"bvhgpu_closest_hit_dev_{s}").argtypes = [vp, vp, i32, sz, i32, vp, vp, vp]
         getattr(L, f"bvhgpu_traverse_od_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_od_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_refit_dev_{s}").argtypes = [vp, vp, sz]

@@ -60,7 +60,7 @@ template <class T> static void tree_release(Tree<T>* t) {
     bvhgpu_ctx* ctx = t->ctx;
     if (ctx) {
         dfree(ctx, t->d_aabb); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
-        dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
+        dfree(ctx, t->d_tris); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
     }
 }
 
@@ -359,6 +359,31 @@ static int ordered_host_impl(Tree<T>* tree, const typename Traits<T>::Ray* rays,
     }
     dfree(ctx, d_rays); dfree(ctx, d_off); dfree(ctx, d_hits); dfree(ctx, d_dists);
     return rc;
+}
+
+template <class T>
+static int closest_host_impl(Tree<T>* tree, const void* rays, uint32_t fmt, size_t nrays, int use_triangles, uint32_t* out_shape, T* out_dist, T* out_uv) {
+    if (!tree || (nrays && (!rays || !out_shape || !out_dist))) { set_error("closest_hit: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (nrays == 0) return BVHGPU_OK;
+    Scratch scratch(ctx);
+    const size_t ray_bytes = (fmt == BVHGPU_RAYS_FULL ? 9 : 6) * sizeof(T);
+    unsigned char* d_rays = nullptr;
+    uint32_t* d_s = nullptr;
+    T *d_d = nullptr, *d_uv = nullptr;
+    BVH_TRY(scratch.get(&d_rays, ray_bytes * nrays));
+    BVH_TRY(scratch.get(&d_s, nrays));
+    BVH_TRY(scratch.get(&d_d, nrays));
+    if (out_uv) BVH_TRY(scratch.get(&d_uv, 2 * nrays));
+    BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, ray_bytes * nrays, cudaMemcpyHostToDevice, ctx->stream));
+    BVH_TRY(closest_hit_device<T>(tree, d_rays, fmt, nrays, use_triangles, d_s, d_d, d_uv));
+    BVH_CUDA_TRY(cudaMemcpyAsync(out_shape, d_s, sizeof(uint32_t) * nrays, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaMemcpyAsync(out_dist, d_d, sizeof(T) * nrays, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_uv) BVH_CUDA_TRY(cudaMemcpyAsync(out_uv, d_uv, sizeof(T) * 2 * nrays, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
 }
 
 template <class T> static int fetch_impl(Tree<T>* tree, uint32_t* hits, size_t cap) {
@@ -741,6 +766,26 @@ BVH_EXPORT int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p) {
     BVH_EXPORT int bvhgpu_traverse_ordered_##SUF(TREE* tree, const RAY* rays, size_t nrays, int ascending, uint32_t* offsets,      \
                                                  uint32_t* hits, T* dists, size_t cap, size_t* total) {                  \
         return ordered_host_impl<T>(tree, rays, nrays, ascending, offsets, hits, dists, cap, total);                      \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_tree_set_triangles_##SUF(TREE* tree, const T* triangles, size_t n) {                            \
+        if (!tree || (n && !triangles)) { set_error("set_triangles: null argument"); return BVHGPU_ERR_INVALID; }         \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return set_triangles<T>(tree, triangles, n, false);                                                               \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_tree_set_triangles_dev_##SUF(TREE* tree, const void* dev_triangles, size_t n) {                 \
+        if (!tree || (n && !dev_triangles)) { set_error("set_triangles_dev: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return set_triangles<T>(tree, (const T*)dev_triangles, n, true);                                                  \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_closest_hit_##SUF(TREE* tree, const RAY* rays, size_t nrays, int use_triangles, uint32_t* out_shape, \
+                                            T* out_dist, T* out_uv) {                                                     \
+        return closest_host_impl<T>(tree, rays, BVHGPU_RAYS_FULL, nrays, use_triangles, out_shape, out_dist, out_uv);     \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_closest_hit_dev_##SUF(TREE* tree, const void* dev_rays, int ray_layout, size_t nrays, int use_triangles, \
+                                                void* dev_shape, void* dev_dist, void* dev_uv) {                          \
+        if (!tree || (nrays && (!dev_rays || !dev_shape || !dev_dist))) { set_error("closest_hit_dev: null argument"); return BVHGPU_ERR_INVALID; } \
+        BVH_CUDA_TRY(cudaSetDevice(tree->ctx->device));                                                                   \
+        return closest_hit_device<T>(tree, dev_rays, (uint32_t)ray_layout, nrays, use_triangles, (uint32_t*)dev_shape, (T*)dev_dist, (T*)dev_uv); \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_traverse_stats_##SUF(TREE* tree, uint64_t* out2) {                                              \
         if (!tree || !out2) { set_error("traverse_stats: null argument"); return BVHGPU_ERR_INVALID; }                    \

@@ -85,6 +85,7 @@ template <class T> struct Tree {
     uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
     typename Tr::TNode* d_tnodes = nullptr;   // [n_trec] traversal records
     uint32_t n_trec = 0;
+    void* d_tris = nullptr;                   // [n] triangle vertices (padded), optional: bvhgpu_tree_set_triangles_*
     typename Tr::Flat* d_flat = nullptr;      // [n_flat] reference-layout FlatBvh (built on demand)
     size_t n_flat = 0;
     bool have_flat = false;
@@ -173,6 +174,9 @@ template <class T> int query_device(Tree<T>* tree, int mode, int kind, const T* 
 // nearest_to for a batch of points (device pointers): exact reference walk for AABB-distance shapes; candidate lists for any shape
 template <class T> int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist);
 template <class T> int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint32_t* d_offsets, uint32_t* d_cand, size_t cap, size_t* total);
+// ---- closest.cu ----
+template <class T> int set_triangles(Tree<T>* tree, const T* tris9, size_t n, bool dev_input);
+template <class T> int closest_hit_device(Tree<T>* tree, const void* d_rays, uint32_t fmt, size_t nrays, int use_triangles, uint32_t* d_shape, T* d_dist, T* d_uv);
 template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, const T* d_dirs, size_t n,
                                        typename Traits<T>::Ray* d_rays);
 

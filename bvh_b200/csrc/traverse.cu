@@ -367,10 +367,11 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
 //                      largest count): 1 byte per ray crosses NVLink on ordinary batches, not a 4-byte offset
 //   table entry g    : u64 at table_off + 8*g = exclusive hit offset of the tile inside its source's list | width << 56
 // The step is the SAME number of kernels as on one GPU (after the walk: scan_post, emit, + goffsets):
-//   scan_post  per tile: local scan, counts pushed to all ranks; the last block scans the tile sums, pushes the tile table and
-//              publishes the total (a peer that sees the seq also sees counts and table)
-//   emit       every block first waits for all posts (LOCAL polling) -> hit base; hit lists into the local copy of the global
-//              hit buffer, then the block copies its contiguous piece to every peer (16-byte P2P stores); last block: done flags
+//   scan_post  per tile: local scan, counts pushed to all ranks; the last block scans the tile sums, pushes the tile table,
+//              publishes the total (a peer that sees the seq also sees counts and table) and then waits for the peers' posts
+//              (LOCAL polling), which fixes every source's hit base
+//   emit       hit lists into the local copy of the global hit buffer at hit base + local offset, then the block copies its
+//              contiguous piece to every peer (16-byte P2P stores); last block: done flags
 //   goffsets   per tile of every source: offsets = hit base of the source + tile offset + prefix of the staged counts;
 //              block 0 ends the step by waiting for the peers' done flags
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -425,23 +426,14 @@ __device__ __forceinline__ void wait_posts(const PeerBoxes& pb, XInfo* xs) {
     if (lane == 0) { xs->grand = run; xs->waited = wmax; }
 }
 
-// One warp waits for the posts and leaves {hit base of every source, grand total, ns waited} in xinfo[0..9] for the two kernels
-// behind it (polling the mailbox from every block of those kernels cost 30 us per step, measured).
-__global__ void xchg_wait_kernel(PeerBoxes pb, unsigned long long* __restrict__ xinfo) {
-    __shared__ XInfo xs;
-    wait_posts(pb, &xs);
-    __syncwarp();
-    if (threadIdx.x < BVHGPU_MAX_PEERS) xinfo[threadIdx.x] = xs.base[threadIdx.x];
-    if (threadIdx.x == 0) { xinfo[8] = xs.grand; xinfo[9] = xs.waited; }
-}
-
 // Exclusive scan of the per-ray counts: per-tile local offsets + (last block) exclusive tile offsets and the total -- one kernel
 // (the last block to arrive scans the tile sums).  SHARDED: the tile's counts, then the tile table and the total, go to all ranks.
 template <bool SHARDED>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_post_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ local,
                                                                  unsigned long long* __restrict__ blocksum, unsigned long long* __restrict__ total,
-                                                                 uint32_t* __restrict__ arrival, PeerBoxes pb) {
+                                                                 uint32_t* __restrict__ arrival, PeerBoxes pb, unsigned long long* __restrict__ xinfo) {
     __shared__ uint32_t wsum[SCAN_THREADS / 32], wmax[SCAN_THREADS / 32];
+    __shared__ XInfo xs;
     __shared__ unsigned long long wsum64[SCAN_THREADS / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool last;
@@ -533,6 +525,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_post_kernel(const uint32_t*
             __threadfence_system();
             st_release_sys(slot, pb.seq);
         }
+        // ... and the same (last) block waits for the peers' posts and leaves {hit base of every source, grand total, ns waited} in
+        // xinfo[0..9] for the two kernels behind it: no kernel of its own, and no polling from every block of emit / goffsets
+        // (that polling cost 30 us per step, measured)
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            wait_posts(pb, &xs);
+            __syncwarp();
+            if (threadIdx.x < BVHGPU_MAX_PEERS) xinfo[threadIdx.x] = xs.base[threadIdx.x];
+            if (threadIdx.x == 0) { xinfo[8] = xs.grand; xinfo[9] = xs.waited; }
+        }
     }
 }
 
@@ -578,8 +580,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) goffsets_kernel(PeerBoxes pb, co
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
         unsigned long long run = hb + (entry & OFF_MASK) + woff + incl - s;
         const unsigned long long j0 = rb + (g - tb) * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+        uint32_t ov[SCAN_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) { if (j0 + k < re) offsets[j0 + k] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run; run += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS; ++k) { ov[k] = run > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)run; run += v[k]; }
+        if (j0 + SCAN_ITEMS <= re && (j0 & 3ull) == 0ull) {
+            uint4* o4 = reinterpret_cast<uint4*>(offsets + j0);
+            o4[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+            o4[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) if (j0 + k < re) offsets[j0 + k] = ov[k];
+        }
         if (g == gridDim.x - 1 && threadIdx.x == 0) {
             unsigned long long ng = 0;
 #pragma unroll
@@ -825,12 +836,10 @@ int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, s
         if (NG > 0x7FFFFFFFull) { set_error("traverse_sharded: %llu rays in total exceed 2^31-1", NG); return BVHGPU_ERR_INVALID; }
         cap = shard->cap;
         dst.offsets = nullptr; dst.hits = pb.hits[pb.rank];
-        scan_post_kernel<true><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb);
-        xchg_wait_kernel<<<1, 32, 0, st>>>(pb, tail + S_XINFO);
-        ctx->launches++;
+        scan_post_kernel<true><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb, tail + S_XINFO);
     } else {
         dst.offsets = d_offsets; dst.hits = d_hits; dst.nrays_out = R;
-        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb);
+        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, pb, tail + S_XINFO);
     }
     ctx->launches++;
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_pinned);
@@ -1017,7 +1026,7 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
     }
     stamp(2);                                                     // walk launched
     {
-        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, nopeers);
+        scan_post_kernel<false><<<nblk, SCAN_THREADS, 0, st>>>(counts, R, local, sums, tail + S_TOTAL, arrival, nopeers, tail + S_XINFO);
         // emit + D2H of the offsets in 4 slices so that the copy back overlaps the rest of the emit
         const uint32_t nsl = R >= 400000 ? 4 : 1;
         for (uint32_t c = 0; c < nsl; ++c) {

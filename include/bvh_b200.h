@@ -258,6 +258,31 @@ int bvhgpu_traverse_ordered_f32x3(bvhgpu_tree3f* tree, const bvh_ray3f* rays, si
 int bvhgpu_traverse_ordered_f64x3(bvhgpu_tree3d* tree, const bvh_ray3d* rays, size_t nrays, int ascending,
                                   uint32_t* offsets, uint32_t* hits, double* dists, size_t cap, size_t* total);
 
+/* ---- closest hit with distance pruning: what callers of the reference build from Bvh::traverse (or the distance
+ * iterators, src/bvh/distance_traverse.rs, child_distance_traverse.rs) + Ray::intersects_triangle (src/ray/ray_impl.rs:154-213; the
+ * loop itself: src/bvh/iter.rs:330-365) -- per ray, front to back, subtrees entered behind the best hit are never opened.
+ *   use_triangles == 0: out_shape = the shape whose AABB the ray enters first, key (entry distance as
+ *       Ray::intersection_slice_for_aabb, src/ray/ray_impl.rs:118-145, then DFS order) = the first element of a perfectly sorted
+ *       nearest_traverse_iterator; out_dist = that entry distance.  Exact (ties are never pruned).
+ *   use_triangles != 0: the triangles given with bvhgpu_tree_set_triangles_* (9 scalars per shape: a, b, c; shape i's AABB must
+ *       contain triangle i); out_shape = the triangle with the smallest Moeller-Trumbore distance (backface culled, the reference's
+ *       operation order, no FMA), ties to the lower index; out_dist = that distance, out_uv (may be NULL) = its u, v.  A subtree is
+ *       skipped when its entry distance exceeds best * (1 + 2^-16): results can differ from the unpruned minimum only between hits
+ *       whose distances agree to ~1e-5 relative.
+ * No hit: out_shape = BVHGPU_INVALID_INDEX, out_dist = +inf. */
+int bvhgpu_tree_set_triangles_f32x3(bvhgpu_tree3f* tree, const float* triangles, size_t n);
+int bvhgpu_tree_set_triangles_f64x3(bvhgpu_tree3d* tree, const double* triangles, size_t n);
+int bvhgpu_tree_set_triangles_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_triangles, size_t n);
+int bvhgpu_tree_set_triangles_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_triangles, size_t n);
+int bvhgpu_closest_hit_f32x3(bvhgpu_tree3f* tree, const bvh_ray3f* rays, size_t nrays, int use_triangles,
+                             uint32_t* out_shape, float* out_dist, float* out_uv);
+int bvhgpu_closest_hit_f64x3(bvhgpu_tree3d* tree, const bvh_ray3d* rays, size_t nrays, int use_triangles,
+                             uint32_t* out_shape, double* out_dist, double* out_uv);
+int bvhgpu_closest_hit_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_rays, int ray_layout, size_t nrays, int use_triangles,
+                                 void* dev_shape, void* dev_dist, void* dev_uv);
+int bvhgpu_closest_hit_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_rays, int ray_layout, size_t nrays, int use_triangles,
+                                 void* dev_shape, void* dev_dist, void* dev_uv);
+
 /* ---- nearest_to: batched Bvh::nearest_to (src/bvh/bvh_impl.rs:221-238, src/bvh/bvh_node.rs:327-372) and
  * FlatBvh::nearest_to (src/flat_bvh.rs:513-562).  The reference calls the shape's own PointDistance::distance_squared at the
  * leaves (user code), so there are two forms.  `points`: 3 T per query point, host pointers.

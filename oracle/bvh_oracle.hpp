@@ -165,6 +165,33 @@ template <class T> inline bool ray_slice_for_aabb(const Ray3<T>& ray, const Aabb
     return !(tmin_out > tmax) ;
 }
 
+// Ray::intersects_triangle (src/ray/ray_impl.rs:154-213): Moeller-Trumbore with backface culling.  [3p] nalgebra: cross =
+// (a.y*b.z - a.z*b.y, a.z*b.x - a.x*b.z, a.x*b.y - a.y*b.x), 3-term dot (a.x*b.x + a.y*b.y) + a.z*b.z.  Returns the distance
+// (+inf = no hit); u, v as the reference leaves them.
+template <class T> inline void cross3(const T a[3], const T b[3], T o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <class T> inline T ray_intersects_triangle(const Ray3<T>& ray, const T a[3], const T b[3], const T c[3], T& u_out, T& v_out) {
+    const T INF = std::numeric_limits<T>::infinity(), EPS = std::numeric_limits<T>::epsilon();
+    T ab[3], ac[3], uvec[3], ao[3], vvec[3];
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
+    cross3(ray.direction, ac, uvec);
+    const T det = (ab[0] * uvec[0] + ab[1] * uvec[1]) + ab[2] * uvec[2];
+    u_out = T(0); v_out = T(0);
+    if (det < EPS) return INF;                                   // :178-180 (NaN det falls through, as in the reference)
+    const T inv_det = T(1) / det;
+    for (int k = 0; k < 3; ++k) ao[k] = ray.origin[k] - a[k];
+    const T u = ((ao[0] * uvec[0] + ao[1] * uvec[1]) + ao[2] * uvec[2]) * inv_det;
+    u_out = u;
+    if (!(u >= T(0) && u <= T(1))) return INF;                   // :191-193 RangeInclusive::contains
+    cross3(ao, ab, vvec);
+    const T v = ((ray.direction[0] * vvec[0] + ray.direction[1] * vvec[1]) + ray.direction[2] * vvec[2]) * inv_det;
+    v_out = v;
+    if (v < T(0) || u + v > T(1)) return INF;                    // :201-203
+    const T dist = ((ac[0] * vvec[0] + ac[1] * vvec[1]) + ac[2] * vvec[2]) * inv_det;
+    return dist > EPS ? dist : INF;                              // :207-211
+}
+
 // Other IntersectsAabb implementors (src/aabb/intersection.rs:35-45, src/ball.rs:85-106).
 // Query records: kind 1 = Aabb {min,max} (6 T), kind 2 = Point (3 T), kind 3 = Ball {center, radius} (4 T).
 template <class T> inline bool aabb_intersects_aabb(const Aabb3<T>& q, const Aabb3<T>& b) {          // aabb_impl.rs:240-248
@@ -971,6 +998,33 @@ template <class T> inline void recount(DynBvh<T>& b) {
 // ----------------------------------------------------------------------------
 // Fixtures (src/testbase.rs).
 // ----------------------------------------------------------------------------
+// ---- closest hit, the way callers of the reference compute it ------------------------------------------------
+// kind 0: the shape whose AABB the ray enters first = the first element of a PERFECTLY sorted nearest_traverse_iterator
+//         (src/bvh/distance_traverse.rs is best-effort); candidates = Bvh::traverse, key = (entry distance, DFS order).
+// kind 1: triangle soups: candidates = Bvh::traverse(ray), each tested with Ray::intersects_triangle, minimum distance; ties go to
+//         the lower shape index.  tris: 9 T per shape.  Returns U32_MAX / +inf when nothing is hit.
+template <class T>
+inline uint32_t closest_hit(const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes, const T* tris, int kind, const Ray3<T>& ray,
+                            T& dist_out, T& u_out, T& v_out) {
+    std::vector<uint32_t> cand;
+    traverse_recursive(nodes, n_nodes, shapes, ray, cand);
+    uint32_t best = U32_MAX;
+    T bd = std::numeric_limits<T>::infinity(), bu = T(0), bv = T(0);
+    for (uint32_t s : cand) {
+        if (kind == 0) {
+            T t0, t1;
+            if (!ray_slice_for_aabb(ray, shapes[s], t0, t1)) continue;      // (cannot happen for a tight tree; kept for from_nodes trees)
+            if (best == U32_MAX || t0 < bd) { best = s; bd = t0; }
+        } else {
+            T u, v;
+            const T d = ray_intersects_triangle(ray, tris + 9 * (size_t)s, tris + 9 * (size_t)s + 3, tris + 9 * (size_t)s + 6, u, v);
+            if (d < bd || (d == bd && d < std::numeric_limits<T>::infinity() && s < best)) { best = s; bd = d; bu = u; bv = v; }
+        }
+    }
+    dist_out = bd; u_out = bu; v_out = bv;
+    return best;
+}
+
 inline uint64_t splitmix64(uint64_t& x) {                       // testbase.rs:560-566
     x += 0x9E3779B97F4A7C15ull;
     uint64_t z = x;

@@ -340,6 +340,38 @@ def ray_slice(ray, aabb, prec="f32"):
     return (out[0], out[1]) if ok else None
 
 
+def ray_triangle(ray, tri9, prec="f32"):
+    """Ray::intersects_triangle (ray_impl.rs:154-213): (distance, u, v); distance = inf for a miss / back face."""
+    d = _DT[prec]
+    ray = np.ascontiguousarray(ray, dtype=d["ray"]).reshape(1)
+    tri = np.ascontiguousarray(tri9, dtype=d["f"]).reshape(9)
+    uv = np.zeros(2, dtype=d["f"])
+    fn = getattr(lib(), f"orc_ray_triangle_{prec}")
+    fn.restype = C.c_float if prec == "f32" else C.c_double
+    dist = fn(_p(ray), _p(tri), _p(uv))
+    return d["f"](dist), uv[0], uv[1]
+
+
+CLOSEST_AABB, CLOSEST_TRIANGLE = 0, 1
+
+
+def closest_hit(nodes, shapes, rays, tris=None, prec="f32"):
+    """What a caller of the reference computes per ray: candidates = Bvh::traverse; tris is None: the shape whose AABB is entered first
+    (key: entry distance, then DFS order); else Ray::intersects_triangle on every candidate, minimum distance (ties: lower index).
+    Returns (shape u32 [U32_MAX = none], distance [inf = none], uv (n, 2))."""
+    d = _DT[prec]
+    nodes = np.ascontiguousarray(nodes, dtype=d["node"])
+    shapes = np.ascontiguousarray(shapes, dtype=d["aabb"])
+    rays = np.ascontiguousarray(rays, dtype=d["ray"])
+    tr = None if tris is None else np.ascontiguousarray(tris, dtype=d["f"]).reshape(-1, 9)
+    out_s = np.zeros(len(rays), dtype=np.uint32)
+    out_d = np.zeros(len(rays), dtype=d["f"])
+    out_uv = np.zeros((len(rays), 2), dtype=d["f"])
+    getattr(lib(), f"orc_closest_hit_batch_{prec}")(C.c_int(CLOSEST_AABB if tris is None else CLOSEST_TRIANGLE), _p(nodes), C.c_uint32(len(nodes)), _p(shapes), _p(tr),
+                                                    _p(rays), C.c_uint64(len(rays)), _p(out_s), _p(out_d), _p(out_uv))
+    return out_s, out_d, out_uv
+
+
 def aligned_boxes(prec="f32") -> np.ndarray:
     out = np.zeros(21, dtype=_DT[prec]["aabb"])
     getattr(lib(), f"orc_aligned_boxes_{prec}")(_p(out))

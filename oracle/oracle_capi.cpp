@@ -205,6 +205,18 @@ static uint64_t g_last_build_ns = 0;
         offsets[nq] = total;                                                                                 \
         return total;                                                                                        \
     }                                                                                                        \
+    ORC_API void orc_closest_hit_batch_##SUF(int kind, const Node<T>* nodes, uint32_t n_nodes, const Aabb3<T>* shapes, const T* tris, \
+                                             const Ray3<T>* rays, uint64_t nrays, uint32_t* out_shape, T* out_dist, T* out_uv) { \
+        for (uint64_t i = 0; i < nrays; ++i) {                                                               \
+            T d, u, v;                                                                                       \
+            out_shape[i] = closest_hit(nodes, n_nodes, shapes, tris, kind, rays[i], d, u, v);                \
+            out_dist[i] = d;                                                                                 \
+            if (out_uv) { out_uv[2 * i] = u; out_uv[2 * i + 1] = v; }                                        \
+        }                                                                                                    \
+    }                                                                                                        \
+    ORC_API T orc_ray_triangle_##SUF(const Ray3<T>* ray, const T* abc9, T* uv2) {                            \
+        return ray_intersects_triangle(*ray, abc9, abc9 + 3, abc9 + 6, uv2[0], uv2[1]);                      \
+    }                                                                                                        \
     ORC_API int orc_ray_slice_##SUF(const Ray3<T>* ray, const Aabb3<T>* aabb, T* out2) {                      \
         return ray_slice_for_aabb(*ray, *aabb, out2[0], out2[1]) ? 1 : 0;                                    \
     }                                                                                                        \

@@ -240,3 +240,83 @@ def test_fused_multi_gpu_exchange(nproc):
                         "--master-port", str(29533 + nproc), os.path.join(ROOT, "tools", "check_sharded.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("fused==nccl True  fused==oracle True") == 2 * nproc
+
+
+# ---- closest hit with distance pruning ----------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["cubes1", "boxes21", "cubes1000", "random5000", "points500", "huge300", "skew3000"])
+def test_closest_hit_aabb_mode_is_exact(api, name, prec):
+    """First AABB entered by the ray == the minimum (entry distance, DFS order) over Bvh::traverse's candidates, bit for bit -- although the
+    device prunes subtrees behind the best entry so far and walks front to back (incl. the 3 000-deep skew tree: no stack)."""
+    shapes = scene(name, prec)
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    rays = rays_for(shapes, 3000, prec, seed=17, axis_aligned=300)
+    ws, wd, _ = O.closest_hit(want.nodes, shapes, rays, prec=prec)
+    gs, gd, _ = bvh.closest_hit(rays)
+    assert np.array_equal(gs, ws)
+    assert np.array_equal(gd, wd)
+    if name.startswith("huge"):       # "no split wins" trees store EMPTY child boxes: the ordered traversal reports those (entry 0), this the shape's own AABB
+        bvh.free()
+        return
+    # cross-check against the distance-ordered traversal: its first element per ray is the same shape
+    off, hits, dists = bvh.traverse_ordered(rays, True)
+    has = off[1:] > off[:-1]
+    assert np.array_equal(has, gs != O.U32_MAX)
+    assert np.array_equal(hits[off[:-1][has]], gs[has]) and np.array_equal(dists[off[:-1][has]], gd[has])
+    bvh.free()
+
+
+def _check_triangle_closest(api, shapes, tris, rays, prec="f32"):
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    bvh.set_triangles(tris)
+    ws, wd, wuv = O.closest_hit(want.nodes, shapes, rays, tris, prec)
+    gs, gd, guv = bvh.closest_hit(rays, triangles=True)
+    same = gs == ws
+    # identical hits are identical to the bit (same Moeller-Trumbore arithmetic): distance, u, v
+    assert np.array_equal(gd[same], wd[same]) and np.array_equal(guv[same], wuv[same])
+    # the stated tolerance: a different triangle may only win where both distances agree to 2e-5 relative (pruning margin 2^-16)
+    diff = ~same
+    assert diff.mean() < 1e-3, diff.mean()
+    if diff.any():
+        assert np.all(np.isfinite(gd[diff]) & np.isfinite(wd[diff]))
+        assert np.all(np.abs(gd[diff] - wd[diff]) <= 2e-5 * np.abs(wd[diff]))
+    bvh.free()
+    return int((ws != O.U32_MAX).sum())
+
+
+def test_closest_hit_triangles_cubes(api):
+    shapes, tris = O.create_n_cubes(2000, want_tris=True)
+    rays = rays_for(shapes, 20000, seed=23)
+    # aim a good part of the rays at cube centres so that many of them hit something
+    rng = np.random.default_rng(5)
+    centres = (shapes["min"][::12] + shapes["max"][::12]) * 0.5
+    tgt = centres[rng.integers(0, len(centres), 10000)].astype(np.float64) + rng.uniform(-0.4, 0.4, (10000, 3))
+    org = tgt + rng.normal(0, 1, (10000, 3)) * 3000
+    rays[:10000] = O.ray_new(org, tgt - org)
+    nhit = _check_triangle_closest(api, shapes, tris, rays)
+    assert nhit > 5000
+
+
+def test_closest_hit_triangles_sponza(api):
+    """Sponza (66 450 triangles): primary rays from inside the atrium; closest triangle per ray == the caller's loop over Bvh::traverse +
+    Ray::intersects_triangle (within the stated tolerance where two hits coincide)."""
+    from bvh_b200 import scenes
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sponza_tris.npz"))
+    tris = z["vertices"][z["triangles"].astype(np.int64)].astype(np.float32)
+    shapes = O.tri_aabbs(tris)
+    o, d = scenes.pinhole_rays(160, 120)
+    rays = O.ray_new(o, d)
+    nhit = _check_triangle_closest(api, shapes, tris.reshape(-1, 9), rays)
+    assert nhit > 0.5 * len(rays)
+
+
+def test_closest_hit_f64_and_empty(api):
+    shapes, tris = O.create_n_cubes(300, prec="f64", want_tris=True)
+    rays = rays_for(shapes, 5000, "f64", seed=29)
+    _check_triangle_closest(api, shapes, tris, rays, "f64")
+    e = api.Bvh.build(scene("empty"))
+    s, dist, _ = e.closest_hit(rays_for(scene("empty"), 7))
+    assert np.all(s == O.U32_MAX) and np.all(np.isinf(dist))

@@ -554,3 +554,63 @@ def test_nearest_to_property(n, seed, flat):
     for k in range(len(pts)):
         d2 = O.shape_distances_squared(shapes, pts[k])
         assert d2[int(s[k])] == d2.min() and d[k] == np.sqrt(d2.min())
+
+
+# ---- Ray::intersects_triangle (src/ray/ray_impl.rs:154-213) -----------------------------------------------------------------
+def test_oracle_ray_triangle_property_from_the_reference():
+    """The reference's own property test (ray_impl.rs:361-420, test_ray_hits_triangle), restated: a ray aimed at a point u*AB + v*AC of a
+    triangle hits it (distance < inf, u+v in [0,1]) unless it looks at the back face, in which case the distance is +inf."""
+    rng = np.random.default_rng(1234)
+    checked = 0
+    for _ in range(4000):
+        a, b, c, org = (rng.integers(-1000, 1000, 3).astype(np.float32) for _ in range(4))
+        u = int(rng.integers(0, 101)); v = min(100 - u, int(rng.integers(0, 101)))
+        uf, vf = np.float32(u / 100.0), np.float32(v / 100.0)
+        uvec, vvec = b - a, c - a
+        normal = np.cross(uvec, vvec)
+        p = a + uf * uvec + vf * vvec
+        if np.allclose(p, org):
+            continue
+        ray = O.ray_new((org,), (p - org,))
+        on_back = float(np.dot(normal.astype(np.float64), (org - a).astype(np.float64))) <= 0.0
+        dist, iu, iv = O.ray_triangle(ray, np.concatenate([a, b, c]))
+        if on_back:
+            if abs(float(np.dot(normal.astype(np.float64), (org - a).astype(np.float64)))) > 1e-3 * np.linalg.norm(normal):   # clearly behind
+                assert np.isinf(dist)
+        else:
+            inside = 0.0 <= float(iu) + float(iv) <= 1.0 and np.isfinite(dist)
+            eps = np.finfo(np.float32).eps
+            border = abs(uf) < eps or abs(uf - 1) < eps or abs(vf) < eps or abs(vf - 1) < eps or abs(uf + vf - 1) < eps
+            degenerate = np.linalg.norm(normal) < 1e-3
+            assert inside or border or degenerate, (a, b, c, org, uf, vf, dist, iu, iv)
+        checked += 1
+    assert checked > 3000
+
+
+def test_oracle_ray_triangle_kats():
+    ray = O.ray_new(((0.0, 0.0, -1.0),), ((0.0, 0.0, 1.0),))
+    d, u, v = O.ray_triangle(ray, [-1, -1, 0, 0, 1, 0, 1, -1, 0])        # front face: det > 0
+    assert d == np.float32(1.0) and u == np.float32(0.5) and v == np.float32(0.25)
+    d, u, v = O.ray_triangle(ray, [-1, -1, 0, 1, -1, 0, 0, 1, 0])        # same triangle, other winding: culled
+    assert np.isinf(d)
+    ray2 = O.ray_new(((5.0, 5.0, -1.0),), ((0.0, 0.0, 1.0),))            # misses
+    assert np.isinf(O.ray_triangle(ray2, [-1, -1, 0, 0, 1, 0, 1, -1, 0])[0])
+
+
+def test_oracle_closest_hit_equals_brute_force():
+    shapes, tris = O.create_n_cubes(60, want_tris=True)
+    res = O.build(shapes)
+    rng = np.random.default_rng(3)
+    centres = (shapes["min"][::12] + shapes["max"][::12]) * 0.5
+    tgt = centres[rng.integers(0, len(centres), 400)].astype(np.float64) + rng.uniform(-0.4, 0.4, (400, 3))
+    org = tgt + rng.normal(0, 1, (400, 3)) * 500
+    rays = O.ray_new(org, tgt - org)
+    s, d, _ = O.closest_hit(res.nodes, shapes, rays, tris)
+    assert (s != O.U32_MAX).sum() > 300
+    for i in range(0, 400, 7):                                             # brute force over ALL triangles
+        best, bd = O.U32_MAX, np.inf
+        for t in range(len(tris.reshape(-1, 9))):
+            dist = O.ray_triangle(rays[i:i + 1], tris.reshape(-1, 9)[t])[0]
+            if dist < bd:
+                best, bd = t, dist
+        assert s[i] == best and (np.isinf(bd) or d[i] == np.float32(bd))
