@@ -225,6 +225,12 @@ class Bvh:
         capi.check(getattr(capi.lib(), f"bvhgpu_flatten_{self._d['suffix']}")(self._h, _ptr(out), cap, C.byref(ln)))
         return FlatBvh(self, out[: ln.value])
 
+    def flatten_custom(self, constructor):
+        """Bvh::flatten_custom (src/flat_bvh.rs:240-251): `constructor(aabb, entry, exit, shape)` applied to every FlatNode in the
+        reference's emission order; aabb = (min[3], max[3])."""
+        f = self.flatten().nodes
+        return [constructor((f["aabb"]["min"][i], f["aabb"]["max"][i]), int(f["entry_index"][i]), int(f["exit_index"][i]), int(f["shape_index"][i])) for i in range(len(f))]
+
     def flatten_dev(self) -> int:
         """Build the FlatBvh on the device only (no host copy, asynchronous); returns its length."""
         ln = C.c_size_t(0)
@@ -389,5 +395,19 @@ class Bvh:
         rebuilt = C.c_size_t(0)
         capi.check(getattr(capi.lib(), f"bvhgpu_optimize_{self._d['suffix']}")(self._h, _ptr(aabbs), len(aabbs), C.c_double(max_growth),
                                                                               C.byref(rebuilt)))
+        self._nodes = self._node_index = None
+        return int(rebuilt.value)
+
+    def update_shapes(self, changed, shapes, max_growth: float = 1.5) -> int:
+        """Bvh::update_shapes(changed_shape_indices, shapes) (src/bvh/optimization.rs:304-315): only the changed shapes' AABBs are sent.
+        `shapes` = all shapes (objects with .aabb(), or an AABB array); max_growth <= 0: refit only.  Returns the number of shapes in
+        rebuilt subtrees; node indices must be re-read (set_bh_node_index) when it is non-zero."""
+        idx = np.ascontiguousarray(changed, dtype=np.uint32).reshape(-1)
+        if isinstance(shapes, np.ndarray):
+            fresh = np.ascontiguousarray(shapes[idx], dtype=self._d["aabb"])
+        else:
+            fresh = _gather_aabbs([shapes[int(i)] for i in idx], self.prec)
+        rebuilt = C.c_size_t(0)
+        capi.check(getattr(capi.lib(), f"bvhgpu_update_{self._d['suffix']}")(self._h, _ptr(idx), _ptr(fresh), len(idx), C.c_double(max_growth), C.byref(rebuilt)))
         self._nodes = self._node_index = None
         return int(rebuilt.value)

@@ -102,6 +102,8 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_traverse_od_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_od_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_refit_dev_{s}").argtypes = [vp, vp, sz]
+        getattr(L, f"bvhgpu_update_{s}").argtypes = [vp, vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
+        getattr(L, f"bvhgpu_update_dev_{s}").argtypes = [vp, vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
         getattr(L, f"bvhgpu_optimize_dev_{s}").argtypes = [vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
         getattr(L, f"bvhgpu_traverse_dev_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
         getattr(L, f"bvhgpu_traverse_stats_{s}").argtypes = [vp, u64p]

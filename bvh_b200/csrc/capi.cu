@@ -60,7 +60,7 @@ template <class T> static void tree_release(Tree<T>* t) {
     bvhgpu_ctx* ctx = t->ctx;
     if (ctx) {
         dfree(ctx, t->d_aabb); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
-        dfree(ctx, t->d_tris); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
+        dfree(ctx, t->d_tris); dfree(ctx, t->d_sa_base); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
     }
 }
 
@@ -464,6 +464,51 @@ static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, s
     return BVHGPU_OK;
 }
 
+// Bvh::update_shapes(changed_shape_indices, shapes): only the m changed shapes cross the boundary.  The tree is touched only after
+// the new AABBs passed the NaN / index check.  max_growth <= 0: refit only (topology kept).
+template <class T>
+static int update_impl(Tree<T>* tree, const uint32_t* changed, const typename Traits<T>::Aabb* fresh, size_t m, double max_growth, size_t* rebuilt, bool dev_input) {
+    if (!tree || (m && (!changed || !fresh))) { set_error("update: null argument"); return BVHGPU_ERR_INVALID; }
+    if (max_growth > 0.0 && !(max_growth >= 1.0)) { set_error("update: max_growth = %g, must be >= 1 (or <= 0 for a pure refit)", max_growth); return BVHGPU_ERR_INVALID; }
+    if (m > 0xFFFFFFFFull) { set_error("update: too many changed shapes"); return BVHGPU_ERR_INVALID; }
+    if (rebuilt) *rebuilt = 0;
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (m == 0 || tree->n == 0) return BVHGPU_OK;
+    Scratch scratch(ctx);
+    const uint32_t* d_changed = changed;
+    const typename Traits<T>::Aabb* d_fresh = fresh;
+    if (!dev_input) {
+        uint32_t* c = nullptr;
+        typename Traits<T>::Aabb* f = nullptr;
+        BVH_TRY(scratch.get(&c, m));
+        BVH_TRY(scratch.get(&f, m));
+        BVH_CUDA_TRY(cudaMemcpyAsync(c, changed, sizeof(uint32_t) * m, cudaMemcpyHostToDevice, ctx->stream));
+        BVH_CUDA_TRY(cudaMemcpyAsync(f, fresh, sizeof(*fresh) * m, cudaMemcpyHostToDevice, ctx->stream));
+        d_changed = c; d_fresh = f;
+    }
+    uint32_t* flags = nullptr;
+    BVH_TRY(scratch.get(&flags, 2));
+    BVH_CUDA_TRY(cudaMemsetAsync(flags, 0, 2 * sizeof(uint32_t), ctx->stream));
+    BVH_TRY(update_changed<T>(tree, d_changed, d_fresh, (uint32_t)m, flags));
+    uint32_t* h = ctx->h_pinned + 208;
+    BVH_CUDA_TRY(cudaMemcpyAsync(h, flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h[1]) { set_error("update: a changed shape index is >= %u; the tree was left unchanged", tree->n); return BVHGPU_ERR_INVALID; }
+    if (h[0]) { set_error("update: NaN coordinate in a new AABB; the tree was left unchanged"); return BVHGPU_ERR_NAN; }
+    BVH_TRY(update_scatter<T>(tree, d_changed, d_fresh, (uint32_t)m));
+    BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
+    if (max_growth > 0.0) BVH_TRY(optimize(tree, max_growth)); else BVH_TRY(refit(tree));
+    tree->status_pending = true;
+    if (dev_input && !rebuilt) return BVHGPU_OK;                        // asynchronous from here on
+    BuildStatus hs;
+    BVH_CUDA_TRY(cudaMemcpyAsync(&hs, tree->d_status, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_TRY(resolve_status(tree));
+    if (rebuilt) *rebuilt = hs.rebuilt;
+    return BVHGPU_OK;
+}
+
 }  // namespace bvhb200
 
 using namespace bvhb200;
@@ -810,6 +855,12 @@ BVH_EXPORT int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p) {
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_optimize_dev_##SUF(TREE* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt) { \
         return optimize_impl<T>(tree, (const AABB*)dev_aabbs, n, max_growth, rebuilt, true);                            \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_update_##SUF(TREE* tree, const uint32_t* changed, const AABB* changed_aabbs, size_t m, double max_growth, size_t* rebuilt) { \
+        return update_impl<T>(tree, changed, changed_aabbs, m, max_growth, rebuilt, false);                              \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_update_dev_##SUF(TREE* tree, const void* dev_changed, const void* dev_changed_aabbs, size_t m, double max_growth, size_t* rebuilt) { \
+        return update_impl<T>(tree, (const uint32_t*)dev_changed, (const AABB*)dev_changed_aabbs, m, max_growth, rebuilt, true); \
     }
 
 DEFINE_API(float, f32x3, bvhgpu_tree3f, bvh_aabb3f, bvh_ray3f, bvh_node3f, bvh_flat3f)

@@ -279,15 +279,40 @@ __global__ void __launch_bounds__(256) leaf_order_kernel(const uint32_t* __restr
     if (s < n) idx[node_start[node_index[s]]] = s;
 }
 
+// After a rebuild the nodes of the rebuilt subtrees get a new surface-area baseline; every other node keeps the one it had when
+// it was last built (so slow drift accumulates against it instead of being forgiven at every call).
+template <class T>
+__global__ void __launch_bounds__(256) rebase_kernel(const typename Traits<T>::Node* __restrict__ nodes, const uint32_t* __restrict__ roots,
+                                                     const uint32_t* __restrict__ n_roots, T* __restrict__ sa_base) {
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5), nr = *n_roots;
+    for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nr; k += warps) {
+        const uint32_t r = roots[k];
+        const uint32_t cnt = __ldcg(&nodes[r].shape);                        // shapes below the root: its subtree is the node range [r, r + 2 cnt - 1)
+        for (uint32_t i = r + lane_id(); i < r + 2 * cnt - 1; i += 32) {
+            const typename Traits<T>::Node& nd = nodes[i];
+            if (__ldcg(&nd.child_l) == BVH_INVALID) { sa_base[i] = T(0); continue; }
+            T mn[3], mx[3];
+            for (int c = 0; c < 3; ++c) { mn[c] = min_t(__ldcg(&nd.l_aabb.min[c]), __ldcg(&nd.r_aabb.min[c])); mx[c] = max_t(__ldcg(&nd.l_aabb.max[c]), __ldcg(&nd.r_aabb.max[c])); }
+            sa_base[i] = surface_area(mn, mx);
+        }
+    }
+}
+
 template <class T> int optimize(Tree<T>* tree, double max_growth) {
     bvhgpu_ctx* ctx = tree->ctx;
     if (tree->n < 3) return refit(tree);                                // one or two shapes: nothing a rebuild could change
     cudaStream_t st = ctx->stream;
     const uint32_t n = tree->n, nn = tree->n_nodes;
-    T *sa_old = nullptr, *cb = nullptr;
+    T* cb = nullptr;
     uint8_t* bad = nullptr;
     uint32_t *roots = nullptr, *n_roots = nullptr, *idx0 = nullptr, *arrivals = nullptr;
-    BVH_TRY(dalloc_t(ctx, &sa_old, nn));
+    const unsigned gn0 = (nn + 255) / 256;
+    if (!tree->d_sa_base) {                                             // first optimize on this tree: the baseline is the tree as built
+        BVH_TRY(dalloc(ctx, &tree->d_sa_base, sizeof(T) * nn));
+        node_sa_kernel<T><<<gn0, 256, 0, st>>>(tree->d_nodes, nn, reinterpret_cast<T*>(tree->d_sa_base));
+        ctx->launches++;
+    }
+    T* sa_old = reinterpret_cast<T*>(tree->d_sa_base);
     BVH_TRY(dalloc_t(ctx, &cb, (size_t)nn * 6));
     BVH_TRY(dalloc_t(ctx, &bad, nn));
     BVH_TRY(dalloc_t(ctx, &roots, n));
@@ -297,21 +322,68 @@ template <class T> int optimize(Tree<T>* tree, double max_growth) {
     BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * nn, st));
     BVH_CUDA_TRY(cudaMemsetAsync(n_roots, 0, sizeof(uint32_t), st));
     const unsigned gn = (nn + 255) / 256, gs = (n + 255) / 256;
-    node_sa_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, sa_old);
     refit_kernel<T, true><<<gs, 256, 0, st>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, n, arrivals, cb);
     mark_bad_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, sa_old, (T)max_growth, bad);
     select_roots_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, bad, roots, n_roots);
     leaf_order_kernel<<<gs, 256, 0, st>>>(tree->d_node_index, tree->d_node_start, n, idx0);
-    ctx->launches += 5;
+    ctx->launches += 4;
     BVH_CUDA_TRY(cudaGetLastError());
     BVH_TRY(rebuild_subtrees(ctx, tree, roots, n_roots, cb, idx0));
-    dfree(ctx, sa_old); dfree(ctx, cb); dfree(ctx, bad); dfree(ctx, roots); dfree(ctx, n_roots); dfree(ctx, idx0); dfree(ctx, arrivals);
+    rebase_kernel<T><<<std::max(1, std::min(ctx->sm_count * 4, (int)n)), 256, 0, st>>>(tree->d_nodes, roots, n_roots, sa_old);
+    ctx->launches++;
+    dfree(ctx, cb); dfree(ctx, bad); dfree(ctx, roots); dfree(ctx, n_roots); dfree(ctx, idx0); dfree(ctx, arrivals);
     BVH_TRY(build_traversal_records(tree));
     if (tree->have_flat) BVH_TRY(build_flat(tree));
     return BVHGPU_OK;
 }
 
+// ---- update: Bvh::update_shapes(changed_shape_indices, shapes) (src/bvh/optimization.rs:304-315) --------------------------------
+// Only the changed shapes cross the boundary: m indices + their m new AABBs.  check: NaN / index range, BEFORE anything is written.
+template <class T>
+__global__ void __launch_bounds__(256) update_check_kernel(const uint32_t* __restrict__ changed, const typename Traits<T>::Aabb* __restrict__ fresh,
+                                                           uint32_t m, uint32_t n, uint32_t* __restrict__ flags /* [0] NaN, [1] index out of range */) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (changed[i] >= n) atomicExch(flags + 1, 1u);
+    const T* p = reinterpret_cast<const T*>(fresh + i);
+    bool nan = false;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) nan |= p[c] != p[c];
+    if (nan) atomicExch(flags, 1u);
+}
+template <class T>
+__global__ void __launch_bounds__(256) update_scatter_kernel(const uint32_t* __restrict__ changed, const typename Traits<T>::Aabb* __restrict__ fresh,
+                                                             uint32_t m, typename Traits<T>::DAabb* __restrict__ aabb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const T* p = reinterpret_cast<const T*>(fresh + i);
+    typename Traits<T>::DAabb d;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { d.min[c] = p[c]; d.max[c] = p[3 + c]; }
+    if constexpr (sizeof(T) == 4) { d.pad0 = 0; d.pad1 = 0; }
+    aabb[changed[i]] = d;                                               // an index listed twice: one of its AABBs wins (the reference would use shapes[i] for both)
+}
+template <class T>
+int update_changed(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m, uint32_t* d_flags) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    const unsigned g = (m + 255) / 256;
+    update_check_kernel<T><<<g, 256, 0, ctx->stream>>>(d_changed, d_fresh, m, tree->n, d_flags);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+template <class T>
+int update_scatter(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    update_scatter_kernel<T><<<(m + 255) / 256, 256, 0, ctx->stream>>>(d_changed, d_fresh, m, tree->d_aabb);
+    ctx->launches++;
+    BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
 #define INST(T)                                           \
+    template int update_changed<T>(Tree<T>*, const uint32_t*, const typename Traits<T>::Aabb*, uint32_t, uint32_t*); \
+    template int update_scatter<T>(Tree<T>*, const uint32_t*, const typename Traits<T>::Aabb*, uint32_t); \
     template int optimize<T>(Tree<T>*, double);           \
     template int build_traversal_records<T>(Tree<T>*);    \
     template int build_flat<T>(Tree<T>*);                 \

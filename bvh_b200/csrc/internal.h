@@ -85,6 +85,7 @@ template <class T> struct Tree {
     uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
     typename Tr::TNode* d_tnodes = nullptr;   // [n_trec] traversal records
     uint32_t n_trec = 0;
+    void* d_sa_base = nullptr;                // [2n-1] surface area of every inner node when it was last (re)built: baseline of bvhgpu_optimize / update
     void* d_tris = nullptr;                   // [n] triangle vertices (padded), optional: bvhgpu_tree_set_triangles_*
     typename Tr::Flat* d_flat = nullptr;      // [n_flat] reference-layout FlatBvh (built on demand)
     size_t n_flat = 0;
@@ -156,6 +157,9 @@ template <class T> int build_flat(Tree<T>* tree);                // d_flat (refe
 template <class T> int sah_cost(Tree<T>* tree, double* out2);
 template <class T> int refit(Tree<T>* tree);                     // recompute child AABBs bottom-up from d_aabb
 template <class T> int optimize(Tree<T>* tree, double max_growth);   // refit + exact rebuild of the degraded subtrees
+// update_shapes form: validate (flags[0] NaN, flags[1] bad index) / scatter m changed AABBs (device pointers) into tree->d_aabb
+template <class T> int update_changed(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m, uint32_t* d_flags);
+template <class T> int update_scatter(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m);
 
 // ---- traverse.cu ----
 // d_rays: rays on the device; fmt: BVHGPU_RAYS_FULL (9 scalars: the C-ABI Ray) or BVHGPU_RAYS_OD (6 scalars: origin, direction).

@@ -335,6 +335,15 @@ int bvhgpu_optimize_f32x3(bvhgpu_tree3f* tree, const bvh_aabb3f* aabbs, size_t n
 int bvhgpu_optimize_f64x3(bvhgpu_tree3d* tree, const bvh_aabb3d* aabbs, size_t n, double max_growth, size_t* rebuilt);
 int bvhgpu_optimize_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt);
 int bvhgpu_optimize_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_aabbs, size_t n, double max_growth, size_t* rebuilt);
+/* The same with Bvh::update_shapes' own signature (src/bvh/optimization.rs:304-315: the indices of the changed shapes + the shapes):
+ * `changed[i]` is a shape index, `changed_aabbs[i]` its new AABB -- only the m changed shapes cross the boundary (10 M f64 shapes,
+ * 1 % moved: 5 MB instead of 480 MB).  max_growth >= 1: refit + rebuild of the degraded subtrees as bvhgpu_optimize_*;
+ * max_growth <= 0: refit only.  Indices >= n or NaN AABBs are rejected before the tree is touched.  Growth is judged against the
+ * surface area every node had when it was last (re)built, so slow drift over many calls adds up and is rebuilt eventually. */
+int bvhgpu_update_f32x3(bvhgpu_tree3f* tree, const uint32_t* changed, const bvh_aabb3f* changed_aabbs, size_t m, double max_growth, size_t* rebuilt);
+int bvhgpu_update_f64x3(bvhgpu_tree3d* tree, const uint32_t* changed, const bvh_aabb3d* changed_aabbs, size_t m, double max_growth, size_t* rebuilt);
+int bvhgpu_update_dev_f32x3(bvhgpu_tree3f* tree, const void* dev_changed, const void* dev_changed_aabbs, size_t m, double max_growth, size_t* rebuilt);
+int bvhgpu_update_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_changed, const void* dev_changed_aabbs, size_t m, double max_growth, size_t* rebuilt);
 
 #ifdef __cplusplus
 }

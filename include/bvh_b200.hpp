@@ -24,6 +24,7 @@
 #include <string>
 #include <type_traits>
 #include <vector>
+#include <utility>
 
 #include "bvh_b200.h"
 
@@ -95,6 +96,9 @@ template <> struct Abi<float> {
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f32x3(t, a, n); }
     static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f32x3(t, a, n, g, r); }
     static int candidates(tree* t, const float* p, size_t n, uint32_t* off, uint32_t* c, size_t cap, size_t* tot) { return bvhgpu_nearest_candidates_f32x3(t, p, n, off, c, cap, tot); }
+    static int update(tree* t, const uint32_t* c, const aabb* a, size_t m, double g, size_t* r) { return bvhgpu_update_f32x3(t, c, a, m, g, r); }
+    static int set_triangles(tree* t, const float* abc, size_t n) { return bvhgpu_tree_set_triangles_f32x3(t, abc, n); }
+    static int closest(tree* t, const ray* r, size_t n, int tri, uint32_t* s, float* d, float* uv) { return bvhgpu_closest_hit_f32x3(t, r, n, tri, s, d, uv); }
 };
 template <> struct Abi<double> {
     using aabb = bvh_aabb3d; using ray = bvh_ray3d; using node = bvh_node3d; using flat = bvh_flat3d; using tree = bvhgpu_tree3d;
@@ -107,6 +111,9 @@ template <> struct Abi<double> {
     static int refit(tree* t, const aabb* a, size_t n) { return bvhgpu_refit_f64x3(t, a, n); }
     static int optimize(tree* t, const aabb* a, size_t n, double g, size_t* r) { return bvhgpu_optimize_f64x3(t, a, n, g, r); }
     static int candidates(tree* t, const double* p, size_t n, uint32_t* off, uint32_t* c, size_t cap, size_t* tot) { return bvhgpu_nearest_candidates_f64x3(t, p, n, off, c, cap, tot); }
+    static int update(tree* t, const uint32_t* c, const aabb* a, size_t m, double g, size_t* r) { return bvhgpu_update_f64x3(t, c, a, m, g, r); }
+    static int set_triangles(tree* t, const double* abc, size_t n) { return bvhgpu_tree_set_triangles_f64x3(t, abc, n); }
+    static int closest(tree* t, const ray* r, size_t n, int tri, uint32_t* s, double* d, double* uv) { return bvhgpu_closest_hit_f64x3(t, r, n, tri, s, d, uv); }
 };
 struct Ctx {
     bvhgpu_ctx* h = nullptr;
@@ -218,6 +225,16 @@ template <class T> class Bvh {
         return f;
     }
 
+    // Bvh::flatten_custom (src/flat_bvh.rs:96-143, 240-251): the caller's constructor is applied to (aabb, entry, exit, shape) of every
+    // FlatNode, in the reference's emission order -- the array is the device-built FlatBvh, the constructor runs on the host.
+    template <class F> auto flatten_custom(const F& constructor) const -> std::vector<decltype(constructor(std::declval<const Aabb<T>&>(), uint32_t(), uint32_t(), uint32_t()))> {
+        const FlatBvh<T> f = flatten();
+        std::vector<decltype(constructor(std::declval<const Aabb<T>&>(), uint32_t(), uint32_t(), uint32_t()))> out;
+        out.reserve(f.nodes.size());
+        for (const auto& nd : f.nodes) out.push_back(constructor(nd.aabb, nd.entry_index, nd.exit_index, nd.shape_index));
+        return out;
+    }
+
     // Batched traversal: CSR (offsets[nrays+1], shape indices in the reference's DFS order).
     void traverse_batch(const std::vector<Ray<T>>& rays, std::vector<uint32_t>& offsets, std::vector<uint32_t>& hits,
                         int mode = BVHGPU_TRAVERSE_BVH) const {
@@ -284,6 +301,32 @@ template <class T> class Bvh {
             for (size_t i = 0; i < shapes.size(); ++i) shapes[i].set_bh_node_index(idx[i]);
         }
         return rebuilt;
+    }
+    // Bvh::update_shapes with its own signature (src/bvh/optimization.rs:304-315): the indices of the changed shapes + the shapes.
+    // Only the changed shapes' AABBs cross the boundary.  max_growth <= 0: refit only.
+    template <class Shape> size_t update_shapes(const std::vector<size_t>& changed_shape_indices, std::vector<Shape>& shapes, double max_growth = 1.5) {
+        std::vector<uint32_t> idx(changed_shape_indices.size());
+        std::vector<typename A::aabb> boxes(changed_shape_indices.size());
+        for (size_t i = 0; i < idx.size(); ++i) {
+            idx[i] = (uint32_t)changed_shape_indices[i];
+            const Aabb<T> a = shapes.at(changed_shape_indices[i]).aabb();
+            for (int k = 0; k < 3; ++k) { boxes[i].min[k] = a.min[k]; boxes[i].max[k] = a.max[k]; }
+        }
+        size_t rebuilt = 0;
+        check(A::update(tree_, idx.data(), boxes.data(), idx.size(), max_growth, &rebuilt));
+        if (rebuilt) {
+            std::vector<uint32_t> ni(shapes.size());
+            check(A::nodes(tree_, nullptr, ni.data()));
+            for (size_t i = 0; i < shapes.size(); ++i) shapes[i].set_bh_node_index(ni[i]);
+        }
+        return rebuilt;
+    }
+    // Closest hit per ray (what callers build from traverse + Ray::intersects_triangle, src/ray/ray_impl.rs:154-213).  Triangles: 9 T per
+    // shape (a, b, c), set once; triangle == false: the shape whose AABB is entered first.
+    void set_triangles(const std::vector<T>& abc9) { check(A::set_triangles(tree_, abc9.data(), abc9.size() / 9)); }
+    void closest_hit(const std::vector<Ray<T>>& rays, bool triangles, std::vector<uint32_t>& shape, std::vector<T>& distance) const {
+        shape.assign(rays.size(), 0); distance.assign(rays.size(), T(0));
+        check(A::closest(tree_, reinterpret_cast<const typename A::ray*>(rays.data()), rays.size(), triangles ? 1 : 0, shape.data(), distance.data(), nullptr));
     }
     size_t num_shapes() const { return n_; }
 

@@ -78,6 +78,15 @@ int main() {
         traverse_some_built_bh(boxes, bvh);
         auto flat = bvh.flatten();
         REQUIRE(flat.size() == 3 * boxes.size() - 2);
+        {   // flatten_custom (flat_bvh.rs:214-251): a caller-defined node type built by a caller-defined constructor
+            struct CustomStruct { TAabb3 aabb; uint32_t entry_index, exit_index, shape_index; int tag; };
+            auto custom = bvh.flatten_custom([](const TAabb3& aabb, uint32_t entry, uint32_t exit, uint32_t shape) { return CustomStruct{aabb, entry, exit, shape, 42}; });
+            REQUIRE(custom.size() == flat.size());
+            for (size_t i = 0; i < custom.size(); ++i) {
+                REQUIRE(custom[i].tag == 42 && custom[i].entry_index == flat.nodes[i].entry_index && custom[i].exit_index == flat.nodes[i].exit_index);
+                REQUIRE(custom[i].shape_index == flat.nodes[i].shape_index && custom[i].aabb == flat.nodes[i].aabb);
+            }
+        }
         traverse_some_built_bh(boxes, flat);
         // iterator twin (iter.rs:269-308)
         auto it = bvh.traverse_iterator(TRay3({6.0f, 0.5f, 0.0f}, {-2.0f, -1.0f, 0.0f}), boxes);

@@ -320,3 +320,84 @@ def test_closest_hit_f64_and_empty(api):
     e = api.Bvh.build(scene("empty"))
     s, dist, _ = e.closest_hit(rays_for(scene("empty"), 7))
     assert np.all(s == O.U32_MAX) and np.all(np.isinf(dist))
+
+
+# ---- Bvh::update_shapes form: changed indices + their new AABBs ---------------------------------------------------------------
+@pytest.mark.parametrize("name,prec,frac", [("cubes1000", "f32", 0.02), ("random5000", "f32", 0.10), ("random3000", "f64", 0.05)])
+def test_update_shapes_equals_optimize_with_all_aabbs(api, name, prec, frac):
+    """bvhgpu_update_* (only the changed shapes cross the boundary, optimization.rs:304-315's signature) == bvhgpu_optimize_* fed with
+    the AABBs of ALL shapes: same node array; and with max_growth <= 0 == bvhgpu_refit_*."""
+    shapes = scene(name, prec).copy()
+    F = shapes["min"].dtype
+    rng = np.random.default_rng(31)
+    m = max(1, int(len(shapes) * frac))
+    moved = rng.choice(len(shapes), m, replace=False)
+    ext = float(shapes["max"].max() - shapes["min"].min())
+    delta = rng.uniform(-ext / 8, ext / 8, (m, 3)).astype(F)
+    new = shapes.copy()
+    new["min"][moved] += delta
+    new["max"][moved] += delta
+    a, b = api.Bvh.build(shapes, prec=prec), api.Bvh.build(shapes, prec=prec)
+    ra = a.optimize(new, 1.5)
+    rb = b.update_shapes(moved, new, 1.5)
+    assert ra == rb
+    assert np.array_equal(a.nodes.view(np.uint8), b.nodes.view(np.uint8)) and np.array_equal(a.node_index, b.node_index)
+    assert O.is_consistent(b.nodes, new, prec) and O.is_tight(b.nodes, prec)
+    c, d = api.Bvh.build(shapes, prec=prec), api.Bvh.build(shapes, prec=prec)
+    c.refit(new)
+    assert d.update_shapes(moved, new, 0.0) == 0
+    assert np.array_equal(c.nodes.view(np.uint8), d.nodes.view(np.uint8))
+    for t in (a, b, c, d):
+        t.free()
+
+
+def test_update_shapes_rejects_bad_input_untouched(api):
+    from bvh_b200 import capi
+
+    shapes = scene("cubes1000").copy()
+    bvh = api.Bvh.build(shapes)
+    before = bvh.nodes.copy()
+    bad = shapes.copy()
+    bad["max"][10][2] = np.nan
+    with pytest.raises(capi.BvhGpuError) as e:
+        bvh.update_shapes([3, 10, 11], bad)
+    assert e.value.status == capi.ERR_NAN
+    idx = np.array([1, len(shapes)], dtype=np.uint32)
+    fresh = shapes[[1, 2]]
+    with pytest.raises(capi.BvhGpuError) as e:
+        capi.check(capi.lib().bvhgpu_update_f32x3(bvh._h, _p(idx), _p(fresh), 2, C.c_double(1.5), None))
+    assert e.value.status == capi.ERR_INVALID
+    bvh._nodes = None
+    assert np.array_equal(before.view(np.uint8), bvh.nodes.view(np.uint8))
+    bvh.free()
+
+
+def test_slow_drift_is_rebuilt_eventually(api):
+    """Growth is judged against the surface area a node had when it was last (re)built, not against the previous call: a cluster that
+    drifts away by a little per frame (never x1.5 in one step) must still be rebuilt, and the tree must stay as good as the oracle's
+    update_shapes on the same frames (SAH cost within the stated 1.10)."""
+    shapes = scene("cubes1000").copy()
+    bvh = api.Bvh.build(shapes)
+    ob = O.build(shapes)
+    ref_nodes, ref_index = ob.nodes.copy(), ob.node_index.copy()
+    rng = np.random.default_rng(41)
+    movers = rng.choice(len(shapes) // 12, 40, replace=False)            # 40 whole cubes (12 triangles each) drift together
+    idx = (movers[:, None] * 12 + np.arange(12)[None, :]).reshape(-1).astype(np.uint32)
+    direction = rng.normal(0, 1, (len(movers), 3)).astype(np.float32)
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    total_rebuilt, per_call = 0, []
+    for frame in range(40):
+        step = np.repeat(direction * np.float32(400.0), 12, axis=0)      # << scene extent (200 000) per frame
+        shapes["min"][idx] += step
+        shapes["max"][idx] += step
+        r = bvh.update_shapes(idx, shapes, 1.5)
+        per_call.append(r)
+        total_rebuilt += r
+        ref_nodes, ref_index = O.update_shapes(ref_nodes, ref_index, shapes, idx)
+    assert total_rebuilt > 0, per_call
+    nodes = bvh.nodes
+    assert O.is_consistent(nodes, shapes) and O.is_tight(nodes)
+    c_gpu, c_ref = bvh.sah_cost()[0], O.sah_cost(ref_nodes)[0]
+    c_fresh = O.sah_cost(O.build(shapes).nodes)[0]
+    assert c_gpu <= 1.10 * c_ref, (c_gpu, c_ref, c_fresh, per_call)
+    bvh.free()
