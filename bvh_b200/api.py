@@ -23,7 +23,7 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import capi
-from .dtypes import BY_PREC, U32_MAX
+from .dtypes import BY_PREC, BY_PREC_2D, U32_MAX
 
 
 def _ptr(a):
@@ -411,3 +411,60 @@ class Bvh:
         capi.check(getattr(capi.lib(), f"bvhgpu_update_{self._d['suffix']}")(self._h, _ptr(idx), _ptr(fresh), len(idx), C.c_double(max_growth), C.byref(rebuilt)))
         self._nodes = self._node_index = None
         return int(rebuilt.value)
+
+
+class Bvh2:
+    """Device-resident Bvh<T,2> (the reference is generic in the dimension): build / nodes / flatten / traverse for 2-D AABBs and rays
+    (bvhgpu_*_f32x2 / _f64x2).  Rays: structured array with 2-component origin, direction (normalised), inv_direction."""
+
+    def __init__(self, handle, prec: str, ctx: Context, n: int):
+        self._h, self.prec, self.ctx, self._d, self.n = handle, prec, ctx, BY_PREC_2D[prec], n
+
+    @classmethod
+    def build(cls, aabbs, prec: str = "f32", ctx: Context | None = None, mode: int = capi.BUILD_EXACT_SAH) -> "Bvh2":
+        ctx = ctx or Context.default()
+        d = BY_PREC_2D[prec]
+        a = np.ascontiguousarray(aabbs, dtype=d["aabb"])
+        h = C.c_void_p()
+        capi.check(getattr(capi.lib(), f"bvhgpu_build_{d['suffix']}")(ctx._h, _ptr(a), len(a), mode, C.byref(h)))
+        return cls(h, prec, ctx, len(a))
+
+    def free(self):
+        if self._h:
+            getattr(capi.lib(), f"bvhgpu_tree_free_{self._d['suffix']}")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def nodes_and_index(self):
+        nodes = np.zeros(max(2 * self.n - 1, 0), dtype=self._d["node"])
+        idx = np.zeros(self.n, dtype=np.uint32)
+        capi.check(getattr(capi.lib(), f"bvhgpu_tree_nodes_{self._d['suffix']}")(self._h, _ptr(nodes), _ptr(idx)))
+        return nodes, idx
+
+    def flatten(self) -> np.ndarray:
+        cap = 0 if self.n == 0 else (1 if self.n == 1 else 3 * self.n - 2)
+        out = np.zeros(cap, dtype=self._d["flat"])
+        ln = C.c_size_t(0)
+        capi.check(getattr(capi.lib(), f"bvhgpu_flatten_{self._d['suffix']}")(self._h, _ptr(out), cap, C.byref(ln)))
+        return out[: ln.value]
+
+    def traverse_batch(self, rays, mode: int = capi.TRAVERSE_BVH):
+        rays = np.ascontiguousarray(rays, dtype=self._d["ray"])
+        n = len(rays)
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        cap = max(16 * n, 1024)
+        fn = getattr(capi.lib(), f"bvhgpu_traverse_{self._d['suffix']}")
+        while True:
+            hits = np.zeros(cap, dtype=np.uint32)
+            total = C.c_size_t(0)
+            st = fn(self._h, mode, _ptr(rays), n, _ptr(offsets), _ptr(hits), cap, C.byref(total))
+            if st == capi.ERR_CAPACITY and total.value > cap and total.value <= U32_MAX:
+                cap = total.value
+                continue
+            capi.check(st)
+            return offsets, hits[: total.value]

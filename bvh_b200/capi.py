@@ -117,6 +117,15 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_nearest_{s}").argtypes = [vp, C.c_int, vp, sz, vp, vp]
         getattr(L, f"bvhgpu_nearest_candidates_{s}").argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(C.c_size_t)]
         getattr(L, f"bvhgpu_optimize_{s}").argtypes = [vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
+    for s in ("f32x2", "f64x2"):
+        getattr(L, f"bvhgpu_build_{s}").argtypes = [vp, vp, sz, i32, C.POINTER(vp)]
+        getattr(L, f"bvhgpu_tree_free_{s}").argtypes = [vp]
+        getattr(L, f"bvhgpu_tree_free_{s}").restype = None
+        getattr(L, f"bvhgpu_tree_num_shapes_{s}").argtypes = [vp]
+        getattr(L, f"bvhgpu_tree_num_shapes_{s}").restype = sz
+        getattr(L, f"bvhgpu_tree_nodes_{s}").argtypes = [vp, vp, vp]
+        getattr(L, f"bvhgpu_flatten_{s}").argtypes = [vp, vp, sz, szp]
+        getattr(L, f"bvhgpu_traverse_{s}").argtypes = [vp, i32, vp, sz, vp, vp, sz, szp]
     missing = [n for n in declared_symbols() if not hasattr(L, n)]
     if missing:
         raise ImportError(f"{SO_PATH} does not export {missing}")

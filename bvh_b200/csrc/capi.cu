@@ -59,7 +59,7 @@ template <class T> static void tree_release(Tree<T>* t) {
     if (!t) return;
     bvhgpu_ctx* ctx = t->ctx;
     if (ctx) {
-        dfree(ctx, t->d_aabb); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
+        dfree(ctx, t->d_aabb); dfree(ctx, t->d_aabb_trav); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
         dfree(ctx, t->d_tris); dfree(ctx, t->d_sa_base); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
     }
 }
@@ -464,6 +464,102 @@ static int optimize_impl(Tree<T>* tree, const typename Traits<T>::Aabb* aabbs, s
     return BVHGPU_OK;
 }
 
+// ---- D = 2 (dim2.cu): host PODs in, converted on the device, run through the 3-D path --------------------------------------
+template <class T, class TREE2, class AABB2>
+static int build2_impl(bvhgpu_ctx* ctx, const AABB2* aabbs, size_t n, int mode, TREE2** out) {
+    if (!ctx || !out || (n && !aabbs)) { set_error("build: null argument"); return BVHGPU_ERR_INVALID; }
+    *out = nullptr;
+    if (n > (1ull << 30)) { set_error("build: n = %zu exceeds 2^30 shapes", n); return BVHGPU_ERR_INVALID; }
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    Scratch scratch(ctx);
+    T *in4 = nullptr, *in6 = nullptr;
+    if (n) {
+        BVH_TRY(scratch.get(&in4, 4 * n));
+        BVH_TRY(scratch.get(&in6, 6 * n));
+        BVH_CUDA_TRY(cudaMemcpyAsync(in4, aabbs, sizeof(AABB2) * n, cudaMemcpyHostToDevice, ctx->stream));
+        BVH_TRY(dim2_expand_aabbs<T>(ctx, in4, (uint32_t)n, in6));
+    }
+    TREE2* tree = nullptr;
+    BVH_TRY((build_impl<T, TREE2>(ctx, reinterpret_cast<const typename Traits<T>::Aabb*>(in6), n, mode, false, &tree)));
+    int rc = dim2_finish_build<T>(tree);
+    if (rc == BVHGPU_OK) rc = resolve_status(tree);
+    if (rc != BVHGPU_OK) { tree_release<T>(tree); delete tree; return rc; }
+    *out = tree;
+    return BVHGPU_OK;
+}
+template <class T, class N2>
+static int tree_nodes2_impl(Tree<T>* tree, N2* out_nodes, uint32_t* out_node_index) {
+    if (!tree) { set_error("tree_nodes: null tree"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (tree->n == 0) return BVHGPU_OK;
+    Scratch scratch(ctx);
+    if (out_nodes) {
+        N2* d = nullptr;
+        BVH_TRY(scratch.get(&d, tree->n_nodes));
+        BVH_TRY((dim2_nodes_out<T, N2>(tree, d)));
+        BVH_CUDA_TRY(cudaMemcpyAsync(out_nodes, d, sizeof(N2) * tree->n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (out_node_index) BVH_CUDA_TRY(cudaMemcpyAsync(out_node_index, tree->d_node_index, sizeof(uint32_t) * tree->n, cudaMemcpyDeviceToHost, ctx->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BVHGPU_OK;
+}
+template <class T, class F2>
+static int flatten2_impl(Tree<T>* tree, F2* out, size_t cap, size_t* len) {
+    if (!tree) { set_error("flatten: null tree"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    BVH_TRY(build_flat(tree));
+    if (len) *len = tree->n_flat;
+    if (out) {
+        if (cap < tree->n_flat) { set_error("flatten: capacity %zu < %zu flat nodes", cap, tree->n_flat); return BVHGPU_ERR_CAPACITY; }
+        if (tree->n_flat) {
+            Scratch scratch(ctx);
+            F2* d = nullptr;
+            BVH_TRY(scratch.get(&d, tree->n_flat));
+            BVH_TRY((dim2_flat_out<T, F2>(tree, d)));
+            BVH_CUDA_TRY(cudaMemcpyAsync(out, d, sizeof(F2) * tree->n_flat, cudaMemcpyDeviceToHost, ctx->stream));
+            BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return BVHGPU_OK;
+}
+template <class T, class RAY2>
+static int traverse2_impl(Tree<T>* tree, int mode, const RAY2* rays, size_t nrays, uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total) {
+    if (!tree || (nrays && !rays) || !offsets) { set_error("traverse: null argument"); return BVHGPU_ERR_INVALID; }
+    bvhgpu_ctx* ctx = tree->ctx;
+    BVH_CUDA_TRY(cudaSetDevice(ctx->device));
+    BVH_TRY(resolve_status(tree));
+    if (nrays > 0x7FFFFFFFull) { set_error("traverse: too many rays"); return BVHGPU_ERR_INVALID; }
+    Scratch scratch(ctx);
+    T *r6 = nullptr, *r9 = nullptr;
+    if (nrays) {
+        BVH_TRY(scratch.get(&r6, 6 * nrays));
+        BVH_TRY(scratch.get(&r9, 9 * nrays));
+        BVH_CUDA_TRY(cudaMemcpyAsync(r6, rays, sizeof(RAY2) * nrays, cudaMemcpyHostToDevice, ctx->stream));
+        BVH_TRY(dim2_expand_rays<T>(ctx, r6, (uint32_t)nrays, r9));
+    }
+    size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 4 * nrays), 1024), tot = 0;
+    int rc = BVHGPU_OK;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = ensure_result_buffers(tree, nrays, want);
+        if (rc != BVHGPU_OK) break;
+        rc = traverse_device<T>(tree, mode, r9, BVHGPU_RAYS_FULL, nrays, tree->d_offsets, tree->d_hits, tree->hits_cap, &tot);
+        if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && tot > tree->hits_cap && attempt == 0) { want = tot; continue; }
+        break;
+    }
+    if (total) *total = tot;
+    if (rc != BVHGPU_OK) return rc;
+    BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (nrays + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    int ret = BVHGPU_OK;
+    if (hits && tot <= cap) { if (tot) BVH_CUDA_TRY(cudaMemcpyAsync(hits, tree->d_hits, sizeof(uint32_t) * tot, cudaMemcpyDeviceToHost, ctx->stream)); }
+    else if (tot > cap) { set_error("traverse: %zu hits do not fit the caller's capacity %zu", tot, cap); ret = BVHGPU_ERR_CAPACITY; }
+    BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return ret;
+}
+
 // Bvh::update_shapes(changed_shape_indices, shapes): only the m changed shapes cross the boundary.  The tree is touched only after
 // the new AABBs passed the NaN / index check.  max_growth <= 0: refit only (topology kept).
 template <class T>
@@ -863,5 +959,27 @@ BVH_EXPORT int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p) {
         return update_impl<T>(tree, (const uint32_t*)dev_changed, (const AABB*)dev_changed_aabbs, m, max_growth, rebuilt, true); \
     }
 
+#define DEFINE_API2(T, SUF, TREE, AABB, RAY, NODE, FLAT)                                                                   \
+    BVH_EXPORT int bvhgpu_build_##SUF(bvhgpu_ctx* ctx, const AABB* aabbs, size_t n, int mode, TREE** out) {               \
+        return build2_impl<T, TREE, AABB>(ctx, aabbs, n, mode, out);                                                       \
+    }                                                                                                                      \
+    BVH_EXPORT void bvhgpu_tree_free_##SUF(TREE* tree) {                                                                   \
+        if (!tree) return;                                                                                                 \
+        if (tree->ctx) cudaSetDevice(tree->ctx->device);                                                                   \
+        tree_release<T>(tree);                                                                                             \
+        delete tree;                                                                                                       \
+    }                                                                                                                      \
+    BVH_EXPORT size_t bvhgpu_tree_num_shapes_##SUF(const TREE* tree) { return tree ? tree->n : 0; }                        \
+    BVH_EXPORT int bvhgpu_tree_nodes_##SUF(TREE* tree, NODE* out_nodes, uint32_t* out_node_index) {                        \
+        return tree_nodes2_impl<T, NODE>(tree, out_nodes, out_node_index);                                                 \
+    }                                                                                                                      \
+    BVH_EXPORT int bvhgpu_flatten_##SUF(TREE* tree, FLAT* out, size_t cap, size_t* len) { return flatten2_impl<T, FLAT>(tree, out, cap, len); } \
+    BVH_EXPORT int bvhgpu_traverse_##SUF(TREE* tree, int mode, const RAY* rays, size_t nrays, uint32_t* offsets, uint32_t* hits, \
+                                         size_t cap, size_t* total) {                                                      \
+        return traverse2_impl<T, RAY>(tree, mode, rays, nrays, offsets, hits, cap, total);                                 \
+    }
+
+DEFINE_API2(float, f32x2, bvhgpu_tree2f, bvh_aabb2f, bvh_ray2f, bvh_node2f, bvh_flat2f)
+DEFINE_API2(double, f64x2, bvhgpu_tree2d, bvh_aabb2d, bvh_ray2d, bvh_node2d, bvh_flat2d)
 DEFINE_API(float, f32x3, bvhgpu_tree3f, bvh_aabb3f, bvh_ray3f, bvh_node3f, bvh_flat3f)
 DEFINE_API(double, f64x3, bvhgpu_tree3d, bvh_aabb3d, bvh_ray3d, bvh_node3d, bvh_flat3d)

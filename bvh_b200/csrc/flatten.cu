@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) flat_kernel(const typename Traits<T>::Nod
 template <class T>
 __global__ void __launch_bounds__(256) trec_kernel(const typename Traits<T>::Node* __restrict__ nodes, uint32_t n_nodes,
                                                    const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                   typename Traits<T>::TNode* __restrict__ trec, const BuildStatus* __restrict__ status) {
+                                                   typename Traits<T>::TNode* __restrict__ trec, const BuildStatus* __restrict__ status, int dims) {
     using Tr = Traits<T>;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) trec_kernel(const typename Traits<T>::Nod
         load_aabb(aabb + nodes[0].shape, mn, mx);
         for (int k = 0; k < 3; ++k) { r.min[k] = mn[k]; r.max[k] = mx[k]; }
         r.skip = 1; r.shape = nodes[0].shape;
+        if (dims == 2) { r.min[2] = T(-1); r.max[2] = T(1); }
         if constexpr (sizeof(T) == 8) { r.pad[0] = r.pad[1] = 0; }
         trec[0] = r;
         return;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256) trec_kernel(const typename Traits<T>::Nod
     const uint32_t count = leaf ? 1u : meta.w;
     r.skip = (i - 1) + (2 * count - 1);
     r.shape = leaf ? meta.w : BVH_INVALID;
+    if (dims == 2) { r.min[2] = T(-1); r.max[2] = T(1); }          // 2-D tree: the z slab must not constrain (dim2.cu)
     if constexpr (sizeof(T) == 8) { r.pad[0] = r.pad[1] = 0; }
     trec[i - 1] = r;
 }
@@ -91,7 +93,7 @@ template <class T> int build_traversal_records(Tree<T>* tree) {
     const uint32_t n_trec = tree->n == 1 ? 1u : tree->n_nodes - 1;
     if (!tree->d_tnodes) BVH_TRY(dalloc_t(ctx, &tree->d_tnodes, n_trec));
     tree->n_trec = n_trec;
-    trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->d_aabb, tree->d_tnodes, tree->d_status);
+    trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->dims == 2 && tree->d_aabb_trav ? tree->d_aabb_trav : tree->d_aabb, tree->d_tnodes, tree->d_status, tree->dims);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
     return BVHGPU_OK;

@@ -79,7 +79,9 @@ template <class T> struct Tree {
     bvhgpu_ctx* ctx = nullptr;
     uint32_t n = 0;          // shapes
     uint32_t n_nodes = 0;    // 2n-1
+    int dims = 3;            // 2: a Bvh<T,2> embedded in the plane z = 0 (dim2.cu)
     typename Tr::DAabb* d_aabb = nullptr;     // [n]      shape AABBs (padded device layout)
+    typename Tr::DAabb* d_aabb_trav = nullptr; // [n]     dims == 2 only: the same with z = [-1, +1] for the FLAT leaf re-test
     typename Tr::Node* d_nodes = nullptr;     // [2n-1]   Bvh.nodes, reference preorder layout
     uint32_t* d_node_index = nullptr;         // [n]      leaf node of every shape
     uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
@@ -178,6 +180,12 @@ template <class T> int query_device(Tree<T>* tree, int mode, int kind, const T* 
 // nearest_to for a batch of points (device pointers): exact reference walk for AABB-distance shapes; candidate lists for any shape
 template <class T> int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist);
 template <class T> int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint32_t* d_offsets, uint32_t* d_cand, size_t cap, size_t* total);
+// ---- dim2.cu ----
+template <class T> int dim2_expand_aabbs(bvhgpu_ctx* ctx, const T* d_in4, uint32_t n, T* d_out6);
+template <class T> int dim2_expand_rays(bvhgpu_ctx* ctx, const T* d_in6, uint32_t n, T* d_out9);
+template <class T> int dim2_finish_build(Tree<T>* tree);
+template <class T, class N2> int dim2_nodes_out(Tree<T>* tree, N2* d_out);
+template <class T, class F2> int dim2_flat_out(Tree<T>* tree, F2* d_out);
 // ---- closest.cu ----
 template <class T> int set_triangles(Tree<T>* tree, const T* tris9, size_t n, bool dev_input);
 template <class T> int closest_hit_device(Tree<T>* tree, const void* d_rays, uint32_t fmt, size_t nrays, int use_triangles, uint32_t* d_shape, T* d_dist, T* d_uv);
@@ -188,3 +196,5 @@ template <class T> int rays_new_device(bvhgpu_ctx* ctx, const T* d_origins, cons
 
 struct bvhgpu_tree3f : bvhb200::Tree<float> {};
 struct bvhgpu_tree3d : bvhb200::Tree<double> {};
+struct bvhgpu_tree2f : bvhb200::Tree<float> {};
+struct bvhgpu_tree2d : bvhb200::Tree<double> {};

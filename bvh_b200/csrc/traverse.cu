@@ -39,6 +39,9 @@ static inline uint32_t pick_slots(bvhgpu_ctx* ctx, uint32_t nrays) {
     return p;
 }
 
+// shape AABBs the FLAT leaf re-test reads: a 2-D tree keeps a copy whose z slab never constrains (dim2.cu)
+template <class T> static inline const typename Traits<T>::DAabb* walk_aabbs(const Tree<T>* tree) { return tree->dims == 2 && tree->d_aabb_trav ? tree->d_aabb_trav : tree->d_aabb; }
+
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;     // 2048 counts per block
@@ -741,8 +744,8 @@ static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, ui
     }
     if (pmode == 0 || pmode >= 2) {
         const int grid = (count + 255) / 256;
-        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
-        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
+        if (flat) walk_count_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
+        else      walk_count_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, first, count, counts, slots, K, tail + S_VISITS, gate, 1u);
         ctx->launches++;
         if (pmode == 0) return BVHGPU_OK;
     }
@@ -757,11 +760,11 @@ static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, ui
     const uint32_t* ready = reinterpret_cast<const uint32_t*>(tail + S_READY);
     uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);
     if (stream_mode) {
-        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
-        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
+        if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
+        else      walk_persistent_kernel<T, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
     } else {
-        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
-        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
+        if (flat) walk_persistent_kernel<T, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
+        else      walk_persistent_kernel<T, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, gate, 0u, err, 0ull);
     }
     ctx->launches++;
     return BVHGPU_OK;
@@ -847,8 +850,8 @@ int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, s
         BVH_CUDA_TRY(cudaMemcpyAsync(h, tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
+    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
+    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
     ctx->launches++;
     if (shard) {
         goffsets_kernel<<<(unsigned)pb.tiles_before[pb.world], SCAN_THREADS, 0, st>>>(pb, tail + S_XINFO, (uint32_t*)shard->offsets);
@@ -1032,8 +1035,8 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
         for (uint32_t c = 0; c < nsl; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nsl), hi = (uint32_t)((uint64_t)R * (c + 1) / nsl), cnt = hi - lo;
             const int g = (cnt + 255) / 256;
-            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
-            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
+            if (flat) emit_kernel<T, true><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
+            else      emit_kernel<T, false><<<g, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)tree->hits_cap, lo, cnt, nopeers, tail + S_XINFO, arrival);
             BVH_CUDA_TRY(cudaEventRecord(ctx->ev_emit[c], st));
             BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_emit[c], 0));
             const uint32_t ncopy = cnt + (c + 1 == nsl ? 1u : 0u);
@@ -1192,12 +1195,12 @@ static int query_launch(Tree<T>* tree, bool flat, const T* d_queries, uint32_t n
                         unsigned long long* sums, uint32_t nblk, uint32_t* d_offsets, uint32_t* d_hits, size_t cap) {
     cudaStream_t st = tree->ctx->stream;
     const int grid = (nq + 255) / 256;
-    if (flat) query_kernel<T, KIND, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-    else      query_kernel<T, KIND, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    if (flat) query_kernel<T, KIND, true, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    else      query_kernel<T, KIND, false, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), d_queries, nq, counts, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     scan_local_kernel<<<nblk, SCAN_THREADS, 0, st>>>(counts, nq, local, sums, nullptr);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(sums, nblk, sums + nblk);
-    if (flat) query_kernel<T, KIND, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
-    else      query_kernel<T, KIND, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, tree->d_aabb, d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    if (flat) query_kernel<T, KIND, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
+    else      query_kernel<T, KIND, false, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), d_queries, nq, counts, local, sums, sums + nblk, d_offsets, d_hits, (unsigned long long)cap);
     tree->ctx->launches += 4;
     BVH_CUDA_TRY(cudaGetLastError());
     return BVHGPU_OK;

@@ -58,6 +58,16 @@ typedef struct { uint32_t parent, child_l, child_r, shape; bvh_aabb3d l_aabb, r_
 typedef struct { bvh_aabb3f aabb; uint32_t entry_index, exit_index, shape_index; } bvh_flat3f;             /* 36 B */
 typedef struct { bvh_aabb3d aabb; uint32_t entry_index, exit_index, shape_index, _pad; } bvh_flat3d;      /* 64 B */
 
+/* D = 2 twins (the reference is generic in D; 2-D slab tests: src/ray/intersect_simd.rs:99-133, 181-191) */
+typedef struct { float min[2]; float max[2]; } bvh_aabb2f;                                                   /* 16 B */
+typedef struct { double min[2]; double max[2]; } bvh_aabb2d;                                                 /* 32 B */
+typedef struct { float origin[2]; float direction[2]; float inv_direction[2]; } bvh_ray2f;                   /* 24 B */
+typedef struct { double origin[2]; double direction[2]; double inv_direction[2]; } bvh_ray2d;                /* 48 B */
+typedef struct { uint32_t parent, child_l, child_r, shape; bvh_aabb2f l_aabb, r_aabb; } bvh_node2f;          /* 48 B */
+typedef struct { uint32_t parent, child_l, child_r, shape; bvh_aabb2d l_aabb, r_aabb; } bvh_node2d;          /* 80 B */
+typedef struct { bvh_aabb2f aabb; uint32_t entry_index, exit_index, shape_index; } bvh_flat2f;               /* 28 B */
+typedef struct { bvh_aabb2d aabb; uint32_t entry_index, exit_index, shape_index, _pad; } bvh_flat2d;         /* 48 B */
+
 typedef enum {
     BVHGPU_OK = 0,
     BVHGPU_ERR_INVALID = 1,     /* bad argument */
@@ -89,6 +99,8 @@ typedef enum { BVHGPU_RAYS_FULL = 0, BVHGPU_RAYS_OD = 1 } bvhgpu_ray_layout;
 typedef struct bvhgpu_ctx bvhgpu_ctx;       /* one per device: stream, scratch pool           */
 typedef struct bvhgpu_tree3f bvhgpu_tree3f; /* device-resident Bvh<f32,3> (+ FlatBvh, shape AABBs) */
 typedef struct bvhgpu_tree3d bvhgpu_tree3d; /* device-resident Bvh<f64,3>                      */
+typedef struct bvhgpu_tree2f bvhgpu_tree2f; /* device-resident Bvh<f32,2>                      */
+typedef struct bvhgpu_tree2d bvhgpu_tree2d; /* device-resident Bvh<f64,2>                      */
 
 /* ---- context ------------------------------------------------------------------ */
 int bvhgpu_create(int device, bvhgpu_ctx** out);
@@ -151,6 +163,24 @@ size_t bvhgpu_tree_num_nodes_f64x3(const bvhgpu_tree3d* tree);
  * Either pointer may be NULL. */
 int bvhgpu_tree_nodes_f32x3(bvhgpu_tree3f* tree, bvh_node3f* out_nodes, uint32_t* out_node_index);
 int bvhgpu_tree_nodes_f64x3(bvhgpu_tree3d* tree, bvh_node3d* out_nodes, uint32_t* out_node_index);
+
+/* ---- D = 2: Bvh<T,2>::build / nodes / flatten / traverse.  Host pointers; semantics, modes, error codes and
+ * the CSR output exactly as the 3-D entry points above.  The scene is embedded in the plane z = 0 of the 3-D kernels in a way that
+ * reproduces the 2-D arithmetic bit for bit (dim2.cu). */
+int bvhgpu_build_f32x2(bvhgpu_ctx* ctx, const bvh_aabb2f* aabbs, size_t n, int mode, bvhgpu_tree2f** out);
+int bvhgpu_build_f64x2(bvhgpu_ctx* ctx, const bvh_aabb2d* aabbs, size_t n, int mode, bvhgpu_tree2d** out);
+void bvhgpu_tree_free_f32x2(bvhgpu_tree2f* tree);
+void bvhgpu_tree_free_f64x2(bvhgpu_tree2d* tree);
+size_t bvhgpu_tree_num_shapes_f32x2(const bvhgpu_tree2f* tree);
+size_t bvhgpu_tree_num_shapes_f64x2(const bvhgpu_tree2d* tree);
+int bvhgpu_tree_nodes_f32x2(bvhgpu_tree2f* tree, bvh_node2f* out_nodes, uint32_t* out_node_index);
+int bvhgpu_tree_nodes_f64x2(bvhgpu_tree2d* tree, bvh_node2d* out_nodes, uint32_t* out_node_index);
+int bvhgpu_flatten_f32x2(bvhgpu_tree2f* tree, bvh_flat2f* out, size_t cap, size_t* len);
+int bvhgpu_flatten_f64x2(bvhgpu_tree2d* tree, bvh_flat2d* out, size_t cap, size_t* len);
+int bvhgpu_traverse_f32x2(bvhgpu_tree2f* tree, int mode, const bvh_ray2f* rays, size_t nrays,
+                          uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
+int bvhgpu_traverse_f64x2(bvhgpu_tree2d* tree, int mode, const bvh_ray2d* rays, size_t nrays,
+                          uint32_t* offsets, uint32_t* hits, size_t cap, size_t* total);
 
 /* ---- flatten: replaces Bvh::flatten (src/flat_bvh.rs:60-143, 240-251, 312-319) -----
  * Writes the FlatBvh (3n-2 FlatNodes for n >= 2, 1 for n == 1, 0 for n == 0) into `out`

@@ -9,13 +9,21 @@ import numpy as np
 U32_MAX = 0xFFFFFFFF
 
 
+def _dot(v):
+    """nalgebra small-vector dot, left to right: (x*x + y*y) [+ z*z]."""
+    acc = v[0] * v[0] + v[1] * v[1]
+    for k in range(2, len(v)):
+        acc = acc + v[k] * v[k]
+    return acc
+
+
 def _sa(F, mn, mx):
-    s = [F(mx[k]) - F(mn[k]) for k in range(3)]
-    return F(2) * ((s[0] * s[0] + s[1] * s[1]) + s[2] * s[2])
+    s = [F(mx[k]) - F(mn[k]) for k in range(len(mn))]
+    return F(2) * _dot(s)
 
 
 def _center(F, mn, mx):
-    return [F(mn[k]) * F(0.5) + F(mx[k]) * F(0.5) for k in range(3)]
+    return [F(mn[k]) * F(0.5) + F(mx[k]) * F(0.5) for k in range(len(mn))]
 
 
 def _join(a, b):
@@ -32,7 +40,8 @@ def build(aabbs, F=np.float32):
     if n == 0:
         return [], []
     inf = F(np.inf)
-    EMPTY = ([inf, inf, inf], [-inf, -inf, -inf])
+    D = len(aabbs[0]["min"])
+    EMPTY = ([inf] * D, [-inf] * D)
     boxes = [([F(v) for v in a["min"]], [F(v) for v in a["max"]]) for a in aabbs]
     ctrs = [_center(F, *b) for b in boxes]
     nodes = [None] * (2 * n - 1)
@@ -56,9 +65,9 @@ def build(aabbs, F=np.float32):
                 nodes[me] = ("leaf", parent, I[0])
                 node_index[I[0]] = me
                 continue
-            size = [CB[1][k] - CB[0][k] for k in range(3)]
+            size = [CB[1][k] - CB[0][k] for k in range(D)]
             axis = 0
-            for k in (1, 2):
+            for k in range(1, D):
                 if size[k] > size[axis]:
                     axis = k
             ext = size[axis]
@@ -123,8 +132,8 @@ def flatten(nodes):
 def hit(F, ray, mn, mx):
     o, inv = ray
     with np.errstate(all="ignore"):
-        l = [(F(mn[k]) - o[k]) * inv[k] for k in range(3)]
-        r = [(F(mx[k]) - o[k]) * inv[k] for k in range(3)]
+        l = [(F(mn[k]) - o[k]) * inv[k] for k in range(len(o))]
+        r = [(F(mx[k]) - o[k]) * inv[k] for k in range(len(o))]
     if any(np.isnan(v) for v in l + r):
         return False
     lo = [min(a, b) for a, b in zip(l, r)]
@@ -138,7 +147,7 @@ def ray_new(F, o, d):
     o = [F(v) for v in o]
     d = [F(v) for v in d]
     with np.errstate(all="ignore"):
-        n = np.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+        n = np.sqrt(_dot(d))
         d = [v / n for v in d]
         inv = [F(1) / v for v in d]
     return o, d, inv

@@ -401,3 +401,73 @@ def test_slow_drift_is_rebuilt_eventually(api):
     c_fresh = O.sah_cost(O.build(shapes).nodes)[0]
     assert c_gpu <= 1.10 * c_ref, (c_gpu, c_ref, c_fresh, per_call)
     bvh.free()
+
+
+# ---- D = 2 ------------------------------------------------------------------------------------------------------
+def _scene2d(kind, n, F, rng):
+    from bvh_b200.dtypes import BY_PREC_2D
+
+    a = np.zeros(n, dtype=BY_PREC_2D["f32" if F == np.float32 else "f64"]["aabb"])
+    if kind == "random":
+        mn = rng.uniform(-100, 100, (n, 2))
+        a["min"], a["max"] = mn, mn + rng.uniform(0, 8, (n, 2)) ** 2 / 8
+    elif kind == "points":                      # coincident degenerate boxes: the halving branch
+        base = rng.integers(-4, 4, (max(n // 6, 1), 2)).astype(float)
+        mn = base[rng.integers(0, len(base), n)]
+        a["min"], a["max"] = mn, mn
+    elif kind == "line":                        # all centres on one axis
+        x = rng.integers(0, max(n // 3, 2), n).astype(float)
+        a["min"][:, 0], a["max"][:, 0] = x - 0.25, x + 0.25
+        a["min"][:, 1], a["max"][:, 1] = -0.25, 0.25
+    return a
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("kind,n", [("random", 1), ("random", 2), ("random", 33), ("random", 700), ("points", 300), ("line", 200)])
+def test_two_dimensional_bvh_matches_the_2d_restatement(api, kind, n, prec):
+    """Bvh<T,2>: build, flatten and both traversals against tests/pyref.py run in TWO dimensions (an independent restatement of the
+    reference's generic code: 2-term dot in surface_area, largest_axis over 2 components, 2-D slab test) -- node for node, bit for bit."""
+    from tests import pyref
+    from bvh_b200 import capi
+    from bvh_b200.dtypes import BY_PREC_2D
+
+    F = np.float32 if prec == "f32" else np.float64
+    rng = np.random.default_rng(n * 7 + len(kind))
+    a = _scene2d(kind, n, F, rng)
+    want_nodes, want_index = pyref.build(a, F)
+    bvh = api.Bvh2.build(a, prec=prec)
+    nodes, index = bvh.nodes_and_index()
+    assert list(index) == list(want_index)
+    for i, w in enumerate(want_nodes):
+        if w[0] == "leaf":
+            assert nodes["child_l"][i] == O.U32_MAX and nodes["parent"][i] == w[1] and nodes["shape"][i] == w[2]
+        else:
+            assert (nodes["parent"][i], nodes["child_l"][i], nodes["child_r"][i]) == (w[1], w[2], w[3])
+            for side, box in (("l_aabb", w[4]), ("r_aabb", w[5])):
+                assert np.array_equal(nodes[side]["min"][i], np.array(box[0], dtype=F)) and np.array_equal(nodes[side]["max"][i], np.array(box[1], dtype=F))
+    flat = bvh.flatten()
+    wflat = pyref.flatten(want_nodes)
+    assert len(flat) == len(wflat)
+    for i, (box, entry, exit_, shape) in enumerate(wflat):
+        assert (flat["entry_index"][i], flat["exit_index"][i], flat["shape_index"][i]) == (entry, exit_, shape)
+        if box is not None:
+            assert np.array_equal(flat["aabb"]["min"][i], np.array(box[0], dtype=F)) and np.array_equal(flat["aabb"]["max"][i], np.array(box[1], dtype=F))
+    # rays: random + axis-aligned ones that start on box edges (0 * inf = NaN rule)
+    m = 300
+    org = rng.uniform(-120, 120, (m, 2)); tgt = rng.uniform(-100, 100, (m, 2))
+    dirs = tgt - org
+    for i in range(40):
+        dirs[i] = [1.0, 0.0] if i % 2 else [0.0, -1.0]
+        if i % 4 < 2:
+            org[i] = a["min"][rng.integers(0, n)]
+    rays = np.zeros(m, dtype=BY_PREC_2D[prec]["ray"])
+    prs = [pyref.ray_new(F, org[i], dirs[i]) for i in range(m)]
+    for i, (o, d, inv) in enumerate(prs):
+        rays["origin"][i], rays["direction"][i], rays["inv_direction"][i] = o, d, inv
+    off, hits = bvh.traverse_batch(rays, mode=capi.TRAVERSE_BVH)
+    off2, hits2 = bvh.traverse_batch(rays, mode=capi.TRAVERSE_FLAT)
+    for i in range(m):
+        want = pyref.traverse_recursive(want_nodes, a, (prs[i][0], prs[i][2]), F)
+        assert hits[off[i]:off[i + 1]].tolist() == want, i
+        assert hits2[off2[i]:off2[i + 1]].tolist() == want, i        # tight trees: the FLAT leaf re-test agrees
+    bvh.free()
