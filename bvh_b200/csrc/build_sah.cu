@@ -1479,7 +1479,7 @@ int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSession<T>* S) {
 // [i, i + 2k - 1) and the leaf range [start, start + k), and child_l = i + 1 / child_r = i + 2 n_l stay inside it.
 template <class T>
 __global__ void __launch_bounds__(256) rebuild_push_kernel(BuildParams<T> P, const uint32_t* __restrict__ roots, const uint32_t* __restrict__ n_roots,
-                                                           const T* __restrict__ cb) {
+                                                           const T* __restrict__ cb, bool cb_by_root) {
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t nr = *n_roots;
     if (P.status->nan_found) return;                                   // (cannot happen through the C ABI: new AABBs are checked before the tree is touched)
@@ -1491,7 +1491,8 @@ __global__ void __launch_bounds__(256) rebuild_push_kernel(BuildParams<T> P, con
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             t.ab[k] = min_t(nd.l_aabb.min[k], nd.r_aabb.min[k]); t.ab[3 + k] = max_t(nd.l_aabb.max[k], nd.r_aabb.max[k]);
-            t.cb[k] = cb[6 * (size_t)r + k]; t.cb[3 + k] = cb[6 * (size_t)r + 3 + k];
+            const size_t at = 6 * (size_t)(cb_by_root ? i : r);
+            t.cb[k] = cb[at + k]; t.cb[3 + k] = cb[at + 3 + k];
         }
         if (lane_id() == 0) { atomicSub(&P.ctl->leaves_done, t.count); atomicAdd(&P.ctl->rebuilt, t.count); }
         __syncwarp();
@@ -1506,7 +1507,7 @@ template <class T> __global__ void rebuild_start_kernel(BuildCtl* ctl, uint32_t 
 }
 
 template <class T>
-int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0) {
+int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0, bool cb_by_root) {
     cudaStream_t st = ctx->stream;
     const uint32_t n = tree->n;
     BuildParams<T> P{};
@@ -1526,7 +1527,10 @@ int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, co
     if (ctx->build_gang < 0 && (uint64_t)n / GT > P.gang_budget) P.gang_budget = 0;
     P.sdiv = P.gang_budget ? GT : TILE;
     const size_t nbig = 2 * ((size_t)n / P.sdiv + 2);
-    const bool defer_small = ctx->build_small < 0 ? (sizeof(T) == 8 && n >= 400000u) : ctx->build_small != 0;
+    // a rebuild usually covers a small part of the tree: the thread-per-range kernel (one thread replays a <= 16-shape range) only pays
+    // when millions of ranges keep every SM busy; here the warp-per-subtree builder finishes the job sooner (10 M f64, 2.4 M shapes
+    // rebuilt: 4.2 ms in small_subtrees_kernel)
+    const bool defer_small = ctx->build_small < 0 ? false : ctx->build_small != 0;
     P.small_max = defer_small ? SMALL : 0u;
     P.opt_subtree = ctx->build_subtree < 0 ? !defer_small : ctx->build_subtree != 0;
     P.idx[0] = idx0;
@@ -1542,7 +1546,7 @@ int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, co
     BVH_CUDA_TRY(cudaMemsetAsync(P.ctl, 0, sizeof(BuildCtl), st));
     rebuild_start_kernel<T><<<1, 32, 0, st>>>(P.ctl, n, P.status);
     const int pblocks = (int)std::min<uint64_t>(((uint64_t)n + 63) / 64, (uint64_t)ctx->sm_count * 4);
-    rebuild_push_kernel<T><<<pblocks, 256, 0, st>>>(P, d_roots, d_n_roots, cb);
+    rebuild_push_kernel<T><<<pblocks, 256, 0, st>>>(P, d_roots, d_n_roots, cb, cb_by_root);
     if (P.gang_budget) {
         void* kargs[] = {&P};
         BVH_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)build_kernel<T>, dim3(grid), dim3(WARPS_PER_CTA * 32), kargs, 0, st));
@@ -1563,8 +1567,8 @@ int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, co
     tree->status_pending = true;
     return BVHGPU_OK;
 }
-template int rebuild_subtrees<float>(bvhgpu_ctx*, Tree<float>*, const uint32_t*, const uint32_t*, const float*, uint32_t*);
-template int rebuild_subtrees<double>(bvhgpu_ctx*, Tree<double>*, const uint32_t*, const uint32_t*, const double*, uint32_t*);
+template int rebuild_subtrees<float>(bvhgpu_ctx*, Tree<float>*, const uint32_t*, const uint32_t*, const float*, uint32_t*, bool);
+template int rebuild_subtrees<double>(bvhgpu_ctx*, Tree<double>*, const uint32_t*, const uint32_t*, const double*, uint32_t*, bool);
 
 template int treelet_begin<float>(bvhgpu_ctx*, Tree<float>*, uint32_t*, TreeletSession<float>*);
 template int treelet_begin<double>(bvhgpu_ctx*, Tree<double>*, uint32_t*, TreeletSession<double>*);

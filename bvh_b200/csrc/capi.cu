@@ -60,7 +60,7 @@ template <class T> static void tree_release(Tree<T>* t) {
     bvhgpu_ctx* ctx = t->ctx;
     if (ctx) {
         dfree(ctx, t->d_aabb); dfree(ctx, t->d_aabb_trav); dfree(ctx, t->d_nodes); dfree(ctx, t->d_node_index); dfree(ctx, t->d_node_start);
-        dfree(ctx, t->d_tris); dfree(ctx, t->d_sa_base); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
+        dfree(ctx, t->d_tris); dfree(ctx, t->d_sa_base); dfree(ctx, t->d_arrive); dfree(ctx, t->d_bad); dfree(ctx, t->d_tnodes); dfree(ctx, t->d_flat); dfree(ctx, t->d_status); dfree(ctx, t->d_offsets); dfree(ctx, t->d_hits);
     }
 }
 
@@ -595,7 +595,7 @@ static int update_impl(Tree<T>* tree, const uint32_t* changed, const typename Tr
     if (h[0]) { set_error("update: NaN coordinate in a new AABB; the tree was left unchanged"); return BVHGPU_ERR_NAN; }
     BVH_TRY(update_scatter<T>(tree, d_changed, d_fresh, (uint32_t)m));
     BVH_CUDA_TRY(cudaMemsetAsync(tree->d_status, 0, sizeof(BuildStatus), ctx->stream));
-    if (max_growth > 0.0) BVH_TRY(optimize(tree, max_growth)); else BVH_TRY(refit(tree));
+    BVH_TRY(update_incremental<T>(tree, d_changed, (uint32_t)m, max_growth));      // touches the root paths of the changed leaves only
     tree->status_pending = true;
     if (dev_input && !rebuilt) return BVHGPU_OK;                        // asynchronous from here on
     BuildStatus hs;

@@ -330,7 +330,7 @@ template <class T> int optimize(Tree<T>* tree, double max_growth) {
     leaf_order_kernel<<<gs, 256, 0, st>>>(tree->d_node_index, tree->d_node_start, n, idx0);
     ctx->launches += 4;
     BVH_CUDA_TRY(cudaGetLastError());
-    BVH_TRY(rebuild_subtrees(ctx, tree, roots, n_roots, cb, idx0));
+    BVH_TRY(rebuild_subtrees(ctx, tree, roots, n_roots, cb, idx0, false));
     rebase_kernel<T><<<std::max(1, std::min(ctx->sm_count * 4, (int)n)), 256, 0, st>>>(tree->d_nodes, roots, n_roots, sa_old);
     ctx->launches++;
     dfree(ctx, cb); dfree(ctx, bad); dfree(ctx, roots); dfree(ctx, n_roots); dfree(ctx, idx0); dfree(ctx, arrivals);
@@ -365,6 +365,147 @@ __global__ void __launch_bounds__(256) update_scatter_kernel(const uint32_t* __r
     if constexpr (sizeof(T) == 4) { d.pad0 = 0; d.pad1 = 0; }
     aabb[changed[i]] = d;                                               // an index listed twice: one of its AABBs wins (the reference would use shapes[i] for both)
 }
+// ---- incremental form: only the root paths of the changed leaves are touched ----------------------------------------------------
+// mark: every changed leaf walks up and counts, in arrive[p], how many of p's children lie on a changed path (the first walker through
+// a node carries on, later ones stop).  climb: every changed leaf writes its box into its parent and decrements; the LAST arrival at a
+// node joins the two stored child boxes (both final by then), tests the growth against the node's baseline, logs the node as dirty and
+// carries on.  Work = number of nodes on the changed paths, not n.
+template <class T>
+__global__ void __launch_bounds__(256) mark_paths_kernel(const typename Traits<T>::Node* __restrict__ nodes, const uint32_t* __restrict__ node_index,
+                                                         const uint32_t* __restrict__ changed, uint32_t m, uint32_t* __restrict__ arrive) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t node = node_index[changed[i]];
+    while (node != 0) {
+        const uint32_t p = nodes[node].parent;
+        if (atomicAdd(arrive + p, 1u) != 0u) break;
+        node = p;
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(256) climb_paths_kernel(typename Traits<T>::Node* nodes, const uint32_t* __restrict__ node_index,
+                                                          const typename Traits<T>::DAabb* __restrict__ aabb, const uint32_t* __restrict__ changed, uint32_t m,
+                                                          uint32_t* __restrict__ arrive, const T* __restrict__ sa_base, T max_growth, uint8_t* __restrict__ bad,
+                                                          uint32_t* __restrict__ dirty, uint32_t* __restrict__ n_dirty) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t s = changed[i];
+    T mn[3], mx[3];
+    load_aabb(aabb + s, mn, mx);
+    uint32_t node = node_index[s];
+    while (node != 0) {
+        const uint32_t p = __ldcg(&nodes[node].parent);
+        typename Traits<T>::Node* pn = nodes + p;
+        const bool is_left = __ldcg(&pn->child_l) == node;
+        auto* dst = is_left ? &pn->l_aabb : &pn->r_aabb;
+        for (int k = 0; k < 3; ++k) { __stcg(&dst->min[k], mn[k]); __stcg(&dst->max[k], mx[k]); }
+        __threadfence();
+        if (atomicSub(arrive + p, 1u) != 1u) return;        // another changed path still has to come through p
+        __threadfence();
+        const auto* sib = is_left ? &pn->r_aabb : &pn->l_aabb;
+        for (int k = 0; k < 3; ++k) { mn[k] = min_t(__ldcg(&sib->min[k]), mn[k]); mx[k] = max_t(__ldcg(&sib->max[k]), mx[k]); }
+        if (bad && surface_area(mn, mx) > mul_rn(max_growth, sa_base[p])) bad[p] = 1;
+        dirty[atomicAdd(n_dirty, 1u)] = p;
+        node = p;
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(256) select_roots_dirty_kernel(const typename Traits<T>::Node* __restrict__ nodes, const uint8_t* __restrict__ bad,
+                                                                 const uint32_t* __restrict__ dirty, const uint32_t* __restrict__ n_dirty,
+                                                                 uint32_t* __restrict__ roots, uint32_t* n_roots) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *n_dirty) return;
+    const uint32_t i = dirty[k];
+    const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);
+    if (!rebuild_candidate(i, meta.y, meta.z, bad)) return;
+    uint32_t a = i;
+    while (a != 0) {                                                   // an outer candidate takes this subtree with it
+        a = nodes[a].parent;
+        const uint4 mm = *reinterpret_cast<const uint4*>(nodes + a);
+        if (rebuild_candidate(a, mm.y, mm.z, bad)) return;
+    }
+    roots[atomicAdd(n_roots, 1u)] = i;
+}
+// one warp per rebuild root: the shapes of its subtree in leaf order (index buffer of the rebuild) and the bounds of their centres
+template <class T>
+__global__ void __launch_bounds__(256) root_prep_kernel(const typename Traits<T>::Node* __restrict__ nodes, const uint32_t* __restrict__ node_start,
+                                                        const typename Traits<T>::DAabb* __restrict__ aabb, const uint32_t* __restrict__ roots,
+                                                        const uint32_t* __restrict__ n_roots, uint32_t* __restrict__ idx0, T* __restrict__ cb_roots) {
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5), nr = *n_roots;
+    for (uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < nr; k += warps) {
+        const uint32_t r = roots[k], cnt = nodes[r].shape;
+        T cmn[3] = {Traits<T>::inf(), Traits<T>::inf(), Traits<T>::inf()}, cmx[3] = {-Traits<T>::inf(), -Traits<T>::inf(), -Traits<T>::inf()};
+        for (uint32_t i = r + lane_id(); i < r + 2 * cnt - 1; i += 32) {
+            const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);
+            if (meta.y != BVH_INVALID) continue;
+            idx0[node_start[i]] = meta.w;
+            T mn[3], mx[3];
+            load_aabb(aabb + meta.w, mn, mx);
+            for (int c = 0; c < 3; ++c) { const T ctr = center1(mn[c], mx[c]); cmn[c] = min_t(cmn[c], ctr); cmx[c] = max_t(cmx[c], ctr); }
+        }
+        for (int c = 0; c < 3; ++c) {
+            typename Traits<T>::Key a = f2key(cmn[c]), b = f2key(cmx[c]);
+            a = warp_min_key(a); b = warp_max_key(b);
+            if (lane_id() == 0) { cb_roots[6 * (size_t)k + c] = key2f(a); cb_roots[6 * (size_t)k + 3 + c] = key2f(b); }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) clear_bad_kernel(const uint32_t* __restrict__ dirty, const uint32_t* __restrict__ n_dirty, uint8_t* __restrict__ bad) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < *n_dirty) bad[dirty[k]] = 0;
+}
+
+// The shapes `d_changed[0..m)` already carry their new AABBs in tree->d_aabb.  max_growth <= 0: boxes only.
+template <class T>
+int update_incremental(Tree<T>* tree, const uint32_t* d_changed, uint32_t m, double max_growth) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = tree->n, nn = tree->n_nodes;
+    const bool rebuild = max_growth > 0.0;
+    if (n < 3) return rebuild ? optimize(tree, max_growth) : refit(tree);
+    const unsigned gn = (nn + 255) / 256, gm = (m + 255) / 256;
+    if (!tree->d_arrive) {
+        BVH_TRY(dalloc_t(ctx, &tree->d_arrive, nn));
+        BVH_CUDA_TRY(cudaMemsetAsync(tree->d_arrive, 0, sizeof(uint32_t) * nn, st));
+    }
+    if (rebuild && !tree->d_bad) {
+        BVH_TRY(dalloc_t(ctx, &tree->d_bad, nn));
+        BVH_CUDA_TRY(cudaMemsetAsync(tree->d_bad, 0, nn, st));
+    }
+    if (rebuild && !tree->d_sa_base) {                                  // first update on this tree: the baseline is the tree before the motion
+        BVH_TRY(dalloc(ctx, &tree->d_sa_base, sizeof(T) * nn));
+        node_sa_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, nn, reinterpret_cast<T*>(tree->d_sa_base));
+        ctx->launches++;
+    }
+    Scratch scratch(ctx);
+    uint32_t *dirty = nullptr, *cnts = nullptr, *roots = nullptr, *idx0 = nullptr;
+    T* cb_roots = nullptr;
+    BVH_TRY(scratch.get(&dirty, nn));
+    BVH_TRY(scratch.get(&cnts, 2));                                     // [0] dirty nodes, [1] rebuild roots
+    BVH_CUDA_TRY(cudaMemsetAsync(cnts, 0, 2 * sizeof(uint32_t), st));
+    mark_paths_kernel<T><<<gm, 256, 0, st>>>(tree->d_nodes, tree->d_node_index, d_changed, m, tree->d_arrive);
+    climb_paths_kernel<T><<<gm, 256, 0, st>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, d_changed, m, tree->d_arrive,
+                                              reinterpret_cast<const T*>(tree->d_sa_base), (T)max_growth, rebuild ? tree->d_bad : nullptr, dirty, cnts);
+    ctx->launches += 2;
+    if (rebuild) {
+        BVH_TRY(scratch.get(&roots, n));
+        BVH_TRY(scratch.get(&idx0, n));
+        BVH_TRY(scratch.get(&cb_roots, 6 * (size_t)n / 2 + 6));         // rebuild roots are inner nodes of disjoint subtrees: at most n / 2 of them
+        select_roots_dirty_kernel<T><<<gn, 256, 0, st>>>(tree->d_nodes, tree->d_bad, dirty, cnts, roots, cnts + 1);
+        root_prep_kernel<T><<<std::max(1, ctx->sm_count * 8), 256, 0, st>>>(tree->d_nodes, tree->d_node_start, tree->d_aabb, roots, cnts + 1, idx0, cb_roots);
+        ctx->launches += 2;
+        BVH_CUDA_TRY(cudaGetLastError());
+        BVH_TRY(rebuild_subtrees(ctx, tree, roots, cnts + 1, cb_roots, idx0, true));
+        rebase_kernel<T><<<std::max(1, ctx->sm_count * 8), 256, 0, st>>>(tree->d_nodes, roots, cnts + 1, reinterpret_cast<T*>(tree->d_sa_base));
+        clear_bad_kernel<<<gn, 256, 0, st>>>(dirty, cnts, tree->d_bad);
+        ctx->launches += 2;
+    }
+    BVH_CUDA_TRY(cudaGetLastError());
+    BVH_TRY(build_traversal_records(tree));
+    if (tree->have_flat) BVH_TRY(build_flat(tree));
+    return BVHGPU_OK;
+}
+
 template <class T>
 int update_changed(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m, uint32_t* d_flags) {
     bvhgpu_ctx* ctx = tree->ctx;
@@ -384,6 +525,7 @@ int update_scatter(Tree<T>* tree, const uint32_t* d_changed, const typename Trai
 }
 
 #define INST(T)                                           \
+    template int update_incremental<T>(Tree<T>*, const uint32_t*, uint32_t, double); \
     template int update_changed<T>(Tree<T>*, const uint32_t*, const typename Traits<T>::Aabb*, uint32_t, uint32_t*); \
     template int update_scatter<T>(Tree<T>*, const uint32_t*, const typename Traits<T>::Aabb*, uint32_t); \
     template int optimize<T>(Tree<T>*, double);           \

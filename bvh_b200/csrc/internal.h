@@ -87,6 +87,8 @@ template <class T> struct Tree {
     uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
     typename Tr::TNode* d_tnodes = nullptr;   // [n_trec] traversal records
     uint32_t n_trec = 0;
+    uint32_t* d_arrive = nullptr;             // [2n-1] arrival counters of the incremental update (all zero between calls)
+    uint8_t* d_bad = nullptr;                 // [2n-1] growth flags of the incremental update (all zero between calls)
     void* d_sa_base = nullptr;                // [2n-1] surface area of every inner node when it was last (re)built: baseline of bvhgpu_optimize / update
     void* d_tris = nullptr;                   // [n] triangle vertices (padded), optional: bvhgpu_tree_set_triangles_*
     typename Tr::Flat* d_flat = nullptr;      // [n_flat] reference-layout FlatBvh (built on demand)
@@ -148,7 +150,8 @@ template <class T> int treelet_finish(bvhgpu_ctx* ctx, Tree<T>* tree, TreeletSes
 // ---- rebuild session (build_sah.cu), used by optimize(): the exact builder restarted from inner nodes.  d_roots[0 .. *d_n_roots)
 // are node indices of disjoint subtrees, cb[node][6] the bounds of the shape centres below every node, idx0 the shapes in
 // leaf order.  Rewrites d_nodes / d_node_index / d_node_start of those subtrees in place.
-template <class T> int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0);
+// cb_by_root: cb holds 6 values per ROOT (in d_roots order) instead of per node
+template <class T> int rebuild_subtrees(bvhgpu_ctx* ctx, Tree<T>* tree, const uint32_t* d_roots, const uint32_t* d_n_roots, const T* cb, uint32_t* idx0, bool cb_by_root);
 
 // ---- lbvh.cu ----
 template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aabb* in_aabbs, uint32_t n, Tree<T>* tree, bool treelets);
@@ -161,6 +164,7 @@ template <class T> int refit(Tree<T>* tree);                     // recompute ch
 template <class T> int optimize(Tree<T>* tree, double max_growth);   // refit + exact rebuild of the degraded subtrees
 // update_shapes form: validate (flags[0] NaN, flags[1] bad index) / scatter m changed AABBs (device pointers) into tree->d_aabb
 template <class T> int update_changed(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m, uint32_t* d_flags);
+template <class T> int update_incremental(Tree<T>* tree, const uint32_t* d_changed, uint32_t m, double max_growth);
 template <class T> int update_scatter(Tree<T>* tree, const uint32_t* d_changed, const typename Traits<T>::Aabb* d_fresh, uint32_t m);
 
 // ---- traverse.cu ----

@@ -110,7 +110,47 @@ b64r = api.Bvh.build(a64, prec="f64", ctx=ctx); b64r.refit(a64m); c_refit = b64r
 b64f = api.Bvh.build(a64m, prec="f64", ctx=ctx); c_fresh = b64f.sah_cost()[0]; b64f.free()
 out["optimize_10M_f64_1pct"] = {"host_call_ms": t_opt, "rebuilt_shapes": rb, "sah_cost_before_motion": c0, "sah_cost_refit_only": c_refit,
                                 "sah_cost_optimize": c_opt, "sah_cost_fresh_build": c_fresh}
+# Bvh::update_shapes' own signature: only the changed shapes cross the boundary (5.2 MB instead of 480 MB) and only their root paths are
+# touched.  ONE tree, every call moves a fresh random 1 % of the shapes by <= 10 from their home position (steady state of a moving scene;
+# the first rebuilding call also grows the memory pool by the builder's scratch and is reported separately).
+bu = api.Bvh.build(a64, prec="f64", ctx=ctx)
+fnu = capi.lib().bvhgpu_update_f64x3
+import ctypes as C
+def one_update(growth):
+    idx = rng.choice(len(a64), len(a64) // 100, replace=False).astype(np.uint32)
+    src = a64[idx].copy(); dlt = rng.uniform(-10.0, 10.0, (len(idx), 3)); src["min"] += dlt; src["max"] += dlt
+    rbc = C.c_size_t(0)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    capi.check(fnu(bu._h, idx.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p), len(idx), C.c_double(growth), C.byref(rbc)))
+    return (time.perf_counter() - t0) * 1e3, rbc.value
+refit_ms = [one_update(0.0)[0] for _ in range(6)]
+first_ms, first_rb = one_update(1.5)
+steady = [one_update(1.5) for _ in range(6)]
+out["update_shapes_10M_f64_1pct"] = {"refit_only_host_call_ms_median": sorted(refit_ms)[3], "rebuild_first_call_ms": first_ms, "rebuild_first_call_rebuilt_shapes": first_rb,
+                                     "rebuild_host_call_ms_median": sorted(t for t, _ in steady)[3], "rebuild_host_call_ms_all": [t for t, _ in steady],
+                                     "rebuilt_shapes_per_call": [r for _, r in steady], "sah_cost_after": bu.sah_cost()[0], "bytes_h2d_per_call": int(len(a64) // 100 * (4 + 48))}
+bu.free()
 del a64, a64m
+# closest hit on Sponza: 4 M primary rays, triangle mode (Moeller-Trumbore fused, front to back, pruned) and AABB mode
+z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "sponza_tris.npz"))
+tri9 = z["vertices"][z["triangles"].astype(np.int64)].astype(np.float32).reshape(-1, 9)
+sbvh.set_triangles(tri9)
+o, d = scenes.pinhole_rays(2048, 2048)
+prim = api.Ray.new(o, d, ctx=ctx)
+d_prim = to_dev(prim)
+nq = len(prim)
+d_s = torch.empty(nq, dtype=torch.int32, device=dev); d_d = torch.empty(nq, dtype=torch.float32, device=dev)
+for tri, name in ((1, "triangles"), (0, "aabb")):
+    fn = lambda: capi.check(capi.lib().bvhgpu_closest_hit_dev_f32x3(sbvh._h, C.c_void_p(d_prim.data_ptr()), 0, nq, tri, C.c_void_p(d_s.data_ptr()), C.c_void_p(d_d.data_ptr()), None))
+    ms = timed(fn)
+    hit = int((d_s != -1).sum().item())
+    out[f"closest_hit_sponza_4M_primary_{name}"] = {"ms": ms, "Mrays_per_s": nq / ms / 1e3, "rays_with_a_hit": hit}
+o, d = scenes.ray_endpoints(2_000_000, bounds=(bmin, bmax))
+inc = api.Ray.new(o, d, ctx=ctx); d_inc = to_dev(inc)
+d_s2 = torch.empty(len(inc), dtype=torch.int32, device=dev); d_d2 = torch.empty(len(inc), dtype=torch.float32, device=dev)
+ms = timed(lambda: capi.check(capi.lib().bvhgpu_closest_hit_dev_f32x3(sbvh._h, C.c_void_p(d_inc.data_ptr()), 0, len(inc), 1, C.c_void_p(d_s2.data_ptr()), C.c_void_p(d_d2.data_ptr()), None)))
+out["closest_hit_sponza_2M_incoherent_triangles"] = {"ms": ms, "Mrays_per_s": len(inc) / ms / 1e3, "rays_with_a_hit": int((d_s2 != -1).sum().item())}
 # the reference's own update benchmark shape (optimization.rs:693-725): 120 k triangles, p % moved by <= 10.0.  (The oracle's update_shapes
 # on the same motion is timed and costed in tests/test_gpu_parity.py::test_optimize_vs_reference_update_120k -> gpurun_out/optimize_vs_reference.json.)
 a = scenes.create_n_cubes_aabbs(10000)

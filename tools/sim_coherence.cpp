@@ -81,9 +81,42 @@ int main(int argc, char** argv) {
         printf("%-28s lane-visits/ray %6.1f  lookups/ray %6.1f  warp-steps/ray %5.2f  lanes/step %5.1f  distinct/step %5.1f\n", name,
                (double)lane_visits / R, (double)lookups / R, (double)steps / R, (double)lane_visits / steps, (double)lookups / steps);
     };
+    // the persistent refill kernel: a pool of W warps pulls rays from a ticket counter; a warp refills when >= 8 lanes are idle
+    auto simulate_refill = [&](const char* name, const std::vector<uint32_t>& order) {
+        const int W = 2048;                                   // concurrently resident warps (model: round-robin stepping)
+        struct Warp { uint32_t pos[32], ray[32]; };
+        std::vector<Warp> warps(W);
+        for (auto& w : warps) for (int l = 0; l < 32; ++l) w.ray[l] = U32_MAX;
+        uint32_t ticket = 0;
+        uint64_t lane_visits = 0, lookups = 0, steps = 0;
+        bool any = true;
+        while (any) {
+            any = false;
+            for (auto& w : warps) {
+                int idle = 0;
+                for (int l = 0; l < 32; ++l) idle += w.ray[l] == U32_MAX;
+                if ((idle >= 8 || idle == 32) && ticket < R) for (int l = 0; l < 32 && ticket < R; ++l) if (w.ray[l] == U32_MAX) { w.ray[l] = order[ticket++]; w.pos[l] = 0; }
+                uint32_t act[32]; int na = 0;
+                for (int l = 0; l < 32; ++l) if (w.ray[l] != U32_MAX) act[na++] = w.pos[l];
+                if (!na) continue;
+                any = true;
+                ++steps; lane_visits += na;
+                std::sort(act, act + na);
+                lookups += std::unique(act, act + na) - act;
+                for (int l = 0; l < 32; ++l) if (w.ray[l] != U32_MAX) {
+                    const Rec& r = rec[w.pos[l]];
+                    w.pos[l] = hit(rays[w.ray[l]], r) ? w.pos[l] + 1 : r.skip;
+                    if (w.pos[l] >= rec.size()) w.ray[l] = U32_MAX;
+                }
+            }
+        }
+        printf("refill %-21s lane-visits/ray %6.1f  lookups/ray %6.1f  warp-steps/ray %5.2f  lanes/step %5.1f  distinct/step %5.1f\n", name,
+               (double)lane_visits / R, (double)lookups / R, (double)steps / R, (double)lane_visits / steps, (double)lookups / steps);
+    };
     std::vector<uint32_t> id(R);
     std::iota(id.begin(), id.end(), 0);
     simulate("original order", id);
+    simulate_refill("original order", id);
     auto key_origin = [&](uint32_t i, int bits) {
         uint32_t q[3];
         for (int k = 0; k < 3; ++k) { double f = (rays[i].origin[k] + 100000.0) / 200000.0; f = std::min(std::max(f, 0.0), 0.999999); q[k] = (uint32_t)(f * (1u << bits)); }
@@ -103,6 +136,7 @@ int main(int argc, char** argv) {
         for (uint32_t i = 0; i < R; ++i) { uint64_t oct = (rays[i].direction[0] < 0) | ((rays[i].direction[1] < 0) << 1) | ((rays[i].direction[2] < 0) << 2); key[i] = (oct << 60) | key_origin(i, 10); }
         std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         simulate("octant, morton(origin)", o);
+        simulate_refill("octant, morton(origin)", o);
     }
     {   // origin coarse (4 bits/axis), then direction quantised (morton of dir 5 bits)
         std::vector<uint32_t> o = id;
@@ -114,6 +148,7 @@ int main(int argc, char** argv) {
         }
         std::stable_sort(o.begin(), o.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
         simulate("origin 3b, morton(dir) 5b", o);
+        simulate_refill("origin 3b, morton(dir) 5b", o);
     }
     return 0;
 }
