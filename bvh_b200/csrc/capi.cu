@@ -254,8 +254,9 @@ static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, 
     BVH_TRY(resolve_status(tree));
     const size_t stride = kind == BVHGPU_QUERY_AABB ? 6 : (kind == BVHGPU_QUERY_POINT ? 3 : 4);
     T* d_q = nullptr;
+    Scratch scratch(ctx);                                           // released on every return path
     if (n) {
-        BVH_TRY(dalloc_t(ctx, &d_q, n * stride));
+        BVH_TRY(scratch.get(&d_q, n * stride));
         BVH_CUDA_TRY(cudaMemcpyAsync(d_q, queries, sizeof(T) * n * stride, cudaMemcpyHostToDevice, ctx->stream));
     }
     size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 16 * n), 1024), tot = 0;
@@ -267,7 +268,6 @@ static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, 
         if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }
         break;
     }
-    dfree(ctx, d_q);
     if (total) *total = tot;
     if (rc != BVHGPU_OK) return rc;
     BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -287,9 +287,10 @@ static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n,
     if (n == 0) return BVHGPU_OK;
     T *d_p = nullptr, *d_d = nullptr;
     uint32_t* d_s = nullptr;
-    BVH_TRY(dalloc_t(ctx, &d_p, n * 3));
-    BVH_TRY(dalloc_t(ctx, &d_d, n));
-    BVH_TRY(dalloc_t(ctx, &d_s, n));
+    Scratch scratch(ctx);
+    BVH_TRY(scratch.get(&d_p, n * 3));
+    BVH_TRY(scratch.get(&d_d, n));
+    BVH_TRY(scratch.get(&d_s, n));
     BVH_CUDA_TRY(cudaMemcpyAsync(d_p, points, sizeof(T) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
     int rc = nearest_device<T>(tree, mode, d_p, n, d_s, d_d);
     if (rc == BVHGPU_OK) {
@@ -297,7 +298,6 @@ static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n,
         BVH_CUDA_TRY(cudaMemcpyAsync(out_dist, d_d, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
         BVH_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
-    dfree(ctx, d_p); dfree(ctx, d_d); dfree(ctx, d_s);
     return rc;
 }
 
@@ -308,8 +308,9 @@ static int nearest_candidates_host_impl(Tree<T>* tree, const T* points, size_t n
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
     BVH_TRY(resolve_status(tree));
     T* d_p = nullptr;
+    Scratch scratch(ctx);
     if (n) {
-        BVH_TRY(dalloc_t(ctx, &d_p, n * 3));
+        BVH_TRY(scratch.get(&d_p, n * 3));
         BVH_CUDA_TRY(cudaMemcpyAsync(d_p, points, sizeof(T) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
     }
     size_t want = std::max<size_t>(std::max<size_t>(tree->hits_cap, 16 * n), 1024), tot = 0;
@@ -321,7 +322,6 @@ static int nearest_candidates_host_impl(Tree<T>* tree, const T* points, size_t n
         if (rc == BVHGPU_ERR_CAPACITY && tot <= 0xFFFFFFFFull && attempt == 0) { want = tot; continue; }
         break;
     }
-    dfree(ctx, d_p);
     if (total) *total = tot;
     if (rc != BVHGPU_OK) return rc;
     BVH_CUDA_TRY(cudaMemcpyAsync(offsets, tree->d_offsets, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -342,10 +342,11 @@ static int ordered_host_impl(Tree<T>* tree, const typename Traits<T>::Ray* rays,
     typename Traits<T>::Ray* d_rays = nullptr;
     uint32_t *d_off = nullptr, *d_hits = nullptr;
     T* d_dists = nullptr;
-    BVH_TRY(dalloc_t(ctx, &d_rays, nrays));
-    BVH_TRY(dalloc_t(ctx, &d_off, nrays + 1));
-    BVH_TRY(dalloc_t(ctx, &d_hits, cap));
-    BVH_TRY(dalloc_t(ctx, &d_dists, cap));
+    Scratch scratch(ctx);
+    BVH_TRY(scratch.get(&d_rays, nrays));
+    BVH_TRY(scratch.get(&d_off, nrays + 1));
+    BVH_TRY(scratch.get(&d_hits, cap));
+    BVH_TRY(scratch.get(&d_dists, cap));
     if (nrays) BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, sizeof(*rays) * nrays, cudaMemcpyHostToDevice, ctx->stream));
     size_t tot = 0;
     int rc = traverse_ordered_device<T>(tree, d_rays, nrays, ascending, d_off, d_hits, d_dists, cap, &tot);
@@ -357,7 +358,6 @@ static int ordered_host_impl(Tree<T>* tree, const typename Traits<T>::Ray* rays,
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("traverse_ordered: %s", cudaGetErrorString(e)); rc = BVHGPU_ERR_CUDA; }
     }
-    dfree(ctx, d_rays); dfree(ctx, d_off); dfree(ctx, d_hits); dfree(ctx, d_dists);
     return rc;
 }
 

@@ -211,12 +211,12 @@ template <class T> int refit(Tree<T>* tree) {
     bvhgpu_ctx* ctx = tree->ctx;
     if (tree->n < 2) return tree->n == 1 ? build_traversal_records(tree) : (int)BVHGPU_OK;
     uint32_t* arrivals = nullptr;
-    BVH_TRY(dalloc_t(ctx, &arrivals, tree->n_nodes));
+    Scratch scratch(ctx);
+    BVH_TRY(scratch.get(&arrivals, tree->n_nodes));
     BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * tree->n_nodes, ctx->stream));
     refit_kernel<T, false><<<(tree->n + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->d_node_index, tree->d_aabb, tree->n, arrivals, nullptr);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
-    dfree(ctx, arrivals);
     BVH_TRY(build_traversal_records(tree));
     if (tree->have_flat) BVH_TRY(build_flat(tree));
     return BVHGPU_OK;
@@ -315,12 +315,13 @@ template <class T> int optimize(Tree<T>* tree, double max_growth) {
         ctx->launches++;
     }
     T* sa_old = reinterpret_cast<T*>(tree->d_sa_base);
-    BVH_TRY(dalloc_t(ctx, &cb, (size_t)nn * 6));
-    BVH_TRY(dalloc_t(ctx, &bad, nn));
-    BVH_TRY(dalloc_t(ctx, &roots, n));
-    BVH_TRY(dalloc_t(ctx, &n_roots, 1));
-    BVH_TRY(dalloc_t(ctx, &idx0, n));
-    BVH_TRY(dalloc_t(ctx, &arrivals, nn));
+    Scratch scratch(ctx);                                               // released on every return path
+    BVH_TRY(scratch.get(&cb, (size_t)nn * 6));
+    BVH_TRY(scratch.get(&bad, nn));
+    BVH_TRY(scratch.get(&roots, n));
+    BVH_TRY(scratch.get(&n_roots, 1));
+    BVH_TRY(scratch.get(&idx0, n));
+    BVH_TRY(scratch.get(&arrivals, nn));
     BVH_CUDA_TRY(cudaMemsetAsync(arrivals, 0, sizeof(uint32_t) * nn, st));
     BVH_CUDA_TRY(cudaMemsetAsync(n_roots, 0, sizeof(uint32_t), st));
     const unsigned gn = (nn + 255) / 256, gs = (n + 255) / 256;
@@ -333,7 +334,6 @@ template <class T> int optimize(Tree<T>* tree, double max_growth) {
     BVH_TRY(rebuild_subtrees(ctx, tree, roots, n_roots, cb, idx0, false));
     rebase_kernel<T><<<std::max(1, std::min(ctx->sm_count * 4, (int)n)), 256, 0, st>>>(tree->d_nodes, roots, n_roots, sa_old);
     ctx->launches++;
-    dfree(ctx, cb); dfree(ctx, bad); dfree(ctx, roots); dfree(ctx, n_roots); dfree(ctx, idx0); dfree(ctx, arrivals);
     BVH_TRY(build_traversal_records(tree));
     if (tree->have_flat) BVH_TRY(build_flat(tree));
     return BVHGPU_OK;

@@ -1224,9 +1224,10 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
     const uint32_t R = (uint32_t)nq, nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;
-    BVH_TRY(dalloc_t(ctx, &counts, R));
-    BVH_TRY(dalloc_t(ctx, &local, R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
+    Scratch scratch(ctx);                                      // released on every return path
+    BVH_TRY(scratch.get(&counts, R));
+    BVH_TRY(scratch.get(&local, R));
+    BVH_TRY(scratch.get(&sums, (size_t)nblk + 2));
     BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
     const bool flat = mode == BVHGPU_TRAVERSE_FLAT;
     int rc = kind == BVHGPU_QUERY_AABB  ? query_launch<T, BVHGPU_QUERY_AABB>(tree, flat, d_queries, R, counts, local, sums, nblk, d_offsets, d_hits, cap)
@@ -1241,7 +1242,6 @@ int query_device(Tree<T>* tree, int mode, int kind, const T* d_queries, size_t n
         tree->last_total = (size_t)h[0];
         if (h[0] > 0xFFFFFFFFull || (d_hits && h[0] > cap)) { set_error("query: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
     }
-    dfree(ctx, counts); dfree(ctx, local); dfree(ctx, sums);
     return rc;
 }
 template int query_device<float>(Tree<float>*, int, int, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
@@ -1398,12 +1398,11 @@ int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint3
     BVH_TRY(resolve_status(tree));
     if (nq == 0 || tree->n == 0) return query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, nullptr, nq, d_offsets, d_cand, cap, total);
     T* rec = nullptr;
-    BVH_TRY(dalloc_t(ctx, &rec, nq * 4));
+    Scratch scratch(ctx);
+    BVH_TRY(scratch.get(&rec, nq * 4));
     nearest_bound_kernel<T><<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(tree->d_nodes, tree->d_aabb, d_points, (uint32_t)nq, rec);
     ctx->launches++;
-    const int rc = query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, rec, nq, d_offsets, d_cand, cap, total);
-    dfree(ctx, rec);
-    return rc;
+    return query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, rec, nq, d_offsets, d_cand, cap, total);
 }
 template int nearest_device<float>(Tree<float>*, int, const float*, size_t, uint32_t*, float*);
 template int nearest_device<double>(Tree<double>*, int, const double*, size_t, uint32_t*, double*);
@@ -1481,9 +1480,10 @@ int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays
     const uint32_t R = (uint32_t)nrays, nblk = (R + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t *counts = nullptr, *local = nullptr;
     unsigned long long* sums = nullptr;
-    BVH_TRY(dalloc_t(ctx, &counts, R));
-    BVH_TRY(dalloc_t(ctx, &local, R));
-    BVH_TRY(dalloc_t(ctx, &sums, (size_t)nblk + 2));
+    Scratch scratch(ctx);
+    BVH_TRY(scratch.get(&counts, R));
+    BVH_TRY(scratch.get(&local, R));
+    BVH_TRY(scratch.get(&sums, (size_t)nblk + 2));
     BVH_CUDA_TRY(cudaMemsetAsync(sums + nblk, 0, 2 * sizeof(unsigned long long), st));
     const int grid = (R + 255) / 256;
     ordered_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, d_rays, R, ascending, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
@@ -1500,7 +1500,6 @@ int traverse_ordered_device(Tree<T>* tree, const typename Traits<T>::Ray* d_rays
         *total = (size_t)h[0];
         if (h[0] > 0xFFFFFFFFull || h[0] > cap) { set_error("traverse_ordered: %llu hits do not fit capacity %zu", h[0], cap); rc = BVHGPU_ERR_CAPACITY; }
     }
-    dfree(ctx, counts); dfree(ctx, local); dfree(ctx, sums);
     return rc;
 }
 template int traverse_ordered_device<float>(Tree<float>*, const bvh_ray3f*, size_t, int, uint32_t*, uint32_t*, float*, size_t, size_t*);
