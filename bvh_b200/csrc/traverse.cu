@@ -542,12 +542,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_post_kernel(const uint32_t*
 }
 
 // Global offsets: one block per tile of every source rank.
-__global__ void __launch_bounds__(SCAN_THREADS) goffsets_kernel(PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ offsets) {
+__device__ __forceinline__ void goffsets_body(const PeerBoxes& pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ offsets,
+                                              uint32_t bid, uint32_t ntiles) {
     __shared__ uint32_t wsum[SCAN_THREADS / 32];
     __shared__ uint32_t failed;
     if (threadIdx.x == 0) failed = *(volatile uint32_t*)pb.err;
     __syncthreads();
-    const unsigned long long g = blockIdx.x;
+    const unsigned long long g = bid;
     if (failed == 0u) {
         int sg = 0;
         unsigned long long tb = 0, rb = 0, re = pb.rays_before[1];
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) goffsets_kernel(PeerBoxes pb, co
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) if (j0 + k < re) offsets[j0 + k] = ov[k];
         }
-        if (g == gridDim.x - 1 && threadIdx.x == 0) {
+        if (g == ntiles - 1 && threadIdx.x == 0) {
             unsigned long long ng = 0;
 #pragma unroll
             for (int k = 1; k <= BVHGPU_MAX_PEERS; ++k) if (k == pb.world) ng = pb.rays_before[k];
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) goffsets_kernel(PeerBoxes pb, co
             offsets[ng] = grand > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)grand;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {                 // the step ends when every peer's hit lists have landed here
+    if (bid == 0 && threadIdx.x < 32) {                        // the step ends when every peer's hit lists have landed here
         const int lane = threadIdx.x;
         const unsigned long long par = pb.seq & 1ull;
         unsigned long long waited = 0;
@@ -635,14 +636,15 @@ struct EmitDst {
 // Pass 2: final offsets + hit lists.  Rays with <= K hits copy their slots, the rest walk again.  Sharded: the block then ships
 // its piece of the hit lists -- contiguous, because the block's rays are -- to every peer.
 template <class T, bool FLAT>
-__global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
-                                                   const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                   RaySrc<T> rays, uint32_t nrays,
-                                                   const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
-                                                   const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
-                                                   const unsigned long long* __restrict__ total,
-                                                   EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count,
-                                                   PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ arrival) {
+__device__ __forceinline__ void emit_body(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                          const typename Traits<T>::DAabb* __restrict__ aabb,
+                                          const RaySrc<T>& rays, uint32_t nrays,
+                                          const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
+                                          const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
+                                          const unsigned long long* __restrict__ total,
+                                          const EmitDst& dst, unsigned long long cap, uint32_t first, uint32_t count,
+                                          const PeerBoxes& pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ arrival,
+                                          uint32_t bid, uint32_t nblocks) {
     __shared__ unsigned long long rng[2];
     __shared__ uint32_t failed;
     __shared__ bool last;
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
         __syncthreads();
         hbase = xinfo[pb.rank];
     }
-    const uint32_t r = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = first + bid * blockDim.x + threadIdx.x;
     if (!sharded || failed == 0u) {
         if (r == first && dst.offsets) {          // (sliced host path: the last slice's write is the final total)
             const unsigned long long t = *total;
@@ -665,7 +667,15 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
             const uint32_t c = counts[r];
             if (c != 0 && dst.hits != nullptr) {
                 if (c <= K) {
-                    for (uint32_t k = 0; k < c; ++k) if (off + k < cap) dst.hits[off + k] = slots[(size_t)k * nrays + r];
+                    // 8 slot loads in flight per lane before the first store (one load per iteration left the lane waiting on every
+                    // single slot: 77 % of the kernel's stall samples on the 16 M-ray Sponza batch)
+                    for (uint32_t k0 = 0; k0 < c; k0 += 8) {
+                        uint32_t h[8];
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) if (k0 + j < c) h[j] = __ldcs(slots + (size_t)(k0 + j) * nrays + r);
+#pragma unroll
+                        for (uint32_t j = 0; j < 8; ++j) if (k0 + j < c && off + k0 + j < cap) dst.hits[off + k0 + j] = h[j];
+                    }
                 } else {
                     T o[3], inv[3];
                     load_ray<T, false>(rays, r, o, inv);
@@ -679,7 +689,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
     bool pushed = false;
     if (failed == 0u && pb.world > 1) {
         if (threadIdx.x == 0) {
-            const uint32_t r0 = first + blockIdx.x * blockDim.x;
+            const uint32_t r0 = first + bid * blockDim.x;
             const uint32_t r1 = min(r0 + blockDim.x, first + count) - 1u;
             rng[0] = hbase + blocksum[r0 / SCAN_TILE] + local[r0];
             rng[1] = hbase + blocksum[r1 / SCAN_TILE] + local[r1] + counts[r1];
@@ -713,13 +723,40 @@ __global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNo
     __syncthreads();
     if (threadIdx.x == 0) {
         if (pushed) __threadfence_system();                           // only a block that stored to peers has something to order
-        last = atomicAdd(arrival, 1u) == gridDim.x - 1;
+        last = atomicAdd(arrival, 1u) == nblocks - 1;
     }
     __syncthreads();
     if (!last) return;
     if (threadIdx.x == 0) { __threadfence_system(); *arrival = 0u; }
     __syncthreads();
     if (threadIdx.x < (unsigned)pb.world) st_release_sys(pb.box[threadIdx.x] + MB_DONE + (pb.seq & 1ull) * BVHGPU_MAX_PEERS + pb.rank, pb.seq);
+}
+template <class T, bool FLAT>
+__global__ void __launch_bounds__(256) emit_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                   const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                   RaySrc<T> rays, uint32_t nrays,
+                                                   const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
+                                                   const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
+                                                   const unsigned long long* __restrict__ total,
+                                                   EmitDst dst, unsigned long long cap, uint32_t first, uint32_t count,
+                                                   PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ arrival) {
+    emit_body<T, FLAT>(trec, n_rec, aabb, rays, nrays, counts, slots, K, local, blocksum, total, dst, cap, first, count, pb, xinfo, arrival, blockIdx.x, gridDim.x);
+}
+// Sharded step: the emit blocks and the global-offsets blocks are independent of each other (both only need the posts), so they are
+// ONE launch: blocks [0, emit_blocks) emit and ship hit lists, the rest rebuild the offsets -- one kernel boundary less, and the
+// offsets pass overlaps the emit.
+template <class T, bool FLAT>
+__global__ void __launch_bounds__(256) emit_goffsets_kernel(const typename Traits<T>::TNode* __restrict__ trec, uint32_t n_rec,
+                                                            const typename Traits<T>::DAabb* __restrict__ aabb,
+                                                            RaySrc<T> rays, uint32_t nrays,
+                                                            const uint32_t* __restrict__ counts, const uint32_t* __restrict__ slots, uint32_t K,
+                                                            const uint32_t* __restrict__ local, const unsigned long long* __restrict__ blocksum,
+                                                            const unsigned long long* __restrict__ total,
+                                                            EmitDst dst, unsigned long long cap, uint32_t count,
+                                                            PeerBoxes pb, const unsigned long long* __restrict__ xinfo, uint32_t* __restrict__ arrival,
+                                                            uint32_t emit_blocks, uint32_t* __restrict__ offsets) {
+    if (blockIdx.x < emit_blocks) emit_body<T, FLAT>(trec, n_rec, aabb, rays, nrays, counts, slots, K, local, blocksum, total, dst, cap, 0u, count, pb, xinfo, arrival, blockIdx.x, emit_blocks);
+    else goffsets_body(pb, xinfo, offsets, blockIdx.x - emit_blocks, gridDim.x - emit_blocks);
 }
 
 // Launch pass 1 over rays [first, first+count): persistent refill kernel (default) or one ray per thread.
@@ -850,13 +887,15 @@ int traverse_device(Tree<T>* tree, int mode, const void* d_rays, uint32_t fmt, s
         BVH_CUDA_TRY(cudaMemcpyAsync(h, tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         BVH_CUDA_TRY(cudaEventRecord(ctx->ev_total, st));
     }
-    if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
-    else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
-    ctx->launches++;
     if (shard) {
-        goffsets_kernel<<<(unsigned)pb.tiles_before[pb.world], SCAN_THREADS, 0, st>>>(pb, tail + S_XINFO, (uint32_t*)shard->offsets);
-        ctx->launches++;
+        const unsigned g2 = (unsigned)grid + (unsigned)pb.tiles_before[pb.world];
+        if (flat) emit_goffsets_kernel<T, true><<<g2, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, R, pb, tail + S_XINFO, arrival, (uint32_t)grid, (uint32_t*)shard->offsets);
+        else      emit_goffsets_kernel<T, false><<<g2, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, R, pb, tail + S_XINFO, arrival, (uint32_t)grid, (uint32_t*)shard->offsets);
+    } else {
+        if (flat) emit_kernel<T, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
+        else      emit_kernel<T, false><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, counts, slots, K, local, sums, tail + S_TOTAL, dst, (unsigned long long)cap, 0u, R, pb, tail + S_XINFO, arrival);
     }
+    ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
     int rc = BVHGPU_OK;
     if (total) {
