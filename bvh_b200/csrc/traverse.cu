@@ -369,14 +369,14 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(unsigned long long* _
 //   counts of tile g : 8192 bytes at 8192*g -- the per-ray hit counts in the tile's own width (1, 2 or 4 bytes, from the tile's
 //                      largest count): 1 byte per ray crosses NVLink on ordinary batches, not a 4-byte offset
 //   table entry g    : u64 at table_off + 8*g = exclusive hit offset of the tile inside its source's list | width << 56
-// The step is the SAME number of kernels as on one GPU (after the walk: scan_post, emit, + goffsets):
+// The step is the SAME number of launches as on one GPU (after the walk: scan_post, then emit with the goffsets blocks appended):
 //   scan_post  per tile: local scan, counts pushed to all ranks; the last block scans the tile sums, pushes the tile table,
 //              publishes the total (a peer that sees the seq also sees counts and table) and then waits for the peers' posts
 //              (LOCAL polling), which fixes every source's hit base
 //   emit       hit lists into the local copy of the global hit buffer at hit base + local offset, then the block copies its
 //              contiguous piece to every peer (16-byte P2P stores); last block: done flags
-//   goffsets   per tile of every source: offsets = hit base of the source + tile offset + prefix of the staged counts;
-//              block 0 ends the step by waiting for the peers' done flags
+//   goffsets   (extra blocks of the emit launch) per tile of every source: offsets = hit base of the source + tile offset + prefix of
+//              the staged counts; block 0 ends the step by waiting for the peers' done flags
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }

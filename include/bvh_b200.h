@@ -227,9 +227,9 @@ int bvhgpu_traverse_od_dev_f64x3(bvhgpu_tree3d* tree, int mode, const void* dev_
  *      the global hit buffer, and every block ships its contiguous piece to all peers with whole 16-byte P2P stores
  *      (4-byte stores scattered straight from the emit loop reached a small fraction of the NVLink rate: 12.9 ms per
  *      16 M-ray Sponza step on 4 GPUs against 2.7 ms this way on 8); the last block raises the done flags;
- *   3. one more kernel rebuilds the global u32 offsets on every rank from the staged counts (1 byte per ray crossed
- *      NVLink instead of 4) and ends the step by waiting for the peers' done flags: when the stream reaches the end of the
- *      step, this rank's copy of the global CSR is complete.  Same number of kernels as a single-GPU step plus one.
+ *   3. extra blocks of the same launch rebuild the global u32 offsets on every rank from the staged counts (1 byte per ray
+ *      crossed NVLink instead of 4) and end the step by waiting for the peers' done flags: when the stream reaches the end of
+ *      the step, this rank's copy of the global CSR is complete.  Same number of launches as a single-GPU step.
  * `seq` must increase by one per call on all ranks.  No host synchronisation; failures (a peer that never answers)
  * are reported by bvhgpu_synchronize.  Mailbox layout (trace words for diagnostics included): traverse.cu. */
 #define BVHGPU_MAX_PEERS 8
