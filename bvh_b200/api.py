@@ -322,6 +322,15 @@ class Bvh:
         capi.check(getattr(capi.lib(), f"bvhgpu_nearest_{self._d['suffix']}")(self._h, mode, _ptr(p), len(p), _ptr(shape), _ptr(dist)))
         return shape, dist
 
+    def nearest_triangles_batch(self, points, mode: int = capi.TRAVERSE_BVH):
+        """Bvh::nearest_to / FlatBvh::nearest_to for triangle shapes (set_triangles first): the reference's walk with
+        Triangle::distance_squared (testbase.rs:353-443) at the leaves, on the device: (shape index, distance) per point."""
+        p = np.ascontiguousarray(points, dtype=self._d["scalar"]).reshape(-1, 3)
+        shape = np.zeros(len(p), dtype=np.uint32)
+        dist = np.zeros(len(p), dtype=self._d["scalar"])
+        capi.check(getattr(capi.lib(), f"bvhgpu_nearest_triangles_{self._d['suffix']}")(self._h, mode, _ptr(p), len(p), _ptr(shape), _ptr(dist)))
+        return shape, dist
+
     def nearest_candidates(self, points):
         """For shapes with their own PointDistance: CSR (offsets, shape indices) of candidate lists that contain the nearest shape of
         every point; evaluate distance_squared on each list and keep the minimum (see `nearest_to`)."""

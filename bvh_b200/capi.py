@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         getattr(L, f"bvhgpu_sah_cost_{s}").argtypes = [vp, C.POINTER(C.c_double)]
         getattr(L, f"bvhgpu_refit_{s}").argtypes = [vp, vp, sz]
         getattr(L, f"bvhgpu_nearest_{s}").argtypes = [vp, C.c_int, vp, sz, vp, vp]
+        getattr(L, f"bvhgpu_nearest_triangles_{s}").argtypes = [vp, C.c_int, vp, sz, vp, vp]
         getattr(L, f"bvhgpu_nearest_candidates_{s}").argtypes = [vp, vp, sz, vp, vp, sz, C.POINTER(C.c_size_t)]
         getattr(L, f"bvhgpu_optimize_{s}").argtypes = [vp, vp, sz, C.c_double, C.POINTER(C.c_size_t)]
     for s in ("f32x2", "f64x2"):

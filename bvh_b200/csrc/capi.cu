@@ -279,7 +279,7 @@ static int query_host_impl(Tree<T>* tree, int mode, int kind, const T* queries, 
 }
 
 template <class T>
-static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist) {
+static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist, int use_triangles = 0) {
     if (!tree || (n && (!points || !out_shape || !out_dist))) { set_error("nearest: null argument"); return BVHGPU_ERR_INVALID; }
     bvhgpu_ctx* ctx = tree->ctx;
     BVH_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -292,7 +292,7 @@ static int nearest_host_impl(Tree<T>* tree, int mode, const T* points, size_t n,
     BVH_TRY(scratch.get(&d_d, n));
     BVH_TRY(scratch.get(&d_s, n));
     BVH_CUDA_TRY(cudaMemcpyAsync(d_p, points, sizeof(T) * n * 3, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = nearest_device<T>(tree, mode, d_p, n, d_s, d_d);
+    int rc = nearest_device<T>(tree, mode, d_p, n, d_s, d_d, use_triangles);
     if (rc == BVHGPU_OK) {
         BVH_CUDA_TRY(cudaMemcpyAsync(out_shape, d_s, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
         BVH_CUDA_TRY(cudaMemcpyAsync(out_dist, d_d, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -899,6 +899,9 @@ BVH_EXPORT int bvhgpu_host_free(bvhgpu_ctx* ctx, void* p) {
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_nearest_##SUF(TREE* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist) { \
         return nearest_host_impl<T>(tree, mode, points, n, out_shape, out_dist);                                         \
+    }                                                                                                                     \
+    BVH_EXPORT int bvhgpu_nearest_triangles_##SUF(TREE* tree, int mode, const T* points, size_t n, uint32_t* out_shape, T* out_dist) { \
+        return nearest_host_impl<T>(tree, mode, points, n, out_shape, out_dist, 1);                                      \
     }                                                                                                                     \
     BVH_EXPORT int bvhgpu_nearest_candidates_##SUF(TREE* tree, const T* points, size_t n, uint32_t* offsets, uint32_t* cand, \
                                                    size_t cap, size_t* total) {                                           \

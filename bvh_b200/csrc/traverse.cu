@@ -1313,20 +1313,73 @@ template <class T> __device__ __forceinline__ T aabb_min_d2(const T p[3], const 
 __device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }
 __device__ __forceinline__ double sqrt_rn(double x) { return __dsqrt_rn(x); }
 
+// Triangle::distance_squared of the reference's test shape (src/testbase.rs:353-443: closest_point_segment, closest_point_triangle),
+// operation for operation -- the PointDistance every benchmark scene of the reference uses.  tri: {a.xyz,-, b.xyz,-, c.xyz,-}.
+template <class T> __device__ __forceinline__ T dot3_rn(const T a[3], const T b[3]) { return add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])); }
+template <class T> __device__ __forceinline__ void closest_on_segment(const T p[3], const T a[3], const T b[3], T out[3]) {
+    T ab[3], ap[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ab[k] = sub_rn(b[k], a[k]); ap[k] = sub_rn(p[k], a[k]); }
+    T s = div_rn(dot3_rn(ab, ap), dot3_rn(ab, ab));
+    s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = add_rn(a[k], mul_rn(s, ab[k]));
+}
+template <class T> __device__ __forceinline__ T triangle_distance_squared(const T p[3], const T* __restrict__ tri) {
+    T a[3], b[3], c[3], q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { a[k] = __ldg(tri + k); b[k] = __ldg(tri + 4 + k); c[k] = __ldg(tri + 8 + k); }
+    const bool e_ab = a[0] == b[0] && a[1] == b[1] && a[2] == b[2], e_bc = b[0] == c[0] && b[1] == c[1] && b[2] == c[2], e_ac = a[0] == c[0] && a[1] == c[1] && a[2] == c[2];
+    bool done = false;
+    if (e_ab && e_bc && e_ac) { for (int k = 0; k < 3; ++k) q[k] = a[k]; done = true; }
+    else if (e_ab) { closest_on_segment(p, a, c, q); done = true; }
+    else if (e_bc) { closest_on_segment(p, a, b, q); done = true; }
+    else if (e_ac) { closest_on_segment(p, a, b, q); done = true; }
+    if (!done) {
+        T ab[3], ac[3], ap[3], bp[3], cp[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { ab[k] = sub_rn(b[k], a[k]); ac[k] = sub_rn(c[k], a[k]); ap[k] = sub_rn(p[k], a[k]); bp[k] = sub_rn(p[k], b[k]); cp[k] = sub_rn(p[k], c[k]); }
+        const T d1 = dot3_rn(ab, ap), d2 = dot3_rn(ac, ap), d3 = dot3_rn(ab, bp), d4 = dot3_rn(ac, bp), d5 = dot3_rn(ab, cp), d6 = dot3_rn(ac, cp);
+        const T vc = sub_rn(mul_rn(d1, d4), mul_rn(d3, d2)), vb = sub_rn(mul_rn(d5, d2), mul_rn(d1, d6)), va = sub_rn(mul_rn(d3, d6), mul_rn(d5, d4));
+        if (d1 <= T(0) && d2 <= T(0)) { for (int k = 0; k < 3; ++k) q[k] = a[k]; }
+        else if (d3 >= T(0) && d4 <= d3) { for (int k = 0; k < 3; ++k) q[k] = b[k]; }
+        else if (d6 >= T(0) && d5 <= d6) { for (int k = 0; k < 3; ++k) q[k] = c[k]; }
+        else if (vc <= T(0) && d1 >= T(0) && d3 <= T(0)) { const T v = div_rn(d1, sub_rn(d1, d3)); for (int k = 0; k < 3; ++k) q[k] = add_rn(a[k], mul_rn(v, ab[k])); }
+        else if (vb <= T(0) && d2 >= T(0) && d6 <= T(0)) { const T v = div_rn(d2, sub_rn(d2, d6)); for (int k = 0; k < 3; ++k) q[k] = add_rn(a[k], mul_rn(v, ac[k])); }
+        else if (va <= T(0) && sub_rn(d4, d3) >= T(0) && sub_rn(d5, d6) >= T(0)) {
+            const T v = div_rn(sub_rn(d4, d3), add_rn(sub_rn(d4, d3), sub_rn(d5, d6)));
+            for (int k = 0; k < 3; ++k) q[k] = add_rn(b[k], mul_rn(v, sub_rn(c[k], b[k])));
+        } else {
+            const T denom = div_rn(T(1), add_rn(add_rn(va, vb), vc));
+            const T v = mul_rn(vb, denom), w = mul_rn(vc, denom);
+            for (int k = 0; k < 3; ++k) q[k] = add_rn(add_rn(a[k], mul_rn(v, ab[k])), mul_rn(w, ac[k]));
+        }
+    }
+    T d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d[k] = sub_rn(p[k], q[k]);
+    return dot3_rn(d, d);
+}
+
 // One walk for both kernels.  EXACT: reference semantics (order by min distance, prune with `<`, leaf value = AABB distance).
 // !EXACT: leaf value = farthest-corner bound, children ordered and pruned by the monotone lower bound, ties kept (`<=`).
+// tris != nullptr (EXACT only): the leaf value is the triangle's own distance (Triangle::distance_squared).
 template <class T, bool EXACT>
 __device__ __forceinline__ void nearest_walk(const typename Traits<T>::Node* __restrict__ nodes, const typename Traits<T>::DAabb* __restrict__ aabb,
-                                             const T p[3], uint32_t& best, T& best_d) {
+                                             const T p[3], uint32_t& best, T& best_d, const T* __restrict__ tris = nullptr) {
     best = BVH_INVALID;
     best_d = Traits<T>::inf();
     uint32_t node = 0, from = BVH_INVALID;                 // from: the child we are returning from (BVH_INVALID = arriving from the parent)
     for (;;) {
         const uint4 meta = __ldg(reinterpret_cast<const uint4*>(nodes + node));      // parent, child_l, child_r, shape
         if (meta.y == BVH_INVALID) {                       // leaf
-            T mn[3], mx[3];
-            load_aabb(aabb + meta.w, mn, mx);
-            const T d = EXACT ? aabb_min_d2(p, mn, mx) : box_upper_d2(p, mn, mx);
+            T d;
+            if (EXACT && tris) d = triangle_distance_squared(p, tris + 12 * (size_t)meta.w);
+            else {
+                T mn[3], mx[3];
+                load_aabb(aabb + meta.w, mn, mx);
+                d = EXACT ? aabb_min_d2(p, mn, mx) : box_upper_d2(p, mn, mx);
+            }
             if (best == BVH_INVALID || d < best_d) { best = meta.w; best_d = d; }
             if (node == 0) return;
             from = node; node = meta.x;
@@ -1358,7 +1411,8 @@ __device__ __forceinline__ void nearest_walk(const typename Traits<T>::Node* __r
 template <class T, bool FLAT>
 __global__ void __launch_bounds__(128) nearest_kernel(const typename Traits<T>::Node* __restrict__ nodes, const typename Traits<T>::Flat* __restrict__ flat,
                                                       uint32_t n_flat, const typename Traits<T>::DAabb* __restrict__ aabb,
-                                                      const T* __restrict__ points, uint32_t nq, uint32_t* __restrict__ out_shape, T* __restrict__ out_dist) {
+                                                      const T* __restrict__ points, uint32_t nq, uint32_t* __restrict__ out_shape, T* __restrict__ out_dist,
+                                                      const T* __restrict__ tris) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     T p[3];
@@ -1366,7 +1420,7 @@ __global__ void __launch_bounds__(128) nearest_kernel(const typename Traits<T>::
     uint32_t best = BVH_INVALID;
     T best_d = T(0);
     if (!FLAT) {
-        nearest_walk<T, true>(nodes, aabb, p, best, best_d);
+        nearest_walk<T, true>(nodes, aabb, p, best, best_d, tris);
     } else {                                                // flat_bvh.rs:524-558
         uint32_t index = 0;
         while (index < n_flat) {
@@ -1375,8 +1429,9 @@ __global__ void __launch_bounds__(128) nearest_kernel(const typename Traits<T>::
             if (entry == BVH_INVALID) {
                 T mn[3], mx[3];
                 const uint32_t shape = f.shape_index;
-                load_aabb(aabb + shape, mn, mx);
-                const T d = aabb_min_d2(p, mn, mx);
+                T d;
+                if (tris) d = triangle_distance_squared(p, tris + 12 * (size_t)shape);
+                else { load_aabb(aabb + shape, mn, mx); d = aabb_min_d2(p, mn, mx); }
                 if (best == BVH_INVALID || d < best_d) { best = shape; best_d = d; }
                 index = exit_i;
             } else {
@@ -1406,8 +1461,10 @@ __global__ void __launch_bounds__(128) nearest_bound_kernel(const typename Trait
 }
 
 template <class T>
-int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist) {
+int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32_t* d_shape, T* d_dist, int use_triangles) {
     bvhgpu_ctx* ctx = tree->ctx;
+    if (use_triangles && !tree->d_tris && tree->n) { set_error("nearest: triangle distances need bvhgpu_tree_set_triangles_* first"); return BVHGPU_ERR_INVALID; }
+    const T* tris = use_triangles ? reinterpret_cast<const T*>(tree->d_tris) : nullptr;
     cudaStream_t st = ctx->stream;
     if (nq > 0x7FFFFFFFull) { set_error("nearest: too many points"); return BVHGPU_ERR_INVALID; }
     if (mode != BVHGPU_TRAVERSE_BVH && mode != BVHGPU_TRAVERSE_FLAT) { set_error("nearest: bad mode %d", mode); return BVHGPU_ERR_INVALID; }
@@ -1421,9 +1478,9 @@ int nearest_device(Tree<T>* tree, int mode, const T* d_points, size_t nq, uint32
     const unsigned grid = (unsigned)((nq + 127) / 128);
     if (mode == BVHGPU_TRAVERSE_FLAT) {
         if (!tree->have_flat) BVH_TRY(build_flat(tree));
-        nearest_kernel<T, true><<<grid, 128, 0, st>>>(tree->d_nodes, tree->d_flat, (uint32_t)tree->n_flat, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist);
+        nearest_kernel<T, true><<<grid, 128, 0, st>>>(tree->d_nodes, tree->d_flat, (uint32_t)tree->n_flat, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist, tris);
     } else {
-        nearest_kernel<T, false><<<grid, 128, 0, st>>>(tree->d_nodes, nullptr, 0u, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist);
+        nearest_kernel<T, false><<<grid, 128, 0, st>>>(tree->d_nodes, nullptr, 0u, tree->d_aabb, d_points, (uint32_t)nq, d_shape, d_dist, tris);
     }
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
@@ -1443,8 +1500,8 @@ int nearest_candidates_device(Tree<T>* tree, const T* d_points, size_t nq, uint3
     ctx->launches++;
     return query_device<T>(tree, BVHGPU_TRAVERSE_FLAT, QUERY_WITHIN, rec, nq, d_offsets, d_cand, cap, total);
 }
-template int nearest_device<float>(Tree<float>*, int, const float*, size_t, uint32_t*, float*);
-template int nearest_device<double>(Tree<double>*, int, const double*, size_t, uint32_t*, double*);
+template int nearest_device<float>(Tree<float>*, int, const float*, size_t, uint32_t*, float*, int);
+template int nearest_device<double>(Tree<double>*, int, const double*, size_t, uint32_t*, double*, int);
 template int nearest_candidates_device<float>(Tree<float>*, const float*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 template int nearest_candidates_device<double>(Tree<double>*, const double*, size_t, uint32_t*, uint32_t*, size_t, size_t*);
 

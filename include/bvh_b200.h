@@ -327,6 +327,11 @@ int bvhgpu_closest_hit_dev_f64x3(bvhgpu_tree3d* tree, const void* dev_rays, int 
  *                               keeps the minimum. */
 int bvhgpu_nearest_f32x3(bvhgpu_tree3f* tree, int mode, const float* points, size_t n, uint32_t* out_shape, float* out_dist);
 int bvhgpu_nearest_f64x3(bvhgpu_tree3d* tree, int mode, const double* points, size_t n, uint32_t* out_shape, double* out_dist);
+/* The same walk with the TRIANGLE's own distance at the leaves -- Triangle::distance_squared of the reference's test shape
+ * (closest_point_triangle, src/testbase.rs:353-443), operation for operation; triangles from bvhgpu_tree_set_triangles_*.  This is
+ * the PointDistance of every benchmark scene of the reference, evaluated on the device: same shape, bit-identical distance. */
+int bvhgpu_nearest_triangles_f32x3(bvhgpu_tree3f* tree, int mode, const float* points, size_t n, uint32_t* out_shape, float* out_dist);
+int bvhgpu_nearest_triangles_f64x3(bvhgpu_tree3d* tree, int mode, const double* points, size_t n, uint32_t* out_shape, double* out_dist);
 int bvhgpu_nearest_candidates_f32x3(bvhgpu_tree3f* tree, const float* points, size_t n, uint32_t* offsets, uint32_t* cand,
                                     size_t cap, size_t* total);
 int bvhgpu_nearest_candidates_f64x3(bvhgpu_tree3d* tree, const double* points, size_t n, uint32_t* offsets, uint32_t* cand,

@@ -471,3 +471,31 @@ def test_two_dimensional_bvh_matches_the_2d_restatement(api, kind, n, prec):
         assert hits[off[i]:off[i + 1]].tolist() == want, i
         assert hits2[off2[i]:off2[i + 1]].tolist() == want, i        # tight trees: the FLAT leaf re-test agrees
     bvh.free()
+
+
+# ---- nearest_to with the triangle's own PointDistance on the device ---------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_nearest_to_with_native_triangle_distance(api, prec):
+    """bvhgpu_nearest_triangles_*: the reference's nearest_to walk (bvh_node.rs:327-372 / flat_bvh.rs:513-562) with
+    Triangle::distance_squared (closest_point_triangle, testbase.rs:353-443) at the leaves, evaluated on the device: same triangle (ties
+    included) and bit-identical distance as the oracle -- and as brute force over all triangles."""
+    from bvh_b200 import capi
+
+    shapes, tris = O.create_n_cubes(400, prec=prec, want_tris=True)
+    want = O.build(shapes, prec)
+    bvh = api.Bvh.build(shapes, prec=prec)
+    bvh.set_triangles(tris)
+    rng = np.random.default_rng(77)
+    centres = (shapes["min"][::12] + shapes["max"][::12]) * 0.5
+    pts = np.concatenate([centres[rng.integers(0, len(centres), 1500)] + rng.normal(0, 3.0, (1500, 3)), rng.uniform(-1.2e5, 1.2e5, (1500, 3))])
+    ws, wd = O.nearest_to(want.nodes, shapes, pts, prec, flat=False, kind=O.DIST_TRIANGLE, tris=tris)
+    gs, gd = bvh.nearest_triangles_batch(pts, mode=capi.TRAVERSE_BVH)
+    assert np.array_equal(gs, ws) and np.array_equal(gd, wd)
+    flat = O.flatten(want.nodes, prec)
+    ws2, wd2 = O.nearest_to(flat, shapes, pts, prec, flat=True, kind=O.DIST_TRIANGLE, tris=tris)
+    gs2, gd2 = bvh.nearest_triangles_batch(pts, mode=capi.TRAVERSE_FLAT)
+    assert np.array_equal(gs2, ws2) and np.array_equal(gd2, wd2)
+    for i in range(0, len(pts), 211):                                    # brute force (nearest_to_some_bh, testbase.rs:270-312)
+        d2 = O.shape_distances_squared(shapes, pts[i], prec, kind=O.DIST_TRIANGLE, tris=tris)
+        assert d2[gs[i]] == d2.min()
+    bvh.free()
