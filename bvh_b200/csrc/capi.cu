@@ -643,8 +643,9 @@ BVH_EXPORT int bvhgpu_create(int device, bvhgpu_ctx** out) {
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
     BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_total, cudaEventDisableTiming));
     for (unsigned i = 0; i < BVH_MAX_CHUNKS; ++i) BVH_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-    BVH_CUDA_TRY(cudaMalloc((void**)&ctx->d_async_err, 64));
-    BVH_CUDA_TRY(cudaMemset(ctx->d_async_err, 0, 64));
+    BVH_CUDA_TRY(cudaMalloc((void**)&ctx->d_async_err, 256));
+    BVH_CUDA_TRY(cudaMemset(ctx->d_async_err, 0, 256));
+    ctx->d_ready = ctx->d_async_err + 32;                         // its own 128-byte line of the same small allocation
     {   // NUMA node of the device (bvhgpu_host_alloc): /sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node
         char bus[32] = {0}, path[128];
         if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
@@ -721,6 +722,7 @@ BVH_EXPORT int bvhgpu_get_metric(bvhgpu_ctx* ctx, const char* name, double* out)
     if (!ctx || !name || !out) { set_error("get_metric: null argument"); return BVHGPU_ERR_INVALID; }
     cudaEvent_t* ev = nullptr;
     if (!strncmp(name, "e2e_host_us_", 12) && name[12] >= '0' && name[12] <= '7' && !name[13]) { *out = ctx->host_us[name[12] - '0']; return BVHGPU_OK; }
+    if (!strcmp(name, "stream_write_value")) { *out = (double)ctx->wv_ok; return BVHGPU_OK; }
     if (!strcmp(name, "host_streamed")) { *out = (double)ctx->last_streamed; return BVHGPU_OK; }
     if (!strcmp(name, "numa_node")) { *out = (double)ctx->numa_node; return BVHGPU_OK; }
     if (!strcmp(name, "walk_ms") && ctx->have_walk) ev = ctx->ev_walk;

@@ -67,6 +67,8 @@ struct bvhgpu_ctx {
     int last_streamed = -1;        // did the last host-pointer traversal stream (1) or copy-then-walk (0)
     int64_t traverse_stream = -1;  // option "traverse_stream": -1 auto (probe), 0 never, 1 force
     int64_t traverse_top = -1;     // option "traverse_top": shared-memory top-of-tree walk: -1 auto, 0 off, 1 on
+    uint32_t* d_ready = nullptr;       // cudaMalloc'ed word the streamed host path bumps with cuStreamWriteValue32 (refused on pool memory)
+    int wv_ok = -1;                    // did the last streamed call use stream write-value flags (1) or 4-byte copies (0)
     uint32_t* d_async_err = nullptr;   // sticky device-side error word of asynchronous calls (sharded exchange): surfaced by bvhgpu_synchronize
     int numa_node = -1;            // NUMA node of the device (sysfs), -1 unknown
 };

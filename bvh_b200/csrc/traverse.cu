@@ -794,7 +794,7 @@ static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, ui
     }
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->walk_grid, ((uint64_t)R + 255) / 256);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
-    const uint32_t* ready = reinterpret_cast<const uint32_t*>(tail + S_READY);
+    const uint32_t* ready = ctx->d_ready;                    // only read by the streamed form
     uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);
     if (stream_mode) {
         if (flat) walk_persistent_kernel<T, true, true><<<grid, 256, 0, st>>>(tree->d_tnodes, tree->n_trec, walk_aabbs(tree), rays, R, ticket, ready, counts, slots, K, tail + S_VISITS, nullptr, 0u, err, STREAM_TIMEOUT_NS);
@@ -1033,21 +1033,25 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
     const bool streaming = nchunks > 1 && stream_capable(ctx) == 1;
     ctx->last_streamed = streaming ? 1 : 0;
     stamp(0);                                                     // scratch allocated
+    BVH_CUDA_TRY(cudaMemsetAsync(ctx->d_ready, 0, sizeof(uint32_t), st));
     BVH_CUDA_TRY(cudaEventRecord(ctx->ev_order, st));             // the scratch (and its zeroed tail) exists from here on
     BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_order, 0));
     if (ctx->profile) cudaEventRecord(ctx->ev_e2e[0], st);
     if (streaming) {
         BVH_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
         uint32_t* h_ready = ctx->h_pinned + 64;                  // pinned: one value per chunk, alive until the final sync
-        uint32_t* d_ready = reinterpret_cast<uint32_t*>(tail + S_READY);
+        uint32_t* d_ready = ctx->d_ready;                        // plain cudaMalloc memory: the stream memory operation refuses pool memory
+        ctx->wv_ok = 1;
         for (uint32_t c = 0; c < nchunks; ++c) {
             const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
             cudaError_t e = cudaMemcpyAsync(staged + ray_bytes * lo, (const unsigned char*)h_rays + ray_bytes * lo, ray_bytes * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream);
             h_ready[c] = hi;
             if (e == cudaSuccess) {
                 WriteValue32Fn wv = stream_write_value32();
-                if (!wv || wv(ctx->copy_stream, (unsigned long long)(uintptr_t)d_ready, hi, 0u) != 0)
+                if (!wv || wv(ctx->copy_stream, (unsigned long long)(uintptr_t)d_ready, hi, 0u) != 0) {
+                    ctx->wv_ok = 0;
                     e = cudaMemcpyAsync(d_ready, h_ready + c, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+                }
             }
             if (e != cudaSuccess) {                               // nothing waits on `ready` yet (the kernel is launched below): just report
                 set_error("traverse: H2D copy of chunk %u failed: %s", c, cudaGetErrorString(e));

@@ -33,7 +33,7 @@ for name, fn, stride in (("od", L.bvhgpu_traverse_od_f32x3, 6), ("full", L.bvhgp
             ph.append([ctx.get_metric(f"e2e_host_us_{k}") for k in range(6)] + [ctx.get_metric(m) * 1e3 for m in ("e2e_h2d_ms", "e2e_walk_ms", "e2e_emit_ms", "e2e_d2h_ms")])
         ctx.set_option("profile", 0)
         med = np.median(np.array(ph), axis=0).round(1).tolist()
-        out[f"{name}_stream{stream_opt}"] = {"ms_p10_p50_p90_max": [round(ts[20], 3), round(ts[100], 3), round(ts[180], 3), round(ts[-1], 3)], "streamed": ctx.get_metric("host_streamed"),
+        out[f"{name}_stream{stream_opt}"] = {"ms_p10_p50_p90_max": [round(ts[20], 3), round(ts[100], 3), round(ts[180], 3), round(ts[-1], 3)], "streamed": ctx.get_metric("host_streamed"), "stream_write_value": ctx.get_metric("stream_write_value"),
                                              "host_us[alloc, copies enq, walk launched, all enq, st drained, done]": med[:6], "device_us_since_start[h2d done, walk done, emit done, d2h done]": med[6:]}
     ctx.set_option("traverse_stream", -1)
 print(json.dumps(out, indent=1))
