@@ -93,9 +93,102 @@ template <class T> int build_traversal_records(Tree<T>* tree) {
     const uint32_t n_trec = tree->n == 1 ? 1u : tree->n_nodes - 1;
     if (!tree->d_tnodes) BVH_TRY(dalloc_t(ctx, &tree->d_tnodes, n_trec));
     tree->n_trec = n_trec;
+    tree->top_valid = false;                                    // the shared-memory top records are rebuilt from these lazily
     trec_kernel<T><<<(tree->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(tree->d_nodes, tree->n_nodes, tree->dims == 2 && tree->d_aabb_trav ? tree->d_aabb_trav : tree->d_aabb, tree->d_tnodes, tree->d_status, tree->dims);
     ctx->launches++;
     BVH_CUDA_TRY(cudaGetLastError());
+    return BVHGPU_OK;
+}
+
+// ---- top-of-tree records for the shared-memory walk (walk_top_kernel, f32) ---------------------------------------------------------
+// P = {root} + all inner nodes with >= C shapes below them; T = the children of P's nodes, in preorder: the records a ray meets before it
+// dives below the C-level.  An entry is the node's traversal record with other links:
+//   node in P (top-internal) : w3 = index in T of the first entry behind its subtree, w7 = 0xFFFFFFFF       hit -> next entry
+//   fringe leaf              : w7 = shape                                                               hit -> report, next entry
+//   fringe inner node        : w3 = end of its subtree in the GLOBAL records, w7 = 0x80000000 | first global record of the subtree
+//                                                                                   hit -> walk the global records [begin, end), then next
+// C is chosen on the device (no host round trip: the records are rebuilt inside the asynchronous traversal call after every
+// refit / update): a histogram of count(parent) over 8 bins per octave, then the smallest C whose entries fit the budget.
+// d_top = header {n_top, C, 0, 0, ...} (32 B) followed by lo[n_top], hi[n_top].
+constexpr uint32_t TOP_BINS = 256;
+__device__ __forceinline__ uint32_t top_bin(uint32_t c) { const uint32_t k = 31 - __clz(c); return 8 * k + (((c << 3) >> k) & 7u); }
+__global__ void __launch_bounds__(256) top_hist_kernel(const bvh_node3f* __restrict__ nodes, uint32_t n_nodes, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[TOP_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 1 && i < n_nodes) atomicAdd(sh + top_bin(nodes[nodes[i].parent].shape), 1u);      // an inner node stores the shapes below it
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+__global__ void top_choose_kernel(const uint32_t* __restrict__ hist, uint32_t budget, uint32_t* __restrict__ hdr) {
+    if (threadIdx.x) return;
+    uint32_t total = 0;
+    int b = TOP_BINS - 1;
+    for (; b >= 0; --b) { if (total + hist[b] > budget) break; total += hist[b]; }
+    // the smallest count that falls into an included bin (bins b+1 ..): ceil((8 + sub) * 2^k / 8)
+    uint32_t C = 2;
+    if (b >= 0) { const uint32_t nb = (uint32_t)b + 1, k = nb >> 3, sub = nb & 7u; C = (uint32_t)((((unsigned long long)(8 + sub) << k) + 7ull) >> 3); }
+    hdr[0] = total; hdr[1] = C; hdr[2] = 0; hdr[3] = 0;
+}
+__global__ void __launch_bounds__(256) top_flag_kernel(const bvh_node3f* __restrict__ nodes, uint32_t n_nodes, const uint32_t* __restrict__ hdr, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_nodes) return;
+    const uint32_t C = hdr[1];
+    uint32_t f = 0;
+    if (i >= 1 && i < n_nodes) f = nodes[nodes[i].parent].shape >= C ? 1u : 0u;
+    flags[i] = f;
+}
+__global__ void __launch_bounds__(256) top_emit_kernel(const bvh_node3f* __restrict__ nodes, uint32_t n_nodes, const TNodeF* __restrict__ trec,
+                                                       const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pre, float4* __restrict__ top) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= n_nodes || !flags[i]) return;
+    const uint32_t n_top = reinterpret_cast<const uint32_t*>(top)[0], C = reinterpret_cast<const uint32_t*>(top)[1];
+    float4* lo = top + 2;
+    float4* hi = lo + n_top;
+    const uint32_t k = pre[i];
+    const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);
+    const bool leaf = meta.y == BVH_INVALID;
+    const uint32_t cnt = leaf ? 1u : meta.w;
+    const TNodeF r = trec[i - 1];
+    uint32_t w3, w7;
+    if (!leaf && cnt >= C) { const uint32_t end = i + 2 * cnt - 1; w3 = pre[end < n_nodes ? end : n_nodes]; w7 = 0xFFFFFFFFu; }
+    else if (leaf)         { w3 = k + 1; w7 = meta.w; }
+    else                   { w3 = r.skip; w7 = 0x80000000u | i; }        // global record of node i's left child = i (miss: next entry)
+    lo[k] = make_float4(r.min[0], r.min[1], r.min[2], __uint_as_float(w3));
+    hi[k] = make_float4(r.max[0], r.max[1], r.max[2], __uint_as_float(w7));
+}
+}  // namespace bvhb200
+#include <cub/device/device_scan.cuh>
+namespace bvhb200 {
+// (Re)builds tree->d_top for at most `budget` entries; asynchronous on the context's stream.  n >= 2 only (n_top >= 2 then: the
+// root's two children always fit).
+int build_top_records(Tree<float>* tree, uint32_t budget) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t nn = tree->n_nodes;
+    Scratch scratch(ctx);
+    uint32_t *hist = nullptr, *flags = nullptr, *pre = nullptr;
+    BVH_TRY(scratch.get(&hist, TOP_BINS));
+    BVH_TRY(scratch.get(&flags, (size_t)nn + 1));
+    BVH_TRY(scratch.get(&pre, (size_t)nn + 1));
+    if (tree->d_top && tree->top_cap < budget) { dfree(ctx, tree->d_top); tree->d_top = nullptr; }
+    if (!tree->d_top) { BVH_TRY(dalloc(ctx, &tree->d_top, 32 * ((size_t)budget + 1))); tree->top_cap = budget; }
+    BVH_CUDA_TRY(cudaMemsetAsync(hist, 0, TOP_BINS * sizeof(uint32_t), st));
+    const unsigned g = (nn + 256) / 256;
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(tree->d_top);
+    top_hist_kernel<<<g, 256, 0, st>>>(tree->d_nodes, nn, hist);
+    top_choose_kernel<<<1, 32, 0, st>>>(hist, budget, hdr);
+    top_flag_kernel<<<g, 256, 0, st>>>(tree->d_nodes, nn, hdr, flags);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, pre, (int)(nn + 1), st);
+    unsigned char* tmp = nullptr;
+    BVH_TRY(scratch.get(&tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flags, pre, (int)(nn + 1), st);
+    top_emit_kernel<<<g, 256, 0, st>>>(tree->d_nodes, nn, tree->d_tnodes, flags, pre, reinterpret_cast<float4*>(tree->d_top));
+    ctx->launches += 5;
+    BVH_CUDA_TRY(cudaGetLastError());
+    tree->top_valid = true; tree->top_budget = budget;
     return BVHGPU_OK;
 }
 

@@ -89,6 +89,9 @@ template <class T> struct Tree {
     uint32_t* d_node_start = nullptr;         // [2n-1]   first position of the node's shape range (== #leaves before it)
     typename Tr::TNode* d_tnodes = nullptr;   // [n_trec] traversal records
     uint32_t n_trec = 0;
+    void* d_top = nullptr;                    // f32: top-of-tree records for walk_top_kernel (32-B header {n_top, C}, lo[n_top], hi[n_top] float4), built lazily
+    uint32_t top_cap = 0, top_budget = 0;
+    bool top_valid = false;
     uint32_t* d_arrive = nullptr;             // [2n-1] arrival counters of the incremental update (all zero between calls)
     uint8_t* d_bad = nullptr;                 // [2n-1] growth flags of the incremental update (all zero between calls)
     void* d_sa_base = nullptr;                // [2n-1] surface area of every inner node when it was last (re)built: baseline of bvhgpu_optimize / update
@@ -161,6 +164,7 @@ template <class T> int build_lbvh(bvhgpu_ctx* ctx, const typename Traits<T>::Aab
 // ---- flatten.cu ----
 template <class T> int build_traversal_records(Tree<T>* tree);   // d_tnodes
 template <class T> int build_flat(Tree<T>* tree);                // d_flat (reference FlatNode layout)
+int build_top_records(Tree<float>* tree, uint32_t budget);        // d_top
 template <class T> int sah_cost(Tree<T>* tree, double* out2);
 template <class T> int refit(Tree<T>* tree);                     // recompute child AABBs bottom-up from d_aabb
 template <class T> int optimize(Tree<T>* tree, double max_growth);   // refit + exact rebuild of the degraded subtrees

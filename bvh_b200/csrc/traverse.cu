@@ -308,6 +308,88 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
     if (lane == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
 }
 
+// Shared-memory top-of-tree variant of the persistent walk (f32, opt-in: option traverse_top).  Every CTA (one per SM, 1024 threads)
+// keeps the top records (flatten.cu: build_top_records) in shared memory; a lane walks them with two LDS.128 per visit and drops
+// to the global records (LDG.256, as above) only inside a fringe subtree.  Visit order and tests are exactly the preorder walk's,
+// so counts and hit lists are bit-identical.  Lane state: j = next top entry (also the resume point while g walks [g, gend)).
+template <bool FLAT>
+__global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restrict__ trec, const DAabbF* __restrict__ aabb,
+                                                           uint32_t n_rec, const float4* __restrict__ top,
+                                                           RaySrc<float> rays, uint32_t nrays, uint32_t* __restrict__ ticket,
+                                                           uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
+                                                           unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
+    extern __shared__ float4 s_top[];
+    if (gate && *gate != run_if) return;
+    const uint32_t n_top = reinterpret_cast<const uint32_t*>(top)[0];      // header {n_top, C}, then lo[n_top], hi[n_top]
+    for (uint32_t k = threadIdx.x; k < 2 * n_top; k += blockDim.x) s_top[k] = top[2 + k];
+    __syncthreads();
+    uint32_t s_lo;                                                   // opaque: keeps ptxas from re-deriving the window address every visit
+    asm volatile("mov.u32 %0, %1;" : "=r"(s_lo) : "r"((uint32_t)__cvta_generic_to_shared(s_top)));
+    const uint32_t s_hi = s_lo + 16u * n_top;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
+    constexpr int REFILL = 8;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = lane_id(), lt = lanemask_lt();
+    // Lane state: r ray, j next top entry (the resume point while below the top), [g, gend) global records left to walk in the
+    // current fringe subtree -- empty (gend = 0) while the lane is in the top.
+    uint32_t r = NONE, j = 0, g = 0, gend = 0, cnt = 0, visits = 0;
+    float o[3] = {0.f, 0.f, 0.f}, inv[3] = {0.f, 0.f, 0.f};
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t need = __ballot_sync(FULL, r == NONE);
+        if (need && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(ticket, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= nrays) exhausted = true;
+            const uint32_t mine = base + __popc(need & lt);
+            // (no top records -- a degenerate tree whose first histogram bin already exceeds the budget: everything is "below")
+            if (r == NONE && mine < nrays) { r = mine; j = 0; cnt = 0; g = 0; gend = n_top ? 0u : n_rec; load_ray<float, false>(rays, mine, o, inv); }
+        }
+        if (__ballot_sync(FULL, r != NONE) == 0) break;
+        const int leave = exhausted ? 32 : REFILL;                   // idle lanes at which the warp goes back for tickets
+        for (;;) {
+            if (r != NONE) {
+                float mn[3], mx[3];
+                uint32_t w3, w7;
+                const bool below = g < gend;
+                if (!below) {
+                    float4 a, b;                                      // explicit shared-window addresses: two LDS.128, no per-visit cvta
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(s_lo + 16u * j));
+                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(s_hi + 16u * j));
+                    mn[0] = a.x; mn[1] = a.y; mn[2] = a.z; w3 = __float_as_uint(a.w);
+                    mx[0] = b.x; mx[1] = b.y; mx[2] = b.z; w7 = __float_as_uint(b.w);
+                } else {
+                    fetch(trec + g, mn, mx, w3, w7);
+                }
+                ++visits;
+                // One select chain for both index spaces (no divergence between lanes in the top and lanes below it):
+                //   top entry: w7 = ~0 top-internal | 0x80000000+first global record (fringe inner, w3 = end of that range) | shape
+                const bool hit = slab_hit(o, inv, mn, mx);
+                const bool fringe = !below && (w7 + 0x80000000u) < 0x7FFFFFFFu;
+                const uint32_t cur = below ? g : j;
+                const uint32_t nxt = (hit || fringe) ? cur + 1 : w3;
+                if (hit && (int32_t)w7 >= 0) {                       // a leaf
+                    bool report = true;
+                    if (FLAT) {
+                        float smn[3], smx[3];
+                        load_aabb(aabb + w7, smn, smx);
+                        report = slab_hit(o, inv, smn, smx);
+                    }
+                    if (report) { if (cnt < K) slots[(size_t)cnt * nrays + r] = w7; ++cnt; }
+                }
+                j = below ? j : nxt;
+                gend = below ? gend : ((hit && fringe) ? w3 : 0u);
+                g = below ? nxt : (w7 & 0x7FFFFFFFu);
+                if (g >= gend && j >= n_top) { counts[r] = cnt; r = NONE; }
+            }
+            if (__popc(__ballot_sync(FULL, r == NONE)) >= leave) break;
+        }
+    }
+    visits = __reduce_add_sync(FULL, visits);
+    if (lane == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
+}
+
 // Exclusive scan of counts, phase A: per-block local exclusive offsets + block totals (+ the largest count, if asked for).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(const uint32_t* __restrict__ counts, uint32_t n,
                                                                   uint32_t* __restrict__ local, unsigned long long* __restrict__ blocksum,
@@ -765,6 +847,32 @@ __global__ void __launch_bounds__(256) emit_goffsets_kernel(const typename Trait
 constexpr uint32_t SUMS_TAIL = 20;
 constexpr uint32_t S_TOTAL = 0, S_VISITS = 1, S_XINFO = 2, S_ERR = 12, S_TICKET = 13, S_READY = 14, S_GATE = 15, S_MAXC = 16, S_BLKDONE = 17;
 constexpr unsigned long long STREAM_TIMEOUT_NS = 4ull * 1000ull * 1000ull * 1000ull;
+// The shared-memory top-tree walk: f32 trees only; false = not applicable (the caller launches the plain persistent kernel).
+constexpr uint32_t TOP_BUDGET = 7000;                               // entries: 224 000 B of the 227 KB a CTA may own
+template <class T> static bool launch_top(Tree<T>*, bool, RaySrc<T>, uint32_t, uint32_t*, uint32_t*, uint32_t, unsigned long long*, uint32_t*) { return false; }
+template <> bool launch_top<float>(Tree<float>* tree, bool flat, RaySrc<float> rays, uint32_t R, uint32_t* counts, uint32_t* slots, uint32_t K,
+                                   unsigned long long* tail, uint32_t* gate) {
+    bvhgpu_ctx* ctx = tree->ctx;
+    if (tree->n < 2) return false;
+    const uint32_t budget = ctx->traverse_top > 1 ? (uint32_t)std::min<int64_t>(std::max<int64_t>(ctx->traverse_top, 8), TOP_BUDGET) : TOP_BUDGET;
+    if ((!tree->top_valid || tree->top_budget != budget) && build_top_records(tree, budget) != BVHGPU_OK) return false;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int bytes = (int)(TOP_BUDGET * 32);
+        if (cudaFuncSetAttribute(walk_top_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(walk_top_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+        attr_set = true;
+    }
+    const size_t smem = (size_t)budget * 32;                            // n_top <= budget lives on the device: reserve for the budget
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count, ((uint64_t)R + 1023) / 1024);
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
+    const float4* top = reinterpret_cast<const float4*>(tree->d_top);
+    if (flat) walk_top_kernel<true><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, counts, slots, K, tail + S_VISITS, gate, 0u);
+    else      walk_top_kernel<false><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, counts, slots, K, tail + S_VISITS, gate, 0u);
+    ctx->launches++;
+    return true;
+}
+
 template <class T>
 static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, uint32_t first, uint32_t count,
                         uint32_t* counts, uint32_t* slots, uint32_t K, unsigned long long* sums, uint32_t nblk, bool stream_mode) {
@@ -787,6 +895,7 @@ static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, ui
         if (pmode == 0) return BVHGPU_OK;
     }
     if (first != 0 || count != R) { set_error("internal: persistent walk covers whole batches only"); return BVHGPU_ERR_INTERNAL; }
+    if (!stream_mode && ctx->traverse_top != 0 && launch_top(tree, flat, rays, R, counts, slots, K, tail, gate)) return BVHGPU_OK;
     if (ctx->walk_grid == 0) {
         int occ = 1;
         BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persistent_kernel<float, false, false>, 256, 0));

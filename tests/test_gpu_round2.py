@@ -499,3 +499,38 @@ def test_nearest_to_with_native_triangle_distance(api, prec):
         d2 = O.shape_distances_squared(shapes, pts[i], prec, kind=O.DIST_TRIANGLE, tris=tris)
         assert d2[gs[i]] == d2.min()
     bvh.free()
+
+
+@pytest.mark.parametrize("name", ["cubes1", "boxes21", "cubes1000", "cubes10000", "random5000", "points500", "huge300", "skew3000", "line200"])
+def test_shared_memory_top_tree_walk_is_bit_identical(api, name):
+    """Option traverse_top = 1 (walk_top_kernel: top records in shared memory) == the plain walk == the oracle, BVH and FLAT
+    modes, also after a refit (the top records follow the traversal records)."""
+    from bvh_b200 import capi
+
+    shapes = scene(name, "f32")
+    bvh = api.Bvh.build(shapes, prec="f32")
+    rays = rays_for(shapes, 20000, "f32", seed=5, axis_aligned=500)
+    ctx = bvh.ctx
+    try:
+        ctx.set_option("traverse_persistent", 1); ctx.set_option("traverse_stream", 0)
+        for round_ in range(2):
+            nodes = bvh.nodes
+            for mode, omode in ((capi.TRAVERSE_BVH, O.MODE_RECURSIVE), (capi.TRAVERSE_FLAT, O.MODE_FLAT)):
+                tree = nodes if omode == O.MODE_RECURSIVE else O.flatten(nodes, "f32")
+                r = O.traverse(tree, shapes, rays, omode, "f32")
+                visits = []
+                for top in (0, 1, 64, 500):                      # off, full budget, tiny budgets (64: skew3000 gets no top records at all)
+                    ctx.set_option("traverse_top", top)
+                    off, hits = bvh.traverse_batch(rays, mode=mode)
+                    visits.append(bvh.traverse_stats()[0])
+                    assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits), (mode, top, round_)
+                assert len(set(visits)) == 1, visits
+            if name == "huge300":
+                break
+            rng = np.random.default_rng(1)
+            dl = rng.uniform(-3, 3, (len(shapes), 3)).astype(np.float32)
+            shapes = shapes.copy(); shapes["min"] += dl; shapes["max"] += dl
+            bvh.refit(shapes)
+    finally:
+        ctx.set_option("traverse_top", -1); ctx.set_option("traverse_persistent", 2); ctx.set_option("traverse_stream", -1)
+        bvh.free()
