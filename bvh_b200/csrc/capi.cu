@@ -714,6 +714,7 @@ BVH_EXPORT int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t valu
     if (!strcmp(name, "traverse_persistent")) { ctx->traverse_persistent = value; return BVHGPU_OK; }
     if (!strcmp(name, "traverse_stream")) { ctx->traverse_stream = value; return BVHGPU_OK; }
     if (!strcmp(name, "traverse_top")) { ctx->traverse_top = value; return BVHGPU_OK; }
+    if (!strcmp(name, "walk_grid")) { ctx->walk_grid = value <= 0 ? 0 : (int)value; ctx->walk_grid_forced = value > 0; return BVHGPU_OK; }   // CTAs of the persistent walk (0 = one full wave)
     set_error("set_option: unknown option '%s'", name);
     return BVHGPU_ERR_INVALID;
 }

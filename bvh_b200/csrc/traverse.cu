@@ -312,12 +312,13 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
 // keeps the top records (flatten.cu: build_top_records) in shared memory; a lane walks them with two LDS.128 per visit and drops
 // to the global records (LDG.256, as above) only inside a fringe subtree.  Visit order and tests are exactly the preorder walk's,
 // so counts and hit lists are bit-identical.  Lane state: j = next top entry (also the resume point while g walks [g, gend)).
-template <bool FLAT>
+template <bool FLAT, bool STREAM>
 __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restrict__ trec, const DAabbF* __restrict__ aabb,
                                                            uint32_t n_rec, const float4* __restrict__ top,
-                                                           RaySrc<float> rays, uint32_t nrays, uint32_t* __restrict__ ticket,
+                                                           RaySrc<float> rays, uint32_t nrays, uint32_t* __restrict__ ticket, const uint32_t* ready,
                                                            uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
-                                                           unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if) {
+                                                           unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if,
+                                                           uint32_t* err, unsigned long long timeout_ns) {
     extern __shared__ float4 s_top[];
     if (gate && *gate != run_if) return;
     const uint32_t n_top = reinterpret_cast<const uint32_t*>(top)[0];      // header {n_top, C}, then lo[n_top], hi[n_top]
@@ -331,8 +332,9 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = lane_id(), lt = lanemask_lt();
     // Lane state: r ray, j next top entry (the resume point while below the top), [g, gend) global records left to walk in the
-    // current fringe subtree -- empty (gend = 0) while the lane is in the top.
+    // current fringe subtree -- empty (gend = 0) while the lane is in the top.  STREAM: `loaded` as in walk_persistent_kernel.
     uint32_t r = NONE, j = 0, g = 0, gend = 0, cnt = 0, visits = 0;
+    bool loaded = false;
     float o[3] = {0.f, 0.f, 0.f}, inv[3] = {0.f, 0.f, 0.f};
     bool exhausted = false;
     for (;;) {
@@ -344,12 +346,48 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
             if (base >= nrays) exhausted = true;
             const uint32_t mine = base + __popc(need & lt);
             // (no top records -- a degenerate tree whose first histogram bin already exceeds the budget: everything is "below")
-            if (r == NONE && mine < nrays) { r = mine; j = 0; cnt = 0; g = 0; gend = n_top ? 0u : n_rec; load_ray<float, false>(rays, mine, o, inv); }
+            if (r == NONE && mine < nrays) {
+                r = mine; j = 0; cnt = 0; g = 0; gend = n_top ? 0u : n_rec;
+                if (STREAM) loaded = false;
+                else load_ray<float, false>(rays, mine, o, inv);
+            }
+        }
+        if (STREAM) {                                                // see walk_persistent_kernel: pending lanes never block walking lanes
+            const uint32_t pend = __ballot_sync(FULL, r != NONE && !loaded);
+            if (pend) {
+                const bool any_active = __ballot_sync(FULL, r != NONE && loaded) != 0u;
+                const uint32_t lowest = __reduce_min_sync(FULL, (r != NONE && !loaded) ? r : NONE);
+                uint32_t rd = 0, ok = 1;
+                if (lane == 0) {
+                    rd = *(volatile const uint32_t*)ready;
+                    if (!any_active && rd <= lowest) {
+                        uint32_t ns = 100;
+                        const unsigned long long t0 = global_timer_ns();
+                        while (rd <= lowest) {
+                            if (*(volatile const uint32_t*)err != 0u) { ok = 0; break; }
+                            if (global_timer_ns() - t0 > timeout_ns) { ok = 0; atomicExch(err, (uint32_t)BVHGPU_ERR_TIMEOUT); break; }
+                            __nanosleep(ns);
+                            if (ns < 2000) ns <<= 1;
+                            rd = *(volatile const uint32_t*)ready;
+                        }
+                    }
+                }
+                rd = __shfl_sync(FULL, rd, 0);
+                ok = __shfl_sync(FULL, ok, 0);
+                if (!ok) {
+                    exhausted = true;
+                    if (r != NONE && !loaded) r = NONE;
+                } else if (__ballot_sync(FULL, r != NONE && !loaded && r < rd)) {
+                    __threadfence();
+                    if (r != NONE && !loaded && r < rd) { load_ray<float, true>(rays, r, o, inv); loaded = true; }
+                }
+            }
         }
         if (__ballot_sync(FULL, r != NONE) == 0) break;
         const int leave = exhausted ? 32 : REFILL;                   // idle lanes at which the warp goes back for tickets
+        uint32_t rounds = 0;
         for (;;) {
-            if (r != NONE) {
+            if (r != NONE && (!STREAM || loaded)) {
                 float mn[3], mx[3];
                 uint32_t w3, w7;
                 const bool below = g < gend;
@@ -383,7 +421,12 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
                 g = below ? nxt : (w7 & 0x7FFFFFFFu);
                 if (g >= gend && j >= n_top) { counts[r] = cnt; r = NONE; }
             }
-            if (__popc(__ballot_sync(FULL, r == NONE)) >= leave) break;
+            const uint32_t idle_mask = __ballot_sync(FULL, r == NONE);
+            if (__popc(idle_mask) >= leave) break;
+            if (STREAM) {                                            // look for arrivals every 16 visits, at once if nobody walks
+                const uint32_t pend = __ballot_sync(FULL, r != NONE && !loaded);
+                if (pend && (((++rounds) & 15u) == 0u || (pend | idle_mask) == FULL)) break;
+            }
         }
     }
     visits = __reduce_add_sync(FULL, visits);
@@ -849,9 +892,9 @@ constexpr uint32_t S_TOTAL = 0, S_VISITS = 1, S_XINFO = 2, S_ERR = 12, S_TICKET 
 constexpr unsigned long long STREAM_TIMEOUT_NS = 4ull * 1000ull * 1000ull * 1000ull;
 // The shared-memory top-tree walk: f32 trees only; false = not applicable (the caller launches the plain persistent kernel).
 constexpr uint32_t TOP_BUDGET = 7000;                               // entries: 224 000 B of the 227 KB a CTA may own
-template <class T> static bool launch_top(Tree<T>*, bool, RaySrc<T>, uint32_t, uint32_t*, uint32_t*, uint32_t, unsigned long long*, uint32_t*) { return false; }
+template <class T> static bool launch_top(Tree<T>*, bool, RaySrc<T>, uint32_t, uint32_t*, uint32_t*, uint32_t, unsigned long long*, uint32_t*, bool) { return false; }
 template <> bool launch_top<float>(Tree<float>* tree, bool flat, RaySrc<float> rays, uint32_t R, uint32_t* counts, uint32_t* slots, uint32_t K,
-                                   unsigned long long* tail, uint32_t* gate) {
+                                   unsigned long long* tail, uint32_t* gate, bool stream_mode) {
     bvhgpu_ctx* ctx = tree->ctx;
     if (tree->n < 2) return false;
     const uint32_t budget = ctx->traverse_top > 1 ? (uint32_t)std::min<int64_t>(std::max<int64_t>(ctx->traverse_top, 8), TOP_BUDGET) : TOP_BUDGET;
@@ -859,16 +902,22 @@ template <> bool launch_top<float>(Tree<float>* tree, bool flat, RaySrc<float> r
     static bool attr_set = false;
     if (!attr_set) {
         const int bytes = (int)(TOP_BUDGET * 32);
-        if (cudaFuncSetAttribute(walk_top_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
-            cudaFuncSetAttribute(walk_top_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaFuncSetAttribute(walk_top_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(walk_top_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(walk_top_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+            cudaFuncSetAttribute(walk_top_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
         attr_set = true;
     }
     const size_t smem = (size_t)budget * 32;                            // n_top <= budget lives on the device: reserve for the budget
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count, ((uint64_t)R + 1023) / 1024);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
+    uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);
     const float4* top = reinterpret_cast<const float4*>(tree->d_top);
-    if (flat) walk_top_kernel<true><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, counts, slots, K, tail + S_VISITS, gate, 0u);
-    else      walk_top_kernel<false><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, counts, slots, K, tail + S_VISITS, gate, 0u);
+#define BVH_TOP_LAUNCH(F, S, TMO) walk_top_kernel<F, S><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, ctx->d_ready, \
+                                                                                      counts, slots, K, tail + S_VISITS, gate, 0u, err, TMO)
+    if (stream_mode) { if (flat) BVH_TOP_LAUNCH(true, true, STREAM_TIMEOUT_NS); else BVH_TOP_LAUNCH(false, true, STREAM_TIMEOUT_NS); }
+    else             { if (flat) BVH_TOP_LAUNCH(true, false, 0ull); else BVH_TOP_LAUNCH(false, false, 0ull); }
+#undef BVH_TOP_LAUNCH
     ctx->launches++;
     return true;
 }
@@ -895,13 +944,20 @@ static int launch_pass1(Tree<T>* tree, bool flat, RaySrc<T> rays, uint32_t R, ui
         if (pmode == 0) return BVHGPU_OK;
     }
     if (first != 0 || count != R) { set_error("internal: persistent walk covers whole batches only"); return BVHGPU_ERR_INTERNAL; }
-    if (!stream_mode && ctx->traverse_top != 0 && launch_top(tree, flat, rays, R, counts, slots, K, tail, gate)) return BVHGPU_OK;
+    // Shared-memory top of the tree: measured +7..15 % from 240 k records (7.7 MB) upwards, -3 % on Sponza's 133 k records, whose
+    // global fetches still hit L1 well: automatic from 5 MB of records, forced by option traverse_top >= 1.
+    const bool want_top = ctx->traverse_top >= 1 || (ctx->traverse_top < 0 && (size_t)tree->n_trec * sizeof(typename Traits<T>::TNode) >= ((size_t)5 << 20));
+    if (want_top && launch_top(tree, flat, rays, R, counts, slots, K, tail, gate, stream_mode)) return BVHGPU_OK;
     if (ctx->walk_grid == 0) {
         int occ = 1;
         BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persistent_kernel<float, false, false>, 256, 0));
         ctx->walk_grid = ctx->sm_count * (occ < 1 ? 1 : occ);
     }
-    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->walk_grid, ((uint64_t)R + 255) / 256);
+    // A lane should see ~6 rays or more: with fewer, the last ray of every lane (the drain phase, where warps run half empty) is a
+    // large part of the kernel.  1 M rays: 5 CTAs per SM instead of 8 = -4 % kernel time; from 2.4 M rays on the full wave.
+    const uint64_t sms = (uint64_t)ctx->sm_count;
+    const uint64_t per_sm = std::min<uint64_t>((uint64_t)ctx->walk_grid / sms, std::max<uint64_t>(4, (uint64_t)R / (6ull * 256ull * sms)));
+    const int grid = (int)std::min<uint64_t>(ctx->walk_grid_forced ? (uint64_t)ctx->walk_grid : std::max<uint64_t>(1, per_sm) * sms, ((uint64_t)R + 255) / 256);
     uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
     const uint32_t* ready = ctx->d_ready;                    // only read by the streamed form
     uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);

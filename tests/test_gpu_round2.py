@@ -534,3 +534,28 @@ def test_shared_memory_top_tree_walk_is_bit_identical(api, name):
     finally:
         ctx.set_option("traverse_top", -1); ctx.set_option("traverse_persistent", 2); ctx.set_option("traverse_stream", -1)
         bvh.free()
+
+
+@pytest.mark.parametrize("mode_name", ["bvh", "flat"])
+def test_streamed_host_path_with_the_shared_memory_top(api, mode_name):
+    """The host-pointer path streams the rays into the running walk_top_kernel<.., STREAM> (forced: traverse_stream = 1,
+    traverse_top = 1): same CSR as the oracle; the metric says the call was streamed."""
+    from bvh_b200 import capi
+
+    shapes = O.create_n_cubes(3000)
+    want = O.build(shapes)
+    rays, _ = O.create_rays(400_000)
+    mode, omode = (capi.TRAVERSE_BVH, O.MODE_RECURSIVE) if mode_name == "bvh" else (capi.TRAVERSE_FLAT, O.MODE_FLAT)
+    tree = want.nodes if omode == O.MODE_RECURSIVE else O.flatten(want.nodes)
+    r = O.traverse(tree, shapes, rays, omode, threads=O.hardware_threads())
+    bvh = api.Bvh.build(shapes)
+    ctx = bvh.ctx
+    try:
+        ctx.set_option("traverse_top", 1); ctx.set_option("traverse_stream", 1)
+        for compact in (False, True):
+            off, hits = bvh.traverse_batch(rays, mode=mode, compact=compact)
+            assert ctx.get_metric("host_streamed") == 1.0
+            assert np.array_equal(off.astype(np.uint64), r.offsets) and np.array_equal(hits, r.hits), compact
+    finally:
+        ctx.set_option("traverse_top", -1); ctx.set_option("traverse_stream", -1)
+        bvh.free()
