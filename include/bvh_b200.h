@@ -128,6 +128,9 @@ uint64_t bvhgpu_launch_count(const bvhgpu_ctx* ctx);
  * -- every combination produces the same bits; the switches exist for measurement (tools/build_sweep.py) --
  * "traverse_stream" (host-pointer traversal: consume the rays in a running kernel while the copy is still in flight;
  *   -1 auto = only when launches are asynchronous and no profiler / debugger / sanitizer is attached, 0 never, 1 force),
+ * "traverse_top" (f32 persistent walk with the top of the tree in shared memory: -1 auto = trees with >= 5 MB of traversal records,
+ *   0 never, 1 always, > 1 = always with at most that many top entries; the results are the same bits either way),
+ * "walk_grid" (CTAs of the plain persistent walk; 0 = automatic: 4..8 per SM by batch size),
  * "profile" (1: bracket the dominant kernels with CUDA events, read back with bvhgpu_get_metric). */
 int bvhgpu_set_option(bvhgpu_ctx* ctx, const char* name, int64_t value);
 /* Measurements of the last profiled call on this context: "walk_ms" (traversal walk kernel),
