@@ -46,6 +46,7 @@ struct bvhgpu_ctx {
     int64_t traverse_persistent = 2;   // 0: one ray per thread, 1: persistent refill kernel, 2: coherence probe decides on the device
     int walk_grid = 0;             // persistent grid size: one full wave (computed once), or the value of option "walk_grid"
     bool walk_grid_forced = false;
+    bool top_attr_set = false;     // walk_top_kernel's dynamic shared memory limit has been raised on this device
     int64_t build_gang = -1;       // exact builder: co-resident warp gangs for the top levels (-1 / 1 on, 0 off = queue tiles only)
     int64_t build_subtree = -1;    // exact builder: in-register subtrees for ranges <= 32 shapes (-1 auto, 0 never, 1 always)
     int64_t build_small = -1;      // exact builder: defer ranges <= 16 shapes to the thread-per-range kernel (-1 auto by size, 0 never, 1 always)

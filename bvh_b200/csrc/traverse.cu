@@ -899,14 +899,13 @@ template <> bool launch_top<float>(Tree<float>* tree, bool flat, RaySrc<float> r
     if (tree->n < 2) return false;
     const uint32_t budget = ctx->traverse_top > 1 ? (uint32_t)std::min<int64_t>(std::max<int64_t>(ctx->traverse_top, 8), TOP_BUDGET) : TOP_BUDGET;
     if ((!tree->top_valid || tree->top_budget != budget) && build_top_records(tree, budget) != BVHGPU_OK) return false;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->top_attr_set) {                                           // a per-device function attribute: once per context
         const int bytes = (int)(TOP_BUDGET * 32);
         if (cudaFuncSetAttribute(walk_top_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
             cudaFuncSetAttribute(walk_top_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
             cudaFuncSetAttribute(walk_top_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
             cudaFuncSetAttribute(walk_top_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
-        attr_set = true;
+        ctx->top_attr_set = true;
     }
     const size_t smem = (size_t)budget * 32;                            // n_top <= budget lives on the device: reserve for the budget
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count, ((uint64_t)R + 1023) / 1024);
