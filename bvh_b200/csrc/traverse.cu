@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
                                                            RaySrc<float> rays, uint32_t nrays, uint32_t* __restrict__ ticket, const uint32_t* ready,
                                                            uint32_t* __restrict__ counts, uint32_t* __restrict__ slots, uint32_t K,
                                                            unsigned long long* __restrict__ visit_total, const uint32_t* __restrict__ gate, uint32_t run_if,
-                                                           uint32_t* err, unsigned long long timeout_ns) {
+                                                           uint32_t* err, unsigned long long timeout_ns, int refill) {
     extern __shared__ float4 s_top[];
     if (gate && *gate != run_if) return;
     const uint32_t n_top = reinterpret_cast<const uint32_t*>(top)[0];      // header {n_top, C}, then lo[n_top], hi[n_top]
@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
     asm volatile("mov.u32 %0, %1;" : "=r"(s_lo) : "r"((uint32_t)__cvta_generic_to_shared(s_top)));
     const uint32_t s_hi = s_lo + 16u * n_top;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    constexpr int REFILL = 8;
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = lane_id(), lt = lanemask_lt();
     // Lane state: r ray, j next top entry (the resume point while below the top), [g, gend) global records left to walk in the
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(1024, 1) walk_top_kernel(const TNodeF* __restr
             }
         }
         if (__ballot_sync(FULL, r != NONE) == 0) break;
-        const int leave = exhausted ? 32 : REFILL;                   // idle lanes at which the warp goes back for tickets
+        const int leave = exhausted ? 32 : refill;                   // idle lanes at which the warp goes back for tickets
         uint32_t rounds = 0;
         for (;;) {
             if (r != NONE && (!STREAM || loaded)) {
@@ -912,8 +911,9 @@ template <> bool launch_top<float>(Tree<float>* tree, bool flat, RaySrc<float> r
     uint32_t* ticket = reinterpret_cast<uint32_t*>(tail + S_TICKET);
     uint32_t* err = reinterpret_cast<uint32_t*>(tail + S_ERR);
     const float4* top = reinterpret_cast<const float4*>(tree->d_top);
+    static const int top_refill = getenv("BVHGPU_TOP_REFILL") ? std::max(1, std::min(32, atoi(getenv("BVHGPU_TOP_REFILL")))) : 8;   // dev knob: idle lanes per refill
 #define BVH_TOP_LAUNCH(F, S, TMO) walk_top_kernel<F, S><<<grid, 1024, smem, ctx->stream>>>(tree->d_tnodes, walk_aabbs(tree), tree->n_trec, top, rays, R, ticket, ctx->d_ready, \
-                                                                                      counts, slots, K, tail + S_VISITS, gate, 0u, err, TMO)
+                                                                                      counts, slots, K, tail + S_VISITS, gate, 0u, err, TMO, top_refill)
     if (stream_mode) { if (flat) BVH_TOP_LAUNCH(true, true, STREAM_TIMEOUT_NS); else BVH_TOP_LAUNCH(false, true, STREAM_TIMEOUT_NS); }
     else             { if (flat) BVH_TOP_LAUNCH(true, false, 0ull); else BVH_TOP_LAUNCH(false, false, 0ull); }
 #undef BVH_TOP_LAUNCH
@@ -1193,7 +1193,9 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
     dst.offsets = tree->d_offsets; dst.hits = tree->d_hits; dst.nrays_out = R;
     const PeerBoxes nopeers{};
     uint32_t* arrival = reinterpret_cast<uint32_t*>(tail + S_BLKDONE);
-    const uint32_t nchunks = std::max<uint32_t>(1, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 120000));     // ~8 chunks per million rays
+    static const int force_chunks = getenv("BVHGPU_CHUNKS") ? atoi(getenv("BVHGPU_CHUNKS")) : 0;           // dev knob
+    const uint32_t nchunks = force_chunks > 0 ? std::min<uint32_t>(BVH_MAX_CHUNKS, (uint32_t)force_chunks)
+                                              : (R < 240000u ? 1u : std::max<uint32_t>(2, std::min<uint32_t>(BVH_MAX_CHUNKS, R / 250000)));   // 4 chunks per million rays
     const bool streaming = nchunks > 1 && stream_capable(ctx) == 1;
     ctx->last_streamed = streaming ? 1 : 0;
     stamp(0);                                                     // scratch allocated
@@ -1206,8 +1208,18 @@ int traverse_host_pipelined(Tree<T>* tree, int mode, const void* h_rays, uint32_
         uint32_t* h_ready = ctx->h_pinned + 64;                  // pinned: one value per chunk, alive until the final sync
         uint32_t* d_ready = ctx->d_ready;                        // plain cudaMalloc memory: the stream memory operation refuses pool memory
         ctx->wv_ok = 1;
+        static const int sched = getenv("BVHGPU_CHUNK_SCHEDULE") ? atoi(getenv("BVHGPU_CHUNK_SCHEDULE")) : 1;     // dev knob
+        // Schedule 1 (default): the first half of the chunks carries two thirds of the rays.  Every chunk costs ~9 us of copy-engine
+        // latency (copy + counter update), and the call ends one longest-ray latency (~0.15 ms) behind the LAST chunk whatever its
+        // size: few, large copies early and small ones at the end (1 M rays, tools/e2e_probe.py: 8 equal chunks 0.806 ms, 4 chunks
+        // 333 k / 333 k / 167 k / 167 k 0.764 ms).
+        const uint32_t nhalf = nchunks / 2, units = sched == 1 ? nchunks + nhalf : nchunks;
+        auto bound = [&](uint32_t c) -> uint32_t {
+            const uint32_t u = sched == 1 ? (c <= nhalf ? 2 * c : nhalf + c) : c;
+            return (uint32_t)((uint64_t)R * u / units);
+        };
         for (uint32_t c = 0; c < nchunks; ++c) {
-            const uint32_t lo = (uint32_t)((uint64_t)R * c / nchunks), hi = (uint32_t)((uint64_t)R * (c + 1) / nchunks);
+            const uint32_t lo = bound(c), hi = bound(c + 1);
             cudaError_t e = cudaMemcpyAsync(staged + ray_bytes * lo, (const unsigned char*)h_rays + ray_bytes * lo, ray_bytes * (hi - lo), cudaMemcpyHostToDevice, ctx->copy_stream);
             h_ready[c] = hi;
             if (e == cudaSuccess) {
