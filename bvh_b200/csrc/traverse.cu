@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) walk_persistent_kernel(const typename Tra
     if (lane == 0 && visits) atomicAdd(visit_total, (unsigned long long)visits);
 }
 
-// Shared-memory top-of-tree variant of the persistent walk (f32, opt-in: option traverse_top).  Every CTA (one per SM, 1024 threads)
+// Shared-memory top-of-tree variant of the persistent walk (f32; automatic from 5 MB of records, option traverse_top; STREAM as
+// above).  Every CTA (one per SM, 1024 threads)
 // keeps the top records (flatten.cu: build_top_records) in shared memory; a lane walks them with two LDS.128 per visit and drops
 // to the global records (LDG.256, as above) only inside a fringe subtree.  Visit order and tests are exactly the preorder walk's,
 // so counts and hit lists are bit-identical.  Lane state: j = next top entry (also the resume point while g walks [g, gend)).
