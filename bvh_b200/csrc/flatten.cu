@@ -121,14 +121,26 @@ __global__ void __launch_bounds__(256) top_hist_kernel(const bvh_node3f* __restr
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
 }
-__global__ void top_choose_kernel(const uint32_t* __restrict__ hist, uint32_t budget, uint32_t* __restrict__ hdr) {
-    if (threadIdx.x) return;
-    uint32_t total = 0;
-    int b = TOP_BINS - 1;
-    for (; b >= 0; --b) { if (total + hist[b] > budget) break; total += hist[b]; }
-    // the smallest count that falls into an included bin (bins b+1 ..): ceil((8 + sub) * 2^k / 8)
+__global__ void __launch_bounds__(32) top_choose_kernel(const uint32_t* __restrict__ hist, uint32_t budget, uint32_t* __restrict__ hdr) {
+    // One warp, 8 bins per lane.  Bins are taken from the highest down while their running sum S(b) = sum of hist[b..] fits the budget;
+    // S grows as b falls, so the bins taken are a suffix of the bin range: count them, and the last one's S is the number of entries.
+    const uint32_t l = threadIdx.x & 31u, FULL = 0xffffffffu;
+    uint32_t h[8], t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { h[k] = hist[8 * l + k]; t += h[k]; }
+    uint32_t incl = t;                                                 // this lane's bins and all higher lanes'
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_down_sync(FULL, incl, o); if (l + o < 32) incl += v; }
+    uint32_t run = incl - t, taken = 0, total = 0;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) { run += h[k]; if (run <= budget) { ++taken; total = run; } }
+    taken = __reduce_add_sync(FULL, taken);
+    total = __reduce_max_sync(FULL, total);
+    if (l) return;
+    // the smallest count that falls into a taken bin (bins nb ..): ceil((8 + sub) * 2^k / 8); everything taken: C = 2
     uint32_t C = 2;
-    if (b >= 0) { const uint32_t nb = (uint32_t)b + 1, k = nb >> 3, sub = nb & 7u; C = (uint32_t)((((unsigned long long)(8 + sub) << k) + 7ull) >> 3); }
+    if (taken == 0) C = 0xFFFFFFFFu;                                   // not even the highest bin fits: no node qualifies, n_top = 0 (the walk then stays below)
+    else if (taken < TOP_BINS) { const uint32_t nb = TOP_BINS - taken, k = nb >> 3, sub = nb & 7u; C = (uint32_t)((((unsigned long long)(8 + sub) << k) + 7ull) >> 3); }
     hdr[0] = total; hdr[1] = C; hdr[2] = 0; hdr[3] = 0;
 }
 __global__ void __launch_bounds__(256) top_flag_kernel(const bvh_node3f* __restrict__ nodes, uint32_t n_nodes, const uint32_t* __restrict__ hdr, uint32_t* __restrict__ flags) {
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(256) top_emit_kernel(const bvh_node3f* __restr
     float4* lo = top + 2;
     float4* hi = lo + n_top;
     const uint32_t k = pre[i];
+    if (k >= n_top) return;                                             // (cannot happen: the flags are derived from the same C)
     const uint4 meta = *reinterpret_cast<const uint4*>(nodes + i);
     const bool leaf = meta.y == BVH_INVALID;
     const uint32_t cnt = leaf ? 1u : meta.w;
