@@ -61,3 +61,35 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").lower() or f == "build.py", (dirpath, f)
+
+
+def test_python_mirror_of_the_shard_macros_matches_the_header():
+    """bvh_b200/capi.py restates BVHGPU_MAX_PEERS / BVHGPU_MAILBOX_BYTES / BVHGPU_SHARD_STAGE_BYTES and the struct bvhgpu_shard:
+    compile the header's own macros with gcc and compare (a drift here would make ranks disagree about the staging layout)."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+
+    from bvh_b200 import capi
+
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "bvh_b200.h"
+int main(void) {
+    printf("%d %d %zu %zu", BVHGPU_MAX_PEERS, BVHGPU_MAILBOX_BYTES, sizeof(bvhgpu_shard), offsetof(bvhgpu_shard, shard_rays));
+    size_t n[] = {0, 1, 2047, 2048, 1000000, 8000000, 16000000, 2147483647};
+    for (int i = 0; i < 8; ++i) printf(" %zu", (size_t)BVHGPU_SHARD_STAGE_BYTES(n[i]));
+    return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c, exe = os.path.join(d, "m.c"), os.path.join(d, "m")
+        open(c, "w").write(src)
+        subprocess.run(["gcc", "-std=c11", "-I", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    vals = [int(x) for x in out]
+    assert vals[0] == capi.MAX_PEERS and vals[1] == capi.MAILBOX_BYTES
+    assert vals[2] == C.sizeof(capi.Shard) and vals[3] == capi.Shard.shard_rays.offset
+    for n, want in zip((0, 1, 2047, 2048, 1000000, 8000000, 16000000, 2147483647), vals[4:]):
+        assert capi.shard_stage_bytes(n) == want, n
